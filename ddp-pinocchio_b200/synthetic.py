@@ -1,0 +1,110 @@
+"""Deterministic synthetic DDP problem batches.
+
+Counter-based splitmix64 streams, seed 0xDD9 + problem_id, generated once on the host and
+shared by the GPU path and the CPU oracle.  Replaces the reference's unseeded
+`eq.jac().setRandom()` (/root/reference/include/ddp/ddp.hpp:762) by an explicit input.
+"""
+from dataclasses import dataclass
+import numpy as np
+from . import models
+
+EQ_NONE, EQ_CONFIG, EQ_SPATIAL = 0, 1, 2
+HESS_FD_JACOBIANS, HESS_FD_VALUES = 0, 1   # dynamics_t::second_order_finite_diff = false / true
+FJ_WORLD, FJ_LOCAL_WORLD_ALIGNED = 0, 1
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(seed, count):
+    """`count` uniform doubles in [0,1) from stream `seed` (vectorised over a seed array)."""
+    seed = np.atleast_1d(np.asarray(seed, dtype=np.uint64))
+    idx = np.arange(1, count + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = seed[:, None] + idx[None, :] * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+@dataclass
+class Workload:
+    name: str
+    model: models.ModelDesc
+    B: int
+    T: int
+    dt: float = 0.01
+    c: float = 1.0
+    hess_mode: int = HESS_FD_JACOBIANS
+    eq_kind: int = EQ_CONFIG
+    eq_every_knot: bool = False   # False: terminal constraint only (rows at knot T-2, test/pendulum_ddp.cpp:37-47)
+    frame: int = 0
+    jac_mode: int = FJ_WORLD
+    # double-precision solver parameters (the reference's mu=1e20 / thr=1e-80 are MPFR-only)
+    mu: float = 1e4
+    reg: float = 0.0
+    iterations: int = 10
+
+    @property
+    def n(self):
+        return self.model.nq
+
+    @property
+    def nx(self):
+        return 2 * self.n
+
+    ndx = nx
+
+    @property
+    def nu(self):
+        return self.n
+
+    def ne_per_knot(self):
+        ne_rows = 3 if self.eq_kind == EQ_SPATIAL else (self.n if self.eq_kind == EQ_CONFIG else 0)
+        ne = np.zeros(self.T, dtype=np.int32)
+        if self.eq_kind != EQ_NONE:
+            if self.eq_every_knot:
+                ne[:] = ne_rows
+            else:
+                ne[self.T - 2] = ne_rows
+        return ne
+
+    def generate(self, B=None, first_problem=0):
+        """x0 [B,nx], us [B,T,nu] (zero controls), targets [B,sum ne], mult_jac [B, sum ne*ndx]."""
+        B = self.B if B is None else B
+        n, T = self.n, self.T
+        ne = self.ne_per_knot()
+        net = int(ne.sum())
+        cnt = 2 * n + net + net * self.ndx + 3
+        r = splitmix64(np.uint64(0xDD9) + np.arange(first_problem, first_problem + B, dtype=np.uint64), cnt)
+        q0 = (r[:, :n] - 0.5) * np.pi
+        v0 = r[:, n:2 * n] - 0.5
+        x0 = np.concatenate([q0, v0], axis=1)
+        tg = 2.0 * r[:, 2 * n:2 * n + net] - 1.0
+        if self.eq_kind == EQ_SPATIAL:
+            tg = 0.3 * tg  # reachable end-effector targets around the origin
+        mj = 2.0 * r[:, 2 * n + net:2 * n + net + net * self.ndx] - 1.0
+        us = np.zeros((B, T, self.nu))
+        return dict(x0=np.ascontiguousarray(x0), us=us, targets=np.ascontiguousarray(tg), mult_jac=np.ascontiguousarray(mj), ne=ne)
+
+
+def workload(name, B=None, T=None):
+    """The five BASELINE.json configs (C1..C5) by short name."""
+    if name == "c1":   # pendulum DDP, single problem (test/pendulum_ddp.cpp)
+        w = Workload("c1_pendulum", models.pendulum(), 1, 200, hess_mode=HESS_FD_VALUES)
+    elif name == "c2":  # synthetic 2R "double pendulum", 4096 x 200
+        w = Workload("c2_chain2r_4096x200", models.chain_2r(), 4096, 200)
+    elif name == "c3":  # 6R UR5-style arm, 1024 x 100, analytic first order + FD-of-Jacobians Hessians
+        w = Workload("c3_arm6r_1024x100", models.arm_6r(), 1024, 100)
+    elif name == "c4":  # same arm, spatial end-effector equality constraint
+        m = models.arm_6r()
+        w = Workload("c4_arm6r_spatial_1024x100", m, 1024, 100, eq_kind=EQ_SPATIAL, frame=m.n_frames - 1)
+    elif name == "c5":  # 7R arm, value-based finite-difference Hessians, 8192 x 200 over 8 GPUs
+        w = Workload("c5_arm7r_fd_8192x200", models.arm_7r(), 8192, 200, hess_mode=HESS_FD_VALUES)
+    else:
+        raise ValueError(name)
+    if B is not None:
+        w.B = B
+    if T is not None:
+        w.T = T
+    return w
