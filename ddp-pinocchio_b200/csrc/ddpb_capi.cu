@@ -1,0 +1,638 @@
+// ddpb_capi.cu -- kernels and the extern "C" layer declared in include/ddpb.h.
+// Built for sm_100a only (see __graft_entry__.build()); there is no CPU fallback: every entry point
+// that needs the device returns DDPB_ERR_CUDA when none is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ddpb.h"
+#include "forward.cuh"
+#include "launch.cuh"
+#include "model_host.hpp"
+
+using namespace ddpb;
+
+static_assert((int)NSCALARS == (int)DDPB_NSCALARS, "scalar table mismatch");
+static_assert(sizeof(ModelDev) < 3500, "model must fit the kernel parameter space");
+
+// -------------------------------------------------------------------------------------------------
+// kernels
+// -------------------------------------------------------------------------------------------------
+__global__ void post_forward_kernel(const __grid_constant__ BatchDev bd) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bd.B) return;
+  post_forward_problem(bd, b);
+}
+__global__ void scalar_copy_kernel(double* scal, int B, int dst, int src) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) scal[(size_t)dst * B + b] = scal[(size_t)src * B + b];
+}
+__global__ void fill_kernel(double* p, size_t n, double v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// dst[c * R + r] = src[r * C + c]   (host layout [R = problems][C] <-> SoA-by-batch [C][R])
+__global__ void transpose_kernel(double* __restrict__ dst, const double* __restrict__ src, int R, int C) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[i][threadIdx.x] = src[(size_t)r * C + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[(size_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+// copy x of the current trajectory into an origin sequence: dst[T][nx][B] <- xs[T+1][nx][B] (first T knots)
+__global__ void copy_kernel(double* dst, const double* src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+// packed host sequence of one derivative field <-> slab records.  per_row: doubles per equality row
+// (eq fields, ragged) or 0 for fields with a fixed per-knot size `per_knot`.
+__global__ void slab_field_kernel(const __grid_constant__ BatchDev bd, double* packed, size_t field_total, int field, int per_knot,
+                                  int per_row, int to_slab) {
+  const int nd = bd.nx, nu = bd.nu, nx = bd.nx;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < field_total * bd.B; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / field_total);
+    const size_t pos = i % field_total;
+    int t, e;
+    if (per_row == 0) {
+      t = (int)(pos / per_knot); e = (int)(pos % per_knot);
+    } else {
+      int lo = 0, hi = bd.T;  // largest t with eq_off[t] * per_row <= pos
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) / 2;
+        if ((size_t)bd.eq_off[mid] * per_row <= pos) lo = mid; else hi = mid;
+      }
+      t = lo; e = (int)(pos - (size_t)bd.eq_off[t] * per_row);
+    }
+    const RecLayout L = rec_layout(nd, nu, nx, bd.ne[t]);
+    const int offs[17] = {L.lx, L.lu, L.lxx, L.lux, L.luu, L.f, L.fx, L.fu, L.fxx, L.fux, L.fuu, L.eq, L.eq_x, L.eq_u, L.eq_xx, L.eq_ux, L.eq_uu};
+    double* r = slab_rec(bd, t, b, L.size) + offs[field] + e;
+    if (to_slab) *r = packed[i]; else packed[i] = *r;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(DDPB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct ddpb_model {
+  ModelDev dev;
+  int nq;
+};
+
+struct PhaseEv { cudaEvent_t a, b; int phase; };
+
+struct ddpb_batch {
+  ModelDev model;
+  BatchDev bd;
+  int device = 0;
+  int mt = 0;        // model tag for thread-per-problem kernels: 0 = pendulum, else number of joints
+  int nj = 1;        // joints (1 for the pendulum)
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<int> ne, eq_off;
+  std::vector<long long> slab_off;
+  std::vector<void*> allocs;
+  double* costs_old = nullptr;
+  double* stage = nullptr;
+  size_t stage_bytes = 0;
+  double* h_stage = nullptr;  // pinned bounce buffer for small scalar traffic
+  unsigned long long launches = 0;
+  bool timing = false;
+  std::vector<PhaseEv> events;
+  float phase_ms[4] = {0, 0, 0, 0};
+  size_t lin_smem = 0;
+  int lin_threads = 128, bwd_threads = 128;
+  size_t bwd_smem = 0;
+};
+
+template <class T> static int dev_alloc(ddpb_batch* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(DDPB_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return DDPB_OK;
+}
+static int ensure_stage(ddpb_batch* h, size_t bytes) {
+  if (bytes <= h->stage_bytes) return DDPB_OK;
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr; h->stage_bytes = 0;
+  cudaError_t e = cudaMalloc((void**)&h->stage, bytes);
+  if (e != cudaSuccess) return fail(DDPB_ERR_NOMEM, std::string("cudaMalloc(stage): ") + cudaGetErrorString(e));
+  h->stage_bytes = bytes;
+  return DDPB_OK;
+}
+
+struct PhaseScope {
+  ddpb_batch* h; int idx = -1;
+  PhaseScope(ddpb_batch* hh, int phase) : h(hh) {
+    if (!h->timing) return;
+    PhaseEv ev; ev.phase = phase;
+    cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+    cudaEventRecord(ev.a, h->stream);
+    h->events.push_back(ev); idx = (int)h->events.size() - 1;
+  }
+  ~PhaseScope() { if (idx >= 0) cudaEventRecord(h->events[idx].b, h->stream); }
+};
+
+// run STMT with L = Launch<k> for the model tag k (0 = pendulum, 1..7 = joints)
+#define DISPATCH(tag, STMT)                                     \
+  switch (tag) {                                                \
+    case 0: { using L = Launch<0>; STMT; } break;               \
+    case 1: { using L = Launch<1>; STMT; } break;               \
+    case 2: { using L = Launch<2>; STMT; } break;               \
+    case 3: { using L = Launch<3>; STMT; } break;               \
+    case 4: { using L = Launch<4>; STMT; } break;               \
+    case 5: { using L = Launch<5>; STMT; } break;               \
+    case 6: { using L = Launch<6>; STMT; } break;               \
+    case 7: { using L = Launch<7>; STMT; } break;               \
+    default: return fail(DDPB_ERR_UNSUPPORTED, "n_joints must be 1..7"); \
+  }
+
+static int check_launch(ddpb_batch* h, const char* what) {
+  ++h->launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DDPB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return DDPB_OK;
+}
+
+static int launch_linearize(ddpb_batch* h) {
+  PhaseScope ps(h, 0);
+  DISPATCH(h->mt, L::linearize(h->model, h->bd, h->lin_threads, h->lin_smem, h->stream));
+  return check_launch(h, "linearize");
+}
+static int launch_backward(ddpb_batch* h) {
+  PhaseScope ps(h, 1);
+  DISPATCH(h->nj, L::backward(h->bd, h->bwd_threads, h->bwd_smem, h->stream));
+  return check_launch(h, "backward");
+}
+static int launch_forward(ddpb_batch* h) {
+  PhaseScope ps(h, 2);
+  DISPATCH(h->mt, L::forward(h->model, h->bd, h->costs_old, h->stream));
+  return check_launch(h, "forward");
+}
+static int launch_al_update(ddpb_batch* h, double thr) {
+  PhaseScope ps(h, 3);
+  DISPATCH(h->mt, L::al_update(h->bd, thr, h->stream));
+  return check_launch(h, "al_update");
+}
+static int launch_simple(ddpb_batch* h, int which) {  // 0 post_forward
+  PhaseScope ps(h, 3);
+  const int th = 128;
+  if (which == 0) post_forward_kernel<<<(h->bd.B + th - 1) / th, th, 0, h->stream>>>(h->bd);
+  return check_launch(h, "post_forward");
+}
+static int scalar_copy(ddpb_batch* h, int dst, int src) {
+  scalar_copy_kernel<<<(h->bd.B + 127) / 128, 128, 0, h->stream>>>(h->bd.scal, h->bd.B, dst, src);
+  return check_launch(h, "scalar_copy");
+}
+static int fill(ddpb_batch* h, double* p, size_t n, double v) {
+  if (n == 0) return DDPB_OK;
+  fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, h->stream>>>(p, n, v);
+  return check_launch(h, "fill");
+}
+static int dcopy(ddpb_batch* h, double* dst, const double* src, size_t n) {
+  if (n == 0) return DDPB_OK;
+  copy_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, h->stream>>>(dst, src, n);
+  return check_launch(h, "copy");
+}
+// host [B][C] -> device [C][B]
+static int upload_T(ddpb_batch* h, double* dev, const double* host, size_t C) {
+  if (C == 0) return DDPB_OK;
+  const int B = h->bd.B;
+  int rc = ensure_stage(h, (size_t)B * C * sizeof(double));
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->stage, host, (size_t)B * C * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((B + 31) / 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, h->stream>>>(dev, h->stage, B, (int)C);
+  return check_launch(h, "transpose_in");
+}
+// device [C][B] -> host [B][C]
+static int download_T(ddpb_batch* h, double* host, const double* dev, size_t C) {
+  if (C == 0) return DDPB_OK;
+  const int B = h->bd.B;
+  int rc = ensure_stage(h, (size_t)B * C * sizeof(double));
+  if (rc) return rc;
+  dim3 grid((unsigned)((B + 31) / 32), (unsigned)((C + 31) / 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, h->stream>>>(h->stage, dev, (int)C, B);
+  rc = check_launch(h, "transpose_out");
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(host, h->stage, (size_t)B * C * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+
+extern "C" {
+
+const char* ddpb_last_error(void) { return g_err.c_str(); }
+
+int ddpb_model_create(const ddpb_model_desc* d, ddpb_model** out) {
+  if (!d || !out) return fail(DDPB_ERR_INVALID, "null argument");
+  ddpb_model* m = new ddpb_model();
+  std::string err;
+  const int rc = model_from_desc(d, m->dev, err);
+  if (rc) { delete m; return fail(rc, err); }
+  m->nq = m->dev.n;
+  *out = m;
+  return DDPB_OK;
+}
+void ddpb_model_destroy(ddpb_model* m) { delete m; }
+
+int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot, const ddpb_params* p, int device, ddpb_batch** out) {
+  if (!m || !p || !out || B < 1 || T < 1) return fail(DDPB_ERR_INVALID, "bad arguments");
+  if (p->hess_mode != DDPB_HESS_FD_JACOBIANS && p->hess_mode != DDPB_HESS_FD_VALUES) return fail(DDPB_ERR_INVALID, "bad hess_mode");
+  if (p->eq_kind < 0 || p->eq_kind > 2) return fail(DDPB_ERR_INVALID, "bad eq_kind");
+  const int n = m->nq;
+  if (p->eq_kind == DDPB_EQ_SPATIAL && (m->dev.kind == DDPB_MODEL_PENDULUM || p->frame_id < 0 || p->frame_id >= m->dev.nframes))
+    return fail(DDPB_ERR_INVALID, "frame index must be in bounds");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(DDPB_ERR_CUDA, "no CUDA device available (there is no CPU fallback)"); }
+  if (device < 0 || device >= ndev) return fail(DDPB_ERR_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(DDPB_ERR_CUDA, "this library is built for sm_100a (B200) only");
+  ddpb_batch* h = new ddpb_batch();
+  h->model = m->dev;
+  h->device = device;
+  h->mt = m->dev.kind == DDPB_MODEL_PENDULUM ? 0 : n;
+  h->nj = n;
+  BatchDev& bd = h->bd;
+  std::memset(&bd, 0, sizeof(bd));
+  bd.B = B; bd.T = T; bd.n = n; bd.nx = 2 * n; bd.nu = n;
+  bd.hess_mode = p->hess_mode; bd.eq_kind = p->eq_kind; bd.frame_id = p->frame_id; bd.jac_mode = p->frame_jac_mode;
+  bd.dt = p->dt; bd.c = p->c;
+  h->ne.assign(T, 0); h->eq_off.assign(T + 1, 0); h->slab_off.assign(T + 1, 0);
+  const int row_cap = p->eq_kind == DDPB_EQ_SPATIAL ? 3 : n;
+  for (int t = 0; t < T; ++t) {
+    const int ne = (p->eq_kind == DDPB_EQ_NONE || !ne_per_knot) ? 0 : ne_per_knot[t];
+    if (ne < 0 || ne > row_cap || (p->eq_kind == DDPB_EQ_SPATIAL && ne != 0 && ne != 3)) { delete h; return fail(DDPB_ERR_INVALID, "bad equality row count"); }
+    h->ne[t] = ne;
+    h->eq_off[t + 1] = h->eq_off[t] + ne;
+    bd.ne_max = std::max(bd.ne_max, ne);
+    h->slab_off[t + 1] = h->slab_off[t] + rec_layout(2 * n, n, 2 * n, ne).size;
+  }
+  bd.ne_total = h->eq_off[T];
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  const size_t nx = bd.nx, nu = bd.nu, nd = bd.nx, net = bd.ne_total;
+  int rc = 0;
+  int *d_ne = nullptr, *d_eo = nullptr;
+  long long* d_so = nullptr;
+#define A(ptr, count) if (!rc) rc = dev_alloc(h, &(ptr), (size_t)(count))
+  A(bd.xs, (T + 1) * nx * B); A(bd.us, T * nu * B); A(bd.xs_new, (T + 1) * nx * B); A(bd.us_new, T * nu * B);
+  A(bd.targets, net * B); A(bd.m_origin, T * nx * B); A(bd.m_val, net * B); A(bd.m_jac, net * nd * B);
+  A(bd.fb_origin, T * nx * B); A(bd.fb_k, T * nu * B); A(bd.fb_K, T * nu * nd * B);
+  A(bd.slab, (size_t)h->slab_off[T] * B); A(bd.scal, (size_t)NSCALARS * B); A(h->costs_old, (size_t)(T + 1) * B);
+  A(d_ne, T); A(d_eo, T + 1); A(d_so, T + 1);
+#undef A
+  if (rc) { ddpb_batch_destroy(h); return rc; }
+  bd.ne = d_ne; bd.eq_off = d_eo; bd.slab_off = d_so;
+  CU(cudaMemcpy(d_ne, h->ne.data(), T * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_eo, h->eq_off.data(), (T + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_so, h->slab_off.data(), (T + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+  CU(cudaMemsetAsync(bd.scal, 0, (size_t)NSCALARS * B * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(bd.slab, 0, (size_t)h->slab_off[T] * B * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(bd.m_val, 0, std::max<size_t>(net * B, 1) * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(bd.m_jac, 0, std::max<size_t>(net * nd * B, 1) * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(bd.targets, 0, std::max<size_t>(net * B, 1) * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(bd.fb_k, 0, T * nu * B * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(bd.fb_K, 0, T * nu * nd * B * sizeof(double), h->stream));
+  CU(cudaHostAlloc((void**)&h->h_stage, (size_t)NSCALARS * B * sizeof(double), cudaHostAllocDefault));
+  // launch geometry
+  const bool fdv = p->hess_mode == DDPB_HESS_FD_VALUES;
+  h->lin_threads = n <= 2 ? 32 : (n <= 4 ? (fdv ? 128 : 64) : (fdv ? 256 : 128));
+  h->bwd_threads = n <= 2 ? 32 : (n <= 4 ? 64 : 128);
+  DISPATCH(h->mt, { h->lin_smem = L::lin_smem_bytes(p->hess_mode, bd.ne_max); });
+  if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) { ddpb_batch_destroy(h); return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory"); }
+  DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });
+  DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(); });
+  CU(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return DDPB_OK;
+}
+
+void ddpb_batch_destroy(ddpb_batch* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->stage) cudaFree(h->stage);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  for (auto& e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int ddpb_batch_set_stream(ddpb_batch* h, void* s) {
+  if (!h) return fail(DDPB_ERR_INVALID, "null batch");
+  if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  h->stream = (cudaStream_t)s;
+  h->own_stream = false;
+  return DDPB_OK;
+}
+int ddpb_batch_sync(ddpb_batch* h) {
+  if (!h) return fail(DDPB_ERR_INVALID, "null batch");
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+int ddpb_host_alloc(void** ptr, unsigned long long bytes) {
+  CU(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+  return DDPB_OK;
+}
+int ddpb_host_free(void* ptr) {
+  CU(cudaFreeHost(ptr));
+  return DDPB_OK;
+}
+
+int ddpb_batch_dims(const ddpb_batch* h, int* o) {
+  if (!h || !o) return fail(DDPB_ERR_INVALID, "null argument");
+  o[0] = h->bd.n; o[1] = h->bd.nx; o[2] = h->bd.nx; o[3] = h->bd.nu; o[4] = h->bd.ne_total; o[5] = h->bd.T; o[6] = h->bd.B;
+  return DDPB_OK;
+}
+unsigned long long ddpb_launch_count(const ddpb_batch* h) { return h ? h->launches : 0; }
+int ddpb_enable_phase_timing(ddpb_batch* h, int on) {
+  if (!h) return fail(DDPB_ERR_INVALID, "null batch");
+  h->timing = on != 0;
+  return DDPB_OK;
+}
+int ddpb_phase_times(ddpb_batch* h, float* ms4) {
+  if (!h || !ms4) return fail(DDPB_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 4; ++k) ms4[k] = 0.f;
+  for (auto& e : h->events) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    ms4[e.phase] += ms;
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  h->events.clear();
+  return DDPB_OK;
+}
+
+#define ENTER(h)                                              \
+  if (!(h)) return fail(DDPB_ERR_INVALID, "null batch");      \
+  CU(cudaSetDevice((h)->device));
+
+int ddpb_set_trajectory(ddpb_batch* h, const double* xs, const double* us) {
+  ENTER(h);
+  const BatchDev& bd = h->bd;
+  int rc = DDPB_OK;
+  if (xs) rc = upload_T(h, bd.xs, xs, (size_t)(bd.T + 1) * bd.nx);
+  if (!rc && xs) CU(cudaStreamSynchronize(h->stream));  // the staging buffer is reused below
+  if (!rc && us) rc = upload_T(h, bd.us, us, (size_t)bd.T * bd.nu);
+  if (rc) return rc;
+  // the new-trajectory storage starts as a clone (ddp.hpp:752); x_0 of it is never rewritten
+  rc = dcopy(h, bd.xs_new, bd.xs, (size_t)(bd.T + 1) * bd.nx * bd.B);
+  if (!rc) rc = dcopy(h, bd.us_new, bd.us, (size_t)bd.T * bd.nu * bd.B);
+  CU(cudaStreamSynchronize(h->stream));
+  return rc;
+}
+int ddpb_get_trajectory(ddpb_batch* h, double* xs, double* us) {
+  ENTER(h);
+  int rc = DDPB_OK;
+  if (xs) rc = download_T(h, xs, h->bd.xs, (size_t)(h->bd.T + 1) * h->bd.nx);
+  if (!rc && us) rc = download_T(h, us, h->bd.us, (size_t)h->bd.T * h->bd.nu);
+  return rc;
+}
+int ddpb_get_new_trajectory(ddpb_batch* h, double* xs, double* us) {
+  ENTER(h);
+  int rc = DDPB_OK;
+  if (xs) rc = download_T(h, xs, h->bd.xs_new, (size_t)(h->bd.T + 1) * h->bd.nx);
+  if (!rc && us) rc = download_T(h, us, h->bd.us_new, (size_t)h->bd.T * h->bd.nu);
+  return rc;
+}
+int ddpb_make_trajectory(ddpb_batch* h, const double* x0, const double* us) {
+  ENTER(h);
+  const BatchDev& bd = h->bd;
+  if (!x0) return fail(DDPB_ERR_INVALID, "x0 is required");
+  int rc = upload_T(h, bd.xs, x0, bd.nx);  // knot 0 occupies the first nx rows of xs
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  if (us) { rc = upload_T(h, bd.us, us, (size_t)bd.T * bd.nu); if (rc) return rc; }
+  else CU(cudaMemsetAsync(bd.us, 0, (size_t)bd.T * bd.nu * bd.B * sizeof(double), h->stream));
+  DISPATCH(h->mt, L::rollout(h->model, bd, h->stream));
+  rc = check_launch(h, "rollout");
+  if (!rc) rc = dcopy(h, bd.xs_new, bd.xs, (size_t)(bd.T + 1) * bd.nx * bd.B);
+  if (!rc) rc = dcopy(h, bd.us_new, bd.us, (size_t)bd.T * bd.nu * bd.B);
+  CU(cudaStreamSynchronize(h->stream));
+  return rc;
+}
+int ddpb_set_targets(ddpb_batch* h, const double* targets) {
+  ENTER(h);
+  if (h->bd.ne_total == 0) return DDPB_OK;
+  if (!targets) return fail(DDPB_ERR_INVALID, "targets is null");
+  int rc = upload_T(h, h->bd.targets, targets, h->bd.ne_total);
+  CU(cudaStreamSynchronize(h->stream));
+  return rc;
+}
+int ddpb_set_multipliers(ddpb_batch* h, const double* val, const double* jac) {
+  ENTER(h);
+  const BatchDev& bd = h->bd;
+  const size_t net = bd.ne_total;
+  int rc = DDPB_OK;
+  if (net) {
+    if (val) { rc = upload_T(h, bd.m_val, val, net); CU(cudaStreamSynchronize(h->stream)); }
+    else CU(cudaMemsetAsync(bd.m_val, 0, net * bd.B * sizeof(double), h->stream));
+    if (rc) return rc;
+    if (jac) { rc = upload_T(h, bd.m_jac, jac, net * bd.nx); CU(cudaStreamSynchronize(h->stream)); }
+    else CU(cudaMemsetAsync(bd.m_jac, 0, net * bd.nx * bd.B * sizeof(double), h->stream));
+    if (rc) return rc;
+  }
+  rc = dcopy(h, bd.m_origin, bd.xs, (size_t)bd.T * bd.nx * bd.B);  // eq.origin() = xu.x()  (ddp.hpp:763)
+  CU(cudaStreamSynchronize(h->stream));
+  return rc;
+}
+int ddpb_get_multipliers(ddpb_batch* h, double* origin, double* val, double* jac) {
+  ENTER(h);
+  const BatchDev& bd = h->bd;
+  int rc = DDPB_OK;
+  if (origin) rc = download_T(h, origin, bd.m_origin, (size_t)bd.T * bd.nx);
+  if (!rc && val && bd.ne_total) rc = download_T(h, val, bd.m_val, bd.ne_total);
+  if (!rc && jac && bd.ne_total) rc = download_T(h, jac, bd.m_jac, (size_t)bd.ne_total * bd.nx);
+  return rc;
+}
+int ddpb_set_feedback(ddpb_batch* h, const double* k, const double* K) {
+  ENTER(h);
+  const BatchDev& bd = h->bd;
+  int rc = DDPB_OK;
+  if (k) { rc = upload_T(h, bd.fb_k, k, (size_t)bd.T * bd.nu); CU(cudaStreamSynchronize(h->stream)); }
+  if (!rc && K) { rc = upload_T(h, bd.fb_K, K, (size_t)bd.T * bd.nu * bd.nx); CU(cudaStreamSynchronize(h->stream)); }
+  if (!rc) rc = dcopy(h, bd.fb_origin, bd.xs, (size_t)bd.T * bd.nx * bd.B);
+  CU(cudaStreamSynchronize(h->stream));
+  return rc;
+}
+int ddpb_get_feedback(ddpb_batch* h, double* origin, double* k, double* K) {
+  ENTER(h);
+  const BatchDev& bd = h->bd;
+  int rc = DDPB_OK;
+  if (origin) rc = download_T(h, origin, bd.fb_origin, (size_t)bd.T * bd.nx);
+  if (!rc && k) rc = download_T(h, k, bd.fb_k, (size_t)bd.T * bd.nu);
+  if (!rc && K) rc = download_T(h, K, bd.fb_K, (size_t)bd.T * bd.nu * bd.nx);
+  return rc;
+}
+
+static int derivs_xfer(ddpb_batch* h, const ddpb_derivs* d, int to_slab) {
+  const BatchDev& bd = h->bd;
+  const int nd = bd.nx, nu = bd.nu, nx = bd.nx, T = bd.T;
+  double* ptrs[17] = {d->lx, d->lu, d->lxx, d->lux, d->luu, d->f_val, d->fx, d->fu, d->fxx, d->fux, d->fuu,
+                      d->eq_val, d->eq_x, d->eq_u, d->eq_xx, d->eq_ux, d->eq_uu};
+  const int per_knot[11] = {nd, nu, nd * nd, nu * nd, nu * nu, nx, nd * nd, nd * nu, nd * nd * nd, nd * nu * nd, nd * nu * nu};
+  const int per_row[6] = {1, nd, nu, nd * nd, nu * nd, nu * nu};
+  for (int f = 0; f < 17; ++f) {
+    if (!ptrs[f]) continue;
+    const size_t total = f < 11 ? (size_t)T * per_knot[f] : (size_t)bd.ne_total * per_row[f - 11];
+    if (total == 0) continue;
+    const size_t bytes = total * bd.B * sizeof(double);
+    int rc = ensure_stage(h, bytes);
+    if (rc) return rc;
+    if (to_slab) CU(cudaMemcpyAsync(h->stage, ptrs[f], bytes, cudaMemcpyHostToDevice, h->stream));
+    slab_field_kernel<<<(unsigned)std::min<size_t>((total * bd.B + 255) / 256, 8192), 256, 0, h->stream>>>(
+        bd, h->stage, total, f, f < 11 ? per_knot[f] : 0, f < 11 ? 0 : per_row[f - 11], to_slab);
+    rc = check_launch(h, "slab_field");
+    if (rc) return rc;
+    if (!to_slab) CU(cudaMemcpyAsync(ptrs[f], h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  if (!to_slab) {
+    if (d->lfx) std::memset(d->lfx, 0, (size_t)bd.B * nd * sizeof(double));        // lfx = 0  (problem.hpp:958)
+    if (d->lfxx) std::memset(d->lfxx, 0, (size_t)bd.B * nd * nd * sizeof(double)); // lfxx = 0 (problem.hpp:959)
+  }
+  return DDPB_OK;
+}
+int ddpb_set_derivatives(ddpb_batch* h, const ddpb_derivs* in) {
+  ENTER(h);
+  if (!in) return fail(DDPB_ERR_INVALID, "null derivs");
+  return derivs_xfer(h, in, 1);
+}
+int ddpb_get_derivatives(ddpb_batch* h, const ddpb_derivs* out) {
+  ENTER(h);
+  if (!out) return fail(DDPB_ERR_INVALID, "null derivs");
+  return derivs_xfer(h, out, 0);
+}
+int ddpb_set_scalar(ddpb_batch* h, int field, const double* values) {
+  ENTER(h);
+  if (field < 0 || field >= NSCALARS || !values) return fail(DDPB_ERR_INVALID, "bad scalar field");
+  CU(cudaMemcpyAsync(h->bd.scal + (size_t)field * h->bd.B, values, h->bd.B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+int ddpb_get_scalars(ddpb_batch* h, double* out) {
+  ENTER(h);
+  if (!out) return fail(DDPB_ERR_INVALID, "null output");
+  CU(cudaMemcpyAsync(out, h->bd.scal, (size_t)NSCALARS * h->bd.B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+int ddpb_scalars_device_ptr(ddpb_batch* h, void** ptr) {
+  if (!h || !ptr) return fail(DDPB_ERR_INVALID, "null argument");
+  *ptr = h->bd.scal;
+  return DDPB_OK;
+}
+
+int ddpb_compute_derivatives(ddpb_batch* h) {
+  ENTER(h);
+  int rc = launch_linearize(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+int ddpb_backward_pass(ddpb_batch* h, double* mu, double* reg) {
+  ENTER(h);
+  if (!mu || !reg) return fail(DDPB_ERR_INVALID, "mu / reg are required");
+  const int B = h->bd.B;
+  CU(cudaMemcpyAsync(h->bd.scal + (size_t)S_MU * B, mu, B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->bd.scal + (size_t)S_REG * B, reg, B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int rc = launch_backward(h);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(mu, h->bd.scal + (size_t)S_MU * B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(reg, h->bd.scal + (size_t)S_REG * B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+int ddpb_forward_pass(ddpb_batch* h, double* step_out) {
+  ENTER(h);
+  int rc = launch_forward(h);
+  if (rc) return rc;
+  if (step_out) CU(cudaMemcpyAsync(step_out, h->bd.scal + (size_t)S_STEP * h->bd.B, h->bd.B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+int ddpb_cost_seq_aug(ddpb_batch* h, double* costs) {
+  ENTER(h);
+  if (!costs) return fail(DDPB_ERR_INVALID, "null output");
+  DISPATCH(h->mt, L::cost(h->model, h->bd, h->costs_old, h->stream));
+  int rc = check_launch(h, "cost_seq_aug");
+  if (rc) return rc;
+  return download_T(h, costs, h->costs_old, (size_t)h->bd.T + 1);
+}
+int ddpb_optimality(ddpb_batch* h, double* opt_obj, double* opt_constr) {
+  ENTER(h);
+  const int B = h->bd.B;
+  DISPATCH(h->mt, L::optimality(h->bd, h->stream));
+  int rc = check_launch(h, "optimality");
+  if (rc) return rc;
+  if (opt_obj) CU(cudaMemcpyAsync(opt_obj, h->bd.scal + (size_t)S_OPT_OBJ * B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (opt_constr) CU(cudaMemcpyAsync(opt_constr, h->bd.scal + (size_t)S_OPT_CONSTR * B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+
+int ddpb_solve_async(ddpb_batch* h, const ddpb_solver_params* p) {
+  ENTER(h);
+  if (!p || p->max_iterations < 0) return fail(DDPB_ERR_INVALID, "bad solver parameters");
+  BatchDev& bd = h->bd;
+  const size_t B = bd.B;
+  int rc = DDPB_OK;
+#define R(x) do { rc = (x); if (rc) return rc; } while (0)
+  CU(cudaMemsetAsync(bd.scal, 0, (size_t)NSCALARS * B * sizeof(double), h->stream));
+  R(fill(h, bd.scal + S_MU * B, B, p->mu));
+  R(fill(h, bd.scal + S_REG * B, B, p->reg));
+  R(fill(h, bd.scal + S_W * B, B, p->w));
+  R(fill(h, bd.scal + S_N * B, B, p->n));
+  // warm-up derivative / backward / forward (ddp.hpp:768-773): mu is taken from it, reg is not,
+  // and the trial trajectory is not swapped in
+  R(scalar_copy(h, S_SPARE, S_REG));
+  R(launch_linearize(h));
+  R(launch_backward(h));
+  R(scalar_copy(h, S_REG, S_SPARE));
+  R(launch_forward(h));
+  CU(cudaMemsetAsync(bd.scal + S_ROLLOUTS * B, 0, B * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(bd.scal + S_RESTARTS * B, 0, B * sizeof(double), h->stream));
+  for (int iter = 0; iter < p->max_iterations; ++iter) {
+    R(launch_linearize(h));
+    R(launch_al_update(h, p->optimality_stopping_threshold));
+    R(launch_backward(h));
+    R(launch_forward(h));
+    R(launch_simple(h, 0));
+    std::swap(bd.xs, bd.xs_new);   // swap(traj, new_traj)  (ddp.hpp:826)
+    std::swap(bd.us, bd.us_new);
+  }
+#undef R
+  return DDPB_OK;
+}
+int ddpb_solve(ddpb_batch* h, const ddpb_solver_params* p, double* scalars_out) {
+  int rc = ddpb_solve_async(h, p);
+  if (rc) return rc;
+  if (scalars_out) return ddpb_get_scalars(h, scalars_out);
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+
+}  // extern "C"

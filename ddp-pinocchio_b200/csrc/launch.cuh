@@ -1,0 +1,24 @@
+// launch.cuh -- per-model-size kernel launchers.  Each instantiation Launch<NJ> lives in its own
+// translation unit (kernels_nj.cu compiled with -DDDPB_NJ=<n>) so the build parallelises.
+// NJ = 0 is the analytic pendulum (thread-per-problem kernels only; its backward pass is Launch<1>'s).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "batch.cuh"
+
+namespace ddpb {
+
+template <int NJ> struct Launch {
+  static size_t lin_smem_bytes(int hess_mode, int ne_max);
+  static size_t bwd_smem_bytes();
+  static cudaError_t prepare(size_t lin_smem);
+  static void linearize(const ModelDev& m, const BatchDev& bd, int threads, size_t smem, cudaStream_t s);
+  static void backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s);
+  static void forward(const ModelDev& m, const BatchDev& bd, double* costs_old, cudaStream_t s);
+  static void rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s);
+  static void cost(const ModelDev& m, const BatchDev& bd, double* costs, cudaStream_t s);
+  static void al_update(const BatchDev& bd, double thr, cudaStream_t s);
+  static void optimality(const BatchDev& bd, cudaStream_t s);
+};
+
+}  // namespace ddpb

@@ -1,0 +1,475 @@
+// linearize.cuh -- per-knot linearization: one CTA computes the complete derivative record of
+// one (problem, knot): cost derivatives, Euler-discretised dynamics value / Jacobians / finite-
+// difference Hessians, and the doubly time-advanced equality constraint with its derivatives.
+//
+// Restates problem_t::compute_derivatives (/root/reference/include/ddp/problem.hpp:956-997) with
+//   dynamics_t::eval_to / first_order_deriv            (problem.hpp:441-503)
+//   finite_diff_hessian_compute::second_order_deriv_1  (problem.hpp:67-150, eps = sqrt(eps_mach))
+//   finite_diff_hessian_compute::second_order_deriv_2  (problem.hpp:152-298, eps = eps_mach^(1/4))
+//   constraint_advance_time_t o constraint_advance_time_t o {config,spatial}_constraint_t
+//                                                      (problem.hpp:527-864)
+// The finite-difference stencils are evaluated on exactly the reference's points, but work that the
+// reference repeats is shared: all evaluation points with the same q share one q_task (articulated
+// inertias, M^-1), and the advanced constraint reuses the dynamics already evaluated at the point
+// (c depends on q_{t+2} = q_{t+1} + dt v_{t+1} only, so the second ABA of the reference's
+// eval_to chain never influences the result).
+#pragma once
+#include "batch.cuh"
+
+namespace ddpb {
+
+DDPB_HD int pair_rank(int i, int j, int N) { return i * N - (i * (i + 1)) / 2 + (j - i - 1); }
+DDPB_HD void pair_unrank(int r, int N, int* i, int* j) {
+  int ii = 0;
+  while (r >= N - 1 - ii) { r -= N - 1 - ii; ++ii; }
+  *i = ii; *j = ii + 1 + r;
+}
+
+template <int NJ> struct LinPlan {
+  static constexpr int N = 3 * NJ;
+  int mode, P, NQ, NT;  // evaluation points, distinct-q sets, points that need first-order data
+  int ne;               // equality rows at this knot
+  // shared-memory offsets (doubles)
+  int o_base, o_tgt, o_qrec, o_vrec, o_fval, o_eqv, o_J, o_eqxu, total;
+  DDPB_HD static int points(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + N : 1 + N + N * (N - 1) / 2; }
+  DDPB_HD static int qsets(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + NJ : 1 + NJ + NJ * (NJ - 1) / 2; }
+  DDPB_HD void init(int mode_, int ne_max, int ne_) {
+    mode = mode_; ne = ne_;
+    P = points(mode); NQ = qsets(mode);
+    NT = mode == HESS_FD_JACOBIANS ? P : 1;
+    int o = 0;
+    o_base = o; o += 4 * NJ;
+    o_tgt = o; o += (ne_max + 1) & ~1;
+    o_qrec = o; o += NQ * QRec<NJ>::SIZE;
+    o_vrec = o; o += NT * VRec<NJ>::SIZE;
+    o_fval = o; o += P * 2 * NJ;
+    o_eqv = o; o += P * ne_max;
+    o_J = o; o += NT * 3 * NJ;
+    o_eqxu = o; o += NT * ne_max * N;
+    total = o;
+  }
+  // which tangent index/indices a point perturbs (-1 = none)
+  DDPB_HD void point_pert(int p, int* i, int* j) const {
+    *i = -1; *j = -1;
+    if (p == 0) return;
+    if (p <= N) { *i = p - 1; return; }
+    pair_unrank(p - 1 - N, N, i, j);
+  }
+  DDPB_HD int point_qset(int p) const {
+    int i, j;
+    point_pert(p, &i, &j);
+    if (i < 0 || i >= NJ) return 0;          // i < j, so j >= NJ as well
+    if (j < 0 || j >= NJ) return 1 + i;
+    return 1 + NJ + pair_rank(i, j, NJ);
+  }
+  DDPB_HD void qset_pert(int s, int* i, int* j) const {
+    *i = -1; *j = -1;
+    if (s == 0) return;
+    if (s <= NJ) { *i = s - 1; return; }
+    pair_unrank(s - 1 - NJ, NJ, i, j);
+  }
+  DDPB_HD double eps() const { return mode == HESS_FD_JACOBIANS ? 1.4901161193847656e-08 /* 2^-26 */ : 1.220703125e-04 /* 2^-13 */; }
+};
+
+template <int NJ, class Ex>
+DDPB_HD void linearize_knot(const ModelDev& m, const BatchDev& bd, int b, int t, double* sm, const Ex& ex) {
+  constexpr int n = NJ, nd = 2 * NJ, nu = NJ, nx = 2 * NJ, N = 3 * NJ;
+  using Q = QRec<NJ>;
+  using V = VRec<NJ>;
+  const int B = bd.B;
+  const int ne = bd.ne[t];
+  LinPlan<NJ> pl;
+  pl.init(bd.hess_mode, bd.ne_max, ne);
+  const double eps = pl.eps();
+  const double dt = bd.dt;
+  double* base = sm + pl.o_base;
+  double* tgt = sm + pl.o_tgt;
+  double* qrec = sm + pl.o_qrec;
+  double* vrec = sm + pl.o_vrec;
+  double* fval = sm + pl.o_fval;
+  double* eqv = sm + pl.o_eqv;
+  double* Jsm = sm + pl.o_J;
+  double* eqxu = sm + pl.o_eqxu;
+  const int tid = ex.tid(), nthr = ex.nthr();
+
+  // phase 0: stage x_t, u_t and the target
+  for (int e = tid; e < N + ne; e += nthr) {
+    if (e < nx) base[e] = bd.xs[((size_t)t * nx + e) * B + b];
+    else if (e < N) base[e] = bd.us[((size_t)t * nu + (e - nx)) * B + b];
+    else tgt[e - N] = bd.targets[((size_t)bd.eq_off[t] + (e - N)) * B + b];
+  }
+  ex.sync();
+
+  // phase 1: q-only data for every distinct configuration
+  for (int s = tid; s < pl.NQ; s += nthr) {
+    int i, j;
+    pl.qset_pert(s, &i, &j);
+    double q[NJ];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
+    q_task<NJ>(m, q, qrec + (size_t)s * Q::SIZE);
+  }
+  ex.sync();
+
+  // phase 2: accelerations (and body data where tangents are needed) at every evaluation point
+  for (int p = tid; p < pl.P; p += nthr) {
+    int i, j;
+    pl.point_pert(p, &i, &j);
+    double q[NJ], qd[NJ], tau[NJ], qdd[NJ];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
+      qd[k] = base[n + k] + ((n + k == i || n + k == j) ? eps : 0.0);
+      tau[k] = base[2 * n + k] + ((2 * n + k == i || 2 * n + k == j) ? eps : 0.0);
+    }
+    v_task<NJ>(m, qrec + (size_t)pl.point_qset(p) * Q::SIZE, qd, tau, qdd, p < pl.NT ? vrec + (size_t)p * V::SIZE : nullptr);
+    // dynamics_t::eval_to (problem.hpp:441-461): v_out = dt v ; q_out = q + v_out ; v_out = v + acc dt
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      const double vo = dt * qd[k];
+      fval[p * nx + k] = q[k] + vo;
+      fval[p * nx + n + k] = qd[k] + qdd[k] * dt;
+    }
+  }
+  ex.sync();
+
+  // phase 3: tangent columns of inverse dynamics and columns of M^-1
+  {
+    const int n_tan = pl.NT * 2 * NJ;
+    const int n_minv = (pl.mode == HESS_FD_JACOBIANS ? pl.NQ : 1) * NJ;
+    for (int task = tid; task < n_tan + n_minv; task += nthr) {
+      double col[NJ];
+      if (task < n_tan) {
+        const int j = task / (2 * pl.NT), rem = task - j * 2 * pl.NT;
+        const int wrt = rem / pl.NT, p = rem - wrt * pl.NT;
+        double* vr = vrec + (size_t)p * V::SIZE;
+        tangent_col<NJ>(m, qrec + (size_t)pl.point_qset(p) * Q::SIZE, vr, j, wrt, col);
+        double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) dst[k] = col[k];
+      } else {
+        const int r = task - n_tan;
+        const int c = r % NJ, s = r / NJ;
+        double* qr = qrec + (size_t)s * Q::SIZE;
+        minv_col<NJ>(m, qr, c, col);
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) qr[Q::MINV + c * NJ + k] = col[k];
+      }
+    }
+  }
+  ex.sync();
+
+  // phase 4: da/dq = -M^-1 dtau/dq, da/dv = -M^-1 dtau/dv, already scaled into the bottom blocks of
+  // fx (problem.hpp:495-502): DQ <- dt * da/dq ; DV <- dt * da/dv + I
+  for (int task = tid; task < pl.NT * 2 * NJ; task += nthr) {
+    const int p = task / (2 * NJ), rem = task - p * 2 * NJ;
+    const int wrt = rem / NJ, c = rem - wrt * NJ;
+    double* vr = vrec + (size_t)p * V::SIZE;
+    double* colp = vr + (wrt ? V::DV : V::DQ) + c * NJ;
+    const double* Mi = qrec + (size_t)pl.point_qset(p) * Q::SIZE + Q::MINV;
+    double src[NJ], dst[NJ];
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) src[k] = colp[k];
+#pragma unroll
+    for (int r = 0; r < NJ; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) acc += Mi[k * NJ + r] * src[k];
+      dst[r] = (-acc) * dt;
+      if (wrt && r == c) dst[r] += 1.0;
+    }
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) colp[k] = dst[k];
+  }
+  ex.sync();
+
+  // element accessors of fx / fu at point p (p < NT)
+  auto fx_at = [&](int p, int r, int c) -> double {
+    if (r < n) return c < n ? (r == c ? 1.0 : 0.0) : (r == c - n ? dt : 0.0);
+    const double* vr = vrec + (size_t)p * V::SIZE;
+    return c < n ? vr[V::DQ + c * NJ + (r - n)] : vr[V::DV + (c - n) * NJ + (r - n)];
+  };
+  auto fu_at = [&](int p, int r, int c) -> double {
+    if (r < n) return 0.0;
+    return qrec[(size_t)pl.point_qset(p) * Q::SIZE + Q::MINV + c * NJ + (r - n)] * dt;
+  };
+
+  // phase 5: the doubly advanced equality constraint at every point
+  if (ne > 0) {
+    for (int p = tid; p < pl.P; p += nthr) {
+      // x_{t+1} = f(x,u) is fval[p]; inner eval_to: v_out = dt v ; q_out = q + v_out
+      double qnn[NJ];
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) { const double vo = dt * fval[p * nx + n + k]; qnn[k] = fval[p * nx + k] + vo; }
+      if (bd.eq_kind == EQ_CONFIG) {
+        for (int r = 0; r < ne; ++r) eqv[p * bd.ne_max + r] = qnn[r] - tgt[r];
+      } else {
+        double p3[3];
+        frame_task<NJ>(m, qnn, bd.frame_id, bd.jac_mode, p3, p < pl.NT ? Jsm + p * 3 * NJ : nullptr);
+        for (int r = 0; r < ne; ++r) eqv[p * bd.ne_max + r] = p3[r] - tgt[r];
+      }
+    }
+    ex.sync();
+    // eq_x = c_x [I, dt I] fx ; eq_u = c_x [I, dt I] fu   (problem.hpp:603-604, applied twice)
+    for (int task = tid; task < pl.NT * ne * N; task += nthr) {
+      const int p = task / (ne * N), rem = task - p * ne * N;
+      const int c = rem / ne, r = rem - c * ne;
+      double acc = 0.0;
+      if (bd.eq_kind == EQ_CONFIG) {
+        if (c < nd) { acc = fx_at(p, r, c); acc += dt * fx_at(p, n + r, c); }
+        else { acc = fu_at(p, r, c - nd); acc += dt * fu_at(p, n + r, c - nd); }
+      } else {
+        const double* J = Jsm + p * 3 * NJ;
+        for (int k = 0; k < nd; ++k) {
+          const double e = k < n ? J[k * 3 + r] : J[(k - n) * 3 + r] * dt;
+          acc += e * (c < nd ? fx_at(p, k, c) : fu_at(p, k, c - nd));
+        }
+      }
+      eqxu[(size_t)p * bd.ne_max * N + c * ne + r] = acc;
+    }
+    ex.sync();
+  }
+
+  // phase 6: assemble the record and stream it out (consecutive threads -> consecutive doubles)
+  const RecLayout L = rec_layout(nd, nu, nx, ne);
+  double* rec = slab_rec(bd, t, b, L.size);
+  const double inv_eps = 1.0 / eps, inv_eps2 = 1.0 / (eps * eps);
+  for (int e = tid; e < nd; e += nthr) rec[L.lx + e] = 0.0;
+  for (int e = tid; e < nu; e += nthr) rec[L.lu + e] = bd.c * base[2 * n + e];
+  for (int e = tid; e < nd * nd; e += nthr) rec[L.lxx + e] = 0.0;
+  for (int e = tid; e < nu * nd; e += nthr) rec[L.lux + e] = 0.0;
+  for (int e = tid; e < nu * nu; e += nthr) rec[L.luu + e] = (e / nu == e % nu) ? bd.c : 0.0;
+  for (int e = tid; e < nx; e += nthr) rec[L.f + e] = fval[e];
+  for (int e = tid; e < nd * nd; e += nthr) rec[L.fx + e] = fx_at(0, e % nd, e / nd);
+  for (int e = tid; e < nd * nu; e += nthr) rec[L.fu + e] = fu_at(0, e % nd, e / nd);
+  for (int e = tid; e < ne; e += nthr) rec[L.eq + e] = eqv[e];
+  for (int e = tid; e < ne * nd; e += nthr) rec[L.eq_x + e] = eqxu[e];
+  for (int e = tid; e < ne * nu; e += nthr) rec[L.eq_u + e] = eqxu[ne * nd + e];
+
+  if (pl.mode == HESS_FD_JACOBIANS) {
+    // problem.hpp:128-145: T(k,j,idx) = (J'(k,j) - J(k,j)) / eps ; rows k < n are exact constants
+    for (int e = tid; e < nd * nd * nd; e += nthr) {
+      const int k = e % nd, j = (e / nd) % nd, i = e / (nd * nd);
+      rec[L.fxx + e] = k < n ? 0.0 : (fx_at(1 + i, k, j) - fx_at(0, k, j)) * inv_eps;
+    }
+    for (int e = tid; e < nd * nu * nd; e += nthr) {
+      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
+      rec[L.fux + e] = k < n ? 0.0 : (fu_at(1 + i, k, j) - fu_at(0, k, j)) * inv_eps;
+    }
+    for (int e = tid; e < nd * nu * nu; e += nthr) {
+      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
+      rec[L.fuu + e] = k < n ? 0.0 : (fu_at(1 + nd + i, k, j) - fu_at(0, k, j)) * inv_eps;
+    }
+    if (ne > 0) {
+      const size_t ps = (size_t)bd.ne_max * N;  // eqxu stride per point
+      for (int e = tid; e < ne * nd * nd; e += nthr) {
+        const int k = e % ne, j = (e / ne) % nd, i = e / (ne * nd);
+        rec[L.eq_xx + e] = (eqxu[(1 + i) * ps + j * ne + k] - eqxu[j * ne + k]) * inv_eps;
+      }
+      for (int e = tid; e < ne * nu * nd; e += nthr) {
+        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
+        rec[L.eq_ux + e] = (eqxu[(1 + i) * ps + (nd + j) * ne + k] - eqxu[(nd + j) * ne + k]) * inv_eps;
+      }
+      for (int e = tid; e < ne * nu * nu; e += nthr) {
+        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
+        rec[L.eq_uu + e] = (eqxu[(1 + nd + i) * ps + (nd + j) * ne + k] - eqxu[(nd + j) * ne + k]) * inv_eps;
+      }
+    }
+  } else {
+    // problem.hpp:192-296.  `val0` / `J0col` are the base value and Jacobian column accessors of the
+    // function being differentiated (f or eq); `valp` the value at point p.
+    auto diag = [&](double f1, double f0, double col) -> double {
+      double df = f1 - f0;
+      df -= eps * col;
+      df *= 2.0;
+      return df * inv_eps2;
+    };
+    auto offd = [&](double f1, double f0, double col1, double col2, double d1, double d2) -> double {
+      double df = f1 - f0;
+      df -= eps * col1;
+      df -= eps * col2;
+      df *= 2.0;
+      return 0.5 * (df * inv_eps2 - d1 - d2);
+    };
+    // generic element: output row k of function `which` (0 = f, 1 = eq), global tangent indices ga, gb
+    auto jcol = [&](int which, int k, int g) -> double {
+      if (which == 0) return g < nd ? fx_at(0, k, g) : fu_at(0, k, g - nd);
+      return eqxu[g * ne + k];
+    };
+    auto val = [&](int which, int p, int k) -> double { return which == 0 ? fval[p * nx + k] : eqv[p * bd.ne_max + k]; };
+    auto hess = [&](int which, int k, int ga, int gb) -> double {
+      const double f0 = val(which, 0, k);
+      if (ga == gb) return diag(val(which, 1 + ga, k), f0, jcol(which, k, ga));
+      const int i = ga < gb ? ga : gb, j = ga < gb ? gb : ga;
+      const double ci = jcol(which, k, i), cj = jcol(which, k, j);
+      const double di = diag(val(which, 1 + i, k), f0, ci), dj = diag(val(which, 1 + j, k), f0, cj);
+      return offd(val(which, 1 + N + pair_rank(i, j, N), k), f0, ci, cj, di, dj);
+    };
+    for (int e = tid; e < nd * nd * nd; e += nthr) {
+      const int k = e % nd, j = (e / nd) % nd, i = e / (nd * nd);
+      rec[L.fxx + e] = hess(0, k, j, i);
+    }
+    for (int e = tid; e < nd * nu * nd; e += nthr) {
+      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
+      rec[L.fux + e] = hess(0, k, nd + j, i);
+    }
+    for (int e = tid; e < nd * nu * nu; e += nthr) {
+      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
+      rec[L.fuu + e] = hess(0, k, nd + j, nd + i);
+    }
+    if (ne > 0) {
+      for (int e = tid; e < ne * nd * nd; e += nthr) {
+        const int k = e % ne, j = (e / ne) % nd, i = e / (ne * nd);
+        rec[L.eq_xx + e] = hess(1, k, j, i);
+      }
+      for (int e = tid; e < ne * nu * nd; e += nthr) {
+        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
+        rec[L.eq_ux + e] = hess(1, k, nd + j, i);
+      }
+      for (int e = tid; e < ne * nu * nu; e += nthr) {
+        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
+        rec[L.eq_uu + e] = hess(1, k, nd + j, nd + i);
+      }
+    }
+  }
+}
+
+// ---- pendulum (nx = 2, nu = 1): one thread per knot, following the oracle statement by statement ----
+DDPB_HD void pend_eval(const ModelDev& m, double dt, const double* x, double u, double* f) {
+  const double vo = dt * x[1];
+  f[0] = x[0] + vo;
+  f[1] = x[1] + pend_acc(m, x[0], u) * dt;
+}
+DDPB_HD void pend_first(const ModelDev& m, double dt, const double* x, double u, double* f, double* fx /*2x2 col-major*/, double* fu /*2*/) {
+  pend_eval(m, dt, x, u, f);
+  fx[0] = 1.0; fx[2] = dt;
+  fx[1] = pend_dacc_dq(m, x[0]) * dt;
+  fx[3] = 0.0 * dt + 1.0;
+  fu[0] = 0.0;
+  fu[1] = (1.0 / m.pend_m) * dt;
+}
+// eq(t,x,u) = q_{t+2} - target with x_{t+1} = f(x,u), q_{t+2} = q_{t+1} + dt v_{t+1}
+DDPB_HD double pend_eq(const ModelDev& m, double dt, const double* x, double u, double tgt) {
+  double f[2];
+  pend_eval(m, dt, x, u, f);
+  const double vo = dt * f[1];
+  return (f[0] + vo) - tgt;
+}
+DDPB_HD void pend_eq_first(const ModelDev& m, double dt, const double* x, double u, double tgt, double* e, double* ex /*2*/, double* eu) {
+  double f[2], fx[4], fu[2];
+  pend_first(m, dt, x, u, f, fx, fu);
+  const double vo = dt * f[1];
+  *e = (f[0] + vo) - tgt;
+  // eq_n_x = [1, dt] ; out_x = eq_n_x fx ; out_u = eq_n_x fu
+  ex[0] = fx[0]; ex[0] += dt * fx[1];
+  ex[1] = fx[2]; ex[1] += dt * fx[3];
+  *eu = fu[0]; *eu += dt * fu[1];
+}
+
+DDPB_HD void linearize_pendulum(const ModelDev& m, const BatchDev& bd, int b, int t) {
+  const int B = bd.B;
+  const int ne = bd.ne[t];
+  const double dt = bd.dt;
+  const double x[2] = {bd.xs[((size_t)t * 2 + 0) * B + b], bd.xs[((size_t)t * 2 + 1) * B + b]};
+  const double u = bd.us[(size_t)t * B + b];
+  const double tgt = ne ? bd.targets[(size_t)bd.eq_off[t] * B + b] : 0.0;
+  const RecLayout L = rec_layout(2, 1, 2, ne);
+  double* rec = slab_rec(bd, t, b, L.size);
+  rec[L.lx] = 0.0; rec[L.lx + 1] = 0.0;
+  rec[L.lu] = bd.c * u;
+  for (int e = 0; e < 4; ++e) rec[L.lxx + e] = 0.0;
+  rec[L.lux] = 0.0; rec[L.lux + 1] = 0.0;
+  rec[L.luu] = bd.c;
+  double f0[2], fx0[4], fu0[2];
+  pend_first(m, dt, x, u, f0, fx0, fu0);
+  rec[L.f] = f0[0]; rec[L.f + 1] = f0[1];
+  for (int e = 0; e < 4; ++e) rec[L.fx + e] = fx0[e];
+  rec[L.fu] = fu0[0]; rec[L.fu + 1] = fu0[1];
+  double e0 = 0.0, ex0[2] = {0.0, 0.0}, eu0 = 0.0;
+  if (ne) {
+    pend_eq_first(m, dt, x, u, tgt, &e0, ex0, &eu0);
+    rec[L.eq] = e0; rec[L.eq_x] = ex0[0]; rec[L.eq_x + 1] = ex0[1]; rec[L.eq_u] = eu0;
+  }
+  if (bd.hess_mode == HESS_FD_JACOBIANS) {
+    const double eps = 1.4901161193847656e-08, ie = 1.0 / eps;
+    for (int i = 0; i < 3; ++i) {
+      double xp[2] = {x[0] + (i == 0 ? eps : 0.0), x[1] + (i == 1 ? eps : 0.0)};
+      double up = u + (i == 2 ? eps : 0.0);
+      double f1[2], fx1[4], fu1[2];
+      pend_first(m, dt, xp, up, f1, fx1, fu1);
+      double e1 = 0, ex1[2] = {0, 0}, eu1 = 0;
+      if (ne) pend_eq_first(m, dt, xp, up, tgt, &e1, ex1, &eu1);
+      if (i < 2) {
+        for (int k = 0; k < 2; ++k) {
+          for (int j = 0; j < 2; ++j) rec[L.fxx + k + j * 2 + i * 4] = (fx1[j * 2 + k] - fx0[j * 2 + k]) * ie;
+          rec[L.fux + k + i * 2] = (fu1[k] - fu0[k]) * ie;
+        }
+        if (ne) {
+          for (int j = 0; j < 2; ++j) rec[L.eq_xx + j + i * 2] = (ex1[j] - ex0[j]) * ie;
+          rec[L.eq_ux + i] = (eu1 - eu0) * ie;
+        }
+      } else {
+        for (int k = 0; k < 2; ++k) rec[L.fuu + k] = (fu1[k] - fu0[k]) * ie;
+        if (ne) rec[L.eq_uu] = (eu1 - eu0) * ie;
+      }
+    }
+  } else {
+    const double eps = 1.220703125e-04, ie2 = 1.0 / (eps * eps);
+    // points: 3 singles, 3 pairs (0,1), (0,2), (1,2) over the tangent indices (q, v, u)
+    double fs[3][2], es[3] = {0, 0, 0};
+    double col[3][2] = {{fx0[0], fx0[1]}, {fx0[2], fx0[3]}, {fu0[0], fu0[1]}};
+    double ecol[3] = {ex0[0], ex0[1], eu0};
+    double dg[3][2], edg[3] = {0, 0, 0};
+    for (int i = 0; i < 3; ++i) {
+      double xp[2] = {x[0] + (i == 0 ? eps : 0.0), x[1] + (i == 1 ? eps : 0.0)};
+      double up = u + (i == 2 ? eps : 0.0);
+      pend_eval(m, dt, xp, up, fs[i]);
+      for (int k = 0; k < 2; ++k) {
+        double df = fs[i][k] - f0[k];
+        df -= eps * col[i][k];
+        df *= 2.0;
+        dg[i][k] = df * ie2;
+      }
+      if (ne) {
+        es[i] = pend_eq(m, dt, xp, up, tgt);
+        double df = es[i] - e0;
+        df -= eps * ecol[i];
+        df *= 2.0;
+        edg[i] = df * ie2;
+      }
+    }
+    for (int k = 0; k < 2; ++k) {
+      rec[L.fxx + k + 0 * 2 + 0 * 4] = dg[0][k];
+      rec[L.fxx + k + 1 * 2 + 1 * 4] = dg[1][k];
+      rec[L.fuu + k] = dg[2][k];
+    }
+    if (ne) { rec[L.eq_xx + 0] = edg[0]; rec[L.eq_xx + 3] = edg[1]; rec[L.eq_uu] = edg[2]; }
+    for (int i = 0; i < 3; ++i)
+      for (int j = i + 1; j < 3; ++j) {
+        double xp[2] = {x[0] + ((i == 0 || j == 0) ? eps : 0.0), x[1] + ((i == 1 || j == 1) ? eps : 0.0)};
+        double up = u + ((i == 2 || j == 2) ? eps : 0.0);
+        double f1[2];
+        pend_eval(m, dt, xp, up, f1);
+        for (int k = 0; k < 2; ++k) {
+          double df = f1[k] - f0[k];
+          df -= eps * col[i][k];
+          df -= eps * col[j][k];
+          df *= 2.0;
+          const double v = 0.5 * (df * ie2 - dg[i][k] - dg[j][k]);
+          if (j < 2) { rec[L.fxx + k + j * 2 + i * 4] = v; rec[L.fxx + k + i * 2 + j * 4] = v; }
+          else rec[L.fux + k + i * 2] = v;  // ux(k, u, x_i)
+        }
+        if (ne) {
+          double df = pend_eq(m, dt, xp, up, tgt) - e0;
+          df -= eps * ecol[i];
+          df -= eps * ecol[j];
+          df *= 2.0;
+          const double v = 0.5 * (df * ie2 - edg[i] - edg[j]);
+          if (j < 2) { rec[L.eq_xx + j + i * 2] = v; rec[L.eq_xx + i + j * 2] = v; }
+          else rec[L.eq_ux + i] = v;
+        }
+      }
+  }
+}
+
+}  // namespace ddpb

@@ -1,0 +1,190 @@
+"""Parity checks shared by the CPU-emulated kernels (tests/test_emu_parity.py, no GPU) and the real CUDA
+path through the C ABI (tests/test_gpu_parity.py, -m gpu).  `make(w)` builds a batch for a Workload."""
+import numpy as np
+
+import ddpb_loader
+
+P = ddpb_loader.load()
+import oracle_lib as ol  # noqa: E402
+
+S = P.synthetic
+FIRST_ORDER = ["lx", "lu", "lxx", "lux", "luu", "f_val", "fx", "fu", "eq_val", "eq_x", "eq_u"]
+TENSORS = ["fxx", "fux", "fuu", "eq_xx", "eq_ux", "eq_uu"]
+U = 2.0 ** -53
+# Tolerances.  north_star: Jacobians and gains within 1e-9 relative, trajectories / cost within 1e-8 relative.
+TOL_FIRST = 1e-10       # f, fx, fu, eq, eq_x, eq_u (relative to the block's max magnitude)
+TOL_GAINS = 1e-9        # k, K given identical derivative slabs
+TOL_ROLLOUT = 1e-10     # trajectories / merit given identical gains
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=float).ravel(); b = np.asarray(b, dtype=float).ravel()
+    if a.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def cases():
+    """(id, workload) pairs covering the five BASELINE.json configs at oracle-friendly sizes + edge cases."""
+    out = []
+
+    def add(tag, name, B, T, **kw):
+        w = S.workload(name, B=B, T=T)
+        for k, v in kw.items():
+            setattr(w, k, v)
+        out.append((tag, w))
+
+    add("c1_pendulum_fdvalues", "c1", 2, 16)
+    add("c1_pendulum_fdjac", "c1", 2, 16, hess_mode=S.HESS_FD_JACOBIANS)
+    add("c2_chain2r", "c2", 5, 10)
+    add("c2_chain2r_fdvalues", "c2", 3, 8, hess_mode=S.HESS_FD_VALUES)
+    add("c3_arm6r_terminal", "c3", 3, 8)
+    add("c3_arm6r_every_knot", "c3", 2, 6, eq_every_knot=True)
+    add("c3_arm6r_unconstrained", "c3", 2, 5, eq_kind=S.EQ_NONE)
+    add("c4_arm6r_spatial", "c4", 3, 8)
+    add("c4_arm6r_spatial_lwa_jac", "c4", 2, 6, jac_mode=S.FJ_LOCAL_WORLD_ALIGNED)
+    # value-based FD Hessians subtract eps*J: only meaningful with the true Jacobian (the reference's WORLD-convention
+    # quirk would leave an O(1/eps) residue), so this combination uses LOCAL_WORLD_ALIGNED
+    add("c4_arm6r_spatial_fdvalues", "c4", 2, 5, hess_mode=S.HESS_FD_VALUES, jac_mode=S.FJ_LOCAL_WORLD_ALIGNED)
+    add("c5_arm7r_fdvalues", "c5", 2, 6)
+    add("c5_arm7r_fdjac_every_knot", "c5", 2, 4, hess_mode=S.HESS_FD_JACOBIANS, eq_every_knot=True)
+    w = S.Workload("chain3r_random", P.models.chain_nr(3), 3, 7)
+    out.append(("chain3r_random", w))
+    w = S.Workload("chain5r_random_spatial", P.models.chain_nr(5), 2, 6, eq_kind=S.EQ_SPATIAL, frame=5)
+    out.append(("chain5r_random_spatial", w))
+    w = S.Workload("chain1r", P.models.chain_nr(1), 2, 6)
+    out.append(("chain1r", w))
+    return out
+
+
+def setup(make, w, seed=1, random_controls=True):
+    g = w.generate()
+    bt = make(w)
+    bt.set_targets(g["targets"])
+    rng = np.random.RandomState(seed)
+    us = rng.uniform(-2, 2, (w.B, w.T, w.nu)) if random_controls else g["us"]
+    bt.make_trajectory(g["x0"], us)
+    orcs = [ol.from_workload(w, g["targets"][b]) for b in range(w.B)]
+    return g, bt, us, orcs, rng
+
+
+def check_linearization(make, w):
+    """compute_derivatives vs the oracle on identical trajectories (problem.hpp:956-997)."""
+    g, bt, us, orcs, _ = setup(make, w)
+    xs, us_back = bt.get_trajectory()
+    assert np.array_equal(us_back, us)
+    bt.compute_derivatives()
+    D = bt.get_derivatives()
+    eps = 2.0 ** -26 if w.hess_mode == S.HESS_FD_JACOBIANS else 2.0 ** -13
+    for b in range(w.B):
+        xo = orcs[b].rollout(g["x0"][b], us[b])
+        assert relerr(xs[b], xo) < TOL_ROLLOUT, "make_trajectory"
+        d = orcs[b].compute_derivatives(xs[b], us[b])
+        for f in FIRST_ORDER:
+            assert D[f][b].shape == d[f].shape
+            assert relerr(D[f][b], d[f]) < TOL_FIRST, (f, relerr(D[f][b], d[f]))
+        # finite-difference tensors: both sides carry rounding noise ~ ulp(J)/eps (mode 1: ulp(f)/eps^2);
+        # bound the absolute difference by that floor
+        jscale = max(1.0, np.abs(d["fx"]).max(), np.abs(d["fu"]).max(), np.abs(d["f_val"]).max())
+        floor = 4096 * U * jscale / (eps if w.hess_mode == S.HESS_FD_JACOBIANS else eps * eps)
+        for f in TENSORS:
+            if d[f].size:
+                assert np.abs(D[f][b] - d[f]).max() <= floor, (f, np.abs(D[f][b] - d[f]).max(), floor)
+    bt.close()
+
+
+def check_tensors_vs_quad(make, w):
+    """The product's FD tensors are as close to the __float128 oracle as the double oracle's are."""
+    g, bt, us, orcs, _ = setup(make, w)
+    xs, _ = bt.get_trajectory()
+    bt.compute_derivatives()
+    D = bt.get_derivatives(TENSORS)
+    for b in range(w.B):
+        dd = orcs[b].compute_derivatives(xs[b], us[b])
+        dq = orcs[b].compute_derivatives(xs[b], us[b], prec=1)
+        for f in TENSORS:
+            if dd[f].size:
+                e_ref = np.abs(dd[f] - dq[f]).max()
+                e_dev = np.abs(D[f][b] - dq[f]).max()
+                assert e_dev <= 8 * e_ref + 1e-7, (f, e_dev, e_ref)
+    bt.close()
+
+
+def check_backward(make, w):
+    """backward_pass on IDENTICAL derivative slabs (the oracle's) -> gains within 1e-9, same mu/reg/restarts."""
+    g, bt, us, orcs, rng = setup(make, w)
+    xs, _ = bt.get_trajectory()
+    mval = rng.uniform(-1, 1, (w.B, bt.ne_total))
+    mjac = g["mult_jac"]
+    bt.set_multipliers(mval, mjac)
+    ds = [orcs[b].compute_derivatives(xs[b], us[b]) for b in range(w.B)]
+    bt.set_derivatives({f: np.stack([ds[b][f] for b in range(w.B)]) for f in ol.DERIV_FIELDS})
+    D = bt.get_derivatives()
+    for b in range(w.B):
+        for f in ol.DERIV_FIELDS:
+            if f not in ("lfx", "lfxx"):
+                assert np.array_equal(D[f][b], ds[b][f]), f"slab round trip {f}"
+    restarts_seen = 0
+    for mu, reg in [(1e4, 0.0), (1e-3, 0.0), (10.0, 1.0)]:
+        mu_e, reg_e = bt.backward_pass(mu, reg)
+        _, k, K = bt.get_feedback()
+        for b in range(w.B):
+            ko, Ko, muo, rego, rs = orcs[b].backward_pass(ds[b], xs[b], mval[b], mjac[b], reg, mu)
+            restarts_seen += rs
+            assert mu_e[b] == muo and reg_e[b] == rego, (mu_e[b], muo, reg_e[b], rego)
+            assert relerr(k[b], ko) < TOL_GAINS and relerr(K[b], Ko) < TOL_GAINS, (relerr(k[b], ko), relerr(K[b], Ko))
+    bt.close()
+    return restarts_seen
+
+
+def check_forward(make, w):
+    """forward_pass / cost_seq_aug / optimality on identical gains and multipliers."""
+    g, bt, us, orcs, rng = setup(make, w)
+    xs, _ = bt.get_trajectory()
+    mval = rng.uniform(-1, 1, (w.B, bt.ne_total))
+    bt.set_multipliers(mval, g["mult_jac"])
+    ds = [orcs[b].compute_derivatives(xs[b], us[b]) for b in range(w.B)]
+    bt.set_derivatives({f: np.stack([ds[b][f] for b in range(w.B)]) for f in ol.DERIV_FIELDS})
+    mu_e, reg_e = bt.backward_pass(w.mu, 0.0)
+    bt.set_scalar("mu", mu_e)
+    step = bt.forward_pass()
+    xn, un = bt.get_new_trajectory()
+    _, k, K = bt.get_feedback()
+    mo, mv, mj = bt.get_multipliers()
+    co = bt.cost_seq_aug()
+    oo, oc = bt.optimality()
+    for b in range(w.B):
+        xo, uo, so, ro = orcs[b].forward_pass(xs[b], us[b], mo[b], mv[b], mj[b], k[b], K[b], mu_e[b])
+        assert step[b] == so, (step[b], so)
+        assert relerr(xn[b], xo) < TOL_ROLLOUT and relerr(un[b], uo) < TOL_ROLLOUT
+        cc = orcs[b].cost_seq_aug(xs[b], us[b], mo[b], mv[b], mj[b], mu_e[b])
+        assert relerr(co[b], cc) < TOL_ROLLOUT
+        a, c = orcs[b].optimality(ds[b], xs[b], mo[b], mv[b], mj[b], mu_e[b])
+        assert abs(oo[b] - a) <= 1e-10 * max(a, 1e-300) and abs(oc[b] - c) <= 1e-12 * max(c, 1.0)
+    bt.close()
+
+
+def check_solve(make, w, iters):
+    """End to end: same control flow as the double oracle and trajectories as close to the __float128 oracle
+    as the double oracle's own (the FD Hessians make 1e-8 unreachable for ANY two double implementations,
+    see DESIGN.md 'Parity')."""
+    g = w.generate()
+    bt = make(w)
+    bt.set_targets(g["targets"])
+    bt.make_trajectory(g["x0"])
+    bt.set_multipliers(None, g["mult_jac"])
+    sc = bt.solve(iters, w.mu)
+    xs, us = bt.get_trajectory()
+    stats = []
+    for b in range(w.B):
+        o = ol.from_workload(w, g["targets"][b])
+        xs0 = o.rollout(g["x0"][b], g["us"][b])
+        rd = o.solve(xs0, g["us"][b], g["mult_jac"][b], iters, w.mu)
+        rq = o.solve(xs0, g["us"][b], g["mult_jac"][b], iters, w.mu, prec=1)
+        e_dev_d = relerr(xs[b], rd["xs"]); e_d_q = relerr(rd["xs"], rq["xs"]); e_dev_q = relerr(xs[b], rq["xs"])
+        same_flow = (sc["mu"][b] == rd["log"][-1, 0] and sc["reg"][b] == rd["log"][-1, 1] and
+                     int(sc["rollouts"][b]) == int(rd["log"][:, 7].sum()) and int(sc["restarts"][b]) == int(rd["log"][:, 8].sum()))
+        stats.append(dict(b=b, dev_vs_double=e_dev_d, double_vs_quad=e_d_q, dev_vs_quad=e_dev_q, same_flow=same_flow))
+        assert int(sc["iterations"][b]) == iters
+    bt.close()
+    return stats

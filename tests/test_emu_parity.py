@@ -1,0 +1,44 @@
+"""Kernel arithmetic vs the oracle WITHOUT a GPU: the CTA bodies of csrc/*.cuh are compiled for the host and
+run one thread at a time (tests/hostemu).  Same checks as tests/test_gpu_parity.py."""
+import pytest
+
+import parity_cases as pc
+import hostemu_lib as he
+
+CASES = pc.cases()
+IDS = [c[0] for c in CASES]
+
+
+def make(w):
+    return he.EmuBatch.from_workload(w)
+
+
+@pytest.mark.parametrize("tag,w", CASES, ids=IDS)
+def test_linearization(tag, w):
+    pc.check_linearization(make, w)
+
+
+@pytest.mark.parametrize("tag,w", CASES, ids=IDS)
+def test_backward(tag, w):
+    pc.check_backward(make, w)
+
+
+@pytest.mark.parametrize("tag,w", CASES, ids=IDS)
+def test_forward(tag, w):
+    pc.check_forward(make, w)
+
+
+@pytest.mark.parametrize("tag,w", [c for c in CASES if c[0] in ("c2_chain2r", "c3_arm6r_terminal", "c5_arm7r_fdvalues", "c1_pendulum_fdvalues")],
+                         ids=lambda v: v if isinstance(v, str) else "")
+def test_tensors_vs_quad(tag, w):
+    pc.check_tensors_vs_quad(make, w)
+
+
+@pytest.mark.parametrize("name,T,iters", [("c2", 40, 6), ("c3", 20, 5), ("c4", 12, 4), ("c5", 10, 3)])
+def test_solve(name, T, iters):
+    w = pc.S.workload(name, B=3, T=T)
+    stats = pc.check_solve(make, w, iters)
+    for s in stats:
+        assert s["dev_vs_quad"] <= 50 * s["double_vs_quad"] + 1e-8, s
+        assert s["dev_vs_double"] <= 50 * s["double_vs_quad"] + 1e-8, s
+    assert sum(s["same_flow"] for s in stats) >= len(stats) - 1, stats
