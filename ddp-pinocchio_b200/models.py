@@ -131,4 +131,39 @@ def chain_nr(n, seed=7):
     return _chain(f"chain_{n}r_random", J, [("tip", n - 1, tuple(rng.uniform(-1, 1, 3)), tuple(rng.uniform(-0.2, 0.2, 3)))])
 
 
+def _rodrigues(a, q):
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + np.sin(q) * K + (1 - np.cos(q)) * (K @ K)
+
+
+def potential_energy(m, q):
+    """U(q) = -sum_i m_i g . p_com_i(q) of a serial chain (numpy forward kinematics; input generation only)."""
+    R, p, U = np.eye(3), np.zeros(3), 0.0
+    for i in range(m.n_joints):
+        p = p + R @ m.placement_trans[i]
+        R = R @ m.placement_rot[i] @ _rodrigues(m.axis[i], q[i])
+        U -= m.mass[i] * float(m.gravity @ (p + R @ m.com[i]))
+    return U
+
+
+def frame_position(m, q, frame):
+    """World position of an operational frame (numpy forward kinematics; input generation only)."""
+    R, p = np.eye(3), np.zeros(3)
+    for i in range(int(m.frame_parent[frame]) + 1):
+        p = p + R @ m.placement_trans[i]
+        R = R @ m.placement_rot[i] @ _rodrigues(m.axis[i], q[i])
+    return p + R @ m.frame_trans[frame]
+
+
+def gravity_torque(m, q, h=1e-6):
+    """tau = dU/dq: the static torque that holds the chain at q (hold-still initial control guess of the
+    synthetic workloads; central differences are plenty for an initial guess)."""
+    q = np.asarray(q, dtype=float)
+    g = np.zeros(m.n_joints)
+    for i in range(m.n_joints):
+        e = np.zeros(m.n_joints); e[i] = h
+        g[i] = (potential_energy(m, q + e) - potential_energy(m, q - e)) / (2 * h)
+    return g
+
+
 BY_NAME = {"pendulum": pendulum, "chain_2r": chain_2r, "arm_6r": arm_6r, "arm_7r": arm_7r}

@@ -44,6 +44,11 @@ class Workload:
     mu: float = 1e4
     reg: float = 0.0
     iterations: int = 10
+    # initial control guess: "zero" (the reference tests' zero-control generator, test/pendulum_ddp.cpp:70-82)
+    # or "hold" (static gravity compensation at q0, so a 1-2 s horizon does not start from a free fall)
+    init_controls: str = "hold"
+    v0_scale: float = 0.0
+    target_offset: float = 1.0
 
     @property
     def n(self):
@@ -70,28 +75,51 @@ class Workload:
         return ne
 
     def generate(self, B=None, first_problem=0):
-        """x0 [B,nx], us [B,T,nu] (zero controls), targets [B,sum ne], mult_jac [B, sum ne*ndx]."""
+        """Per-problem inputs: x0 [B,nx], us [B,T,nu], targets [B,sum ne], mult_jac [B, sum ne*ndx].
+
+        Chains: a rest-to-rest reaching task -- q0 ~ U(-pi/2, pi/2)^n, v0 = v0_scale * U(-0.5, 0.5)^n
+        (0 by default: a 1-2 s open-loop horizon of a free-falling arm is chaotic and sends a few percent of
+        the reference algorithm's mu/reg restart loops to infinity, see DESIGN.md "Workloads"), controls =
+        static gravity compensation at q0, goal configuration q* = q0 + target_offset * U(-1, 1)^n imposed on
+        q_T (config constraint) or its end-effector position FK(q*) (spatial constraint).
+        Pendulum: problem 0 is the reference scenario (x0 = 0, u = 0, q_T = 3.14, test/pendulum_ddp.cpp:50-58);
+        further problems start at q0 ~ U(-pi/2, pi/2)."""
         B = self.B if B is None else B
         n, T = self.n, self.T
         ne = self.ne_per_knot()
         net = int(ne.sum())
-        cnt = 2 * n + net + net * self.ndx + 3
+        nknots = int((ne > 0).sum())
+        cnt = 3 * n + net * self.ndx
         r = splitmix64(np.uint64(0xDD9) + np.arange(first_problem, first_problem + B, dtype=np.uint64), cnt)
         q0 = (r[:, :n] - 0.5) * np.pi
-        v0 = r[:, n:2 * n] - 0.5
-        x0 = np.concatenate([q0, v0], axis=1)
-        tg = 2.0 * r[:, 2 * n:2 * n + net] - 1.0
-        if self.eq_kind == EQ_SPATIAL:
-            tg = 0.3 * tg  # reachable end-effector targets around the origin
-        mj = 2.0 * r[:, 2 * n + net:2 * n + net + net * self.ndx] - 1.0
+        v0 = (r[:, n:2 * n] - 0.5) * self.v0_scale
+        dq = (2.0 * r[:, 2 * n:3 * n] - 1.0) * self.target_offset
+        mj = 2.0 * r[:, 3 * n:3 * n + net * self.ndx] - 1.0
         us = np.zeros((B, T, self.nu))
+        if self.model.kind == models.KIND_PENDULUM:
+            qstar = np.full((B, 1), 3.14) + dq * (np.arange(first_problem, first_problem + B)[:, None] > 0)
+            q0 = q0 * (np.arange(first_problem, first_problem + B)[:, None] > 0)
+            v0 = v0 * 0.0
+        else:
+            qstar = q0 + dq
+            if self.init_controls == "hold":
+                for b in range(B):
+                    us[b, :, :] = models.gravity_torque(self.model, q0[b])[None, :]
+        if self.eq_kind == EQ_SPATIAL:
+            one = np.stack([models.frame_position(self.model, qstar[b], self.frame) for b in range(B)])
+        elif self.eq_kind == EQ_CONFIG:
+            one = qstar
+        else:
+            one = np.zeros((B, 0))
+        tg = np.tile(one, (1, nknots)) if net else np.zeros((B, 0))
+        x0 = np.concatenate([q0, v0], axis=1)
         return dict(x0=np.ascontiguousarray(x0), us=us, targets=np.ascontiguousarray(tg), mult_jac=np.ascontiguousarray(mj), ne=ne)
 
 
 def workload(name, B=None, T=None):
     """The five BASELINE.json configs (C1..C5) by short name."""
     if name == "c1":   # pendulum DDP, single problem (test/pendulum_ddp.cpp)
-        w = Workload("c1_pendulum", models.pendulum(), 1, 200, hess_mode=HESS_FD_VALUES)
+        w = Workload("c1_pendulum", models.pendulum(), 1, 200, hess_mode=HESS_FD_VALUES, init_controls="zero")
     elif name == "c2":  # synthetic 2R "double pendulum", 4096 x 200
         w = Workload("c2_chain2r_4096x200", models.chain_2r(), 4096, 200)
     elif name == "c3":  # 6R UR5-style arm, 1024 x 100, analytic first order + FD-of-Jacobians Hessians
