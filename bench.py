@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched DDP hot path (linearize + backward pass + line-search rollouts).
+
+One "step" = one complete fixed-iteration DDP solve (ddp_solver_t::solve, ddp.hpp:744-842, `iterations`
+iterations + the reference's warm-up pass) of the whole synthetic batch from its initial trajectory.
+  value : knots linearized/s = B_total * T * iterations * steps / time, inputs already resident in HBM
+          (a device-side snapshot is restored at the start of every step), CUDA events on the launching stream;
+  e2e   : the same metric through the C ABI with HOST (pinned) inputs: x0 / controls / targets / multiplier
+          seeds go host->device, the initial rollout runs, the solve runs, and per-problem scalars plus the
+          final trajectory come back device->host, every step.
+N > 1: one process per GPU (torchrun), independent problem shards (weak scaling), NCCL only gathers the
+per-problem scalars.  `--impl reference` times the CPU oracle restatement of the reference path instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ddpb_loader  # noqa: E402
+
+ddpb_loader.load()
+from ddp_pinocchio_b200 import synthetic  # noqa: E402
+
+METRIC = "DDP iterations/sec (batch x horizon knots linearized/sec)"
+
+
+def algorithmic_bytes_per_knot(w):
+    """bytes one linearization must write / one backward step must read, per knot."""
+    nd, nu, nx = w.ndx, w.nu, w.nx
+    ne = w.ne_per_knot().astype(np.int64)
+    slab = (nd + nu + nd * nd + nu * nd + nu * nu) + (nx + nd * nd + nd * nu + nd ** 3 + nd * nd * nu + nd * nu * nu) + \
+        ne * (1 + nd + nu + nd * nd + nu * nd + nu * nu)
+    lin = 8.0 * (slab + nx + nu)
+    bwd = 8.0 * (slab + 2 * nx + ne + ne * nd + nu + nu * nd)
+    return float(lin.mean()), float(bwd.mean())
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def calibrate_cpu_sample(ol, w, nthreads, target_s):
+    """Number of problems the CPU path solves in about `target_s` seconds of wall time on `nthreads` threads."""
+    g = w.generate(B=nthreads)
+    sec, _ = ol.solve_batch(w, g, nthreads, nthreads, w.iterations, w.mu)
+    n = int(max(nthreads, min(w.B, nthreads * round(target_s / max(sec, 1e-3)))))
+    return n
+
+
+def run_reference(args, w, rank):
+    """The reference's own CPU path (restated by oracle/; the reference cannot be compiled here)
+    on all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import oracle_lib as ol
+    nthreads = os.cpu_count() or 1
+    nprob = args.cpu_sample or calibrate_cpu_sample(ol, w, nthreads, 5.0)
+    g = w.generate(B=nprob)
+    for _ in range(args.warmup):
+        ol.solve_batch(w, g, min(nprob, nthreads), nthreads, 1, w.mu)
+    t = 0.0
+    ro = rs = 0
+    for _ in range(args.steps):
+        sec, info = ol.solve_batch(w, g, nprob, nthreads, w.iterations, w.mu)
+        t += sec; ro += info["rollouts"]; rs += info["restarts"]
+    val = nprob * w.T * w.iterations * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "knots/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "ddp_iterations_per_sec": nprob * w.iterations * args.steps / t,
+            "config": {"workload": w.name, "problems": nprob, "horizon": w.T, "iterations_per_step": w.iterations},
+            "cpu_baseline": {"value": val, "unit": "knots/s", "cores": nthreads, "kind": "port",
+                             "sample": f"{nprob} of {w.B} problems x {w.T} knots x {w.iterations} iterations per step, OpenMP over problems"},
+            "e2e": {"value": val, "unit": "knots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "rollouts_per_iteration": ro / (nprob * w.iterations * args.steps), "backward_restarts_per_problem": rs / (nprob * args.steps)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", help="c1..c5 (BASELINE.json configs); default configs[1]")
+    ap.add_argument("--batch", type=int, default=None, help="problems per GPU (default: the config's batch)")
+    ap.add_argument("--cpu-sample", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    w = synthetic.workload(args.workload)
+    if args.batch:
+        w.B = args.batch
+    elif args.workload == "c5":
+        w.B = 1024  # 8192 problems over 8 GPUs = 1024 per GPU
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ddp_pinocchio_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, T, its = w.B, w.T, w.iterations
+    g = w.generate(first_problem=rank * B)  # weak scaling: every rank owns its own B problems
+    bt = capi.Batch.from_workload(w, device=local)
+    stream = torch.cuda.Stream(device=local)
+    bt.set_stream(stream.cuda_stream)
+    # pinned host inputs / outputs for the e2e leg
+    pins = []
+
+    def pin(a):
+        arr, p = capi.host_alloc(a.nbytes)
+        pins.append(p)
+        arr = arr.reshape(a.shape)
+        arr[...] = a
+        return arr
+    h_x0, h_us, h_tg, h_mj = pin(g["x0"]), pin(g["us"]), pin(g["targets"]) if g["targets"].size else g["targets"], \
+        pin(g["mult_jac"]) if g["mult_jac"].size else g["mult_jac"]
+    h2d = h_x0.nbytes + h_us.nbytes + h_tg.nbytes + h_mj.nbytes
+    d2h = (capi.NSCALARS * B + B * (T + 1) * w.nx + B * T * w.nu) * 8
+
+    def e2e_step():
+        bt.set_targets(h_tg)
+        bt.make_trajectory(h_x0, h_us)
+        bt.set_multipliers(None, h_mj)
+        sc = bt.solve(its, w.mu)
+        xs, us = bt.get_trajectory()
+        return sc, xs
+
+    # resident leg: snapshot once, restore per step
+    bt.set_targets(h_tg); bt.make_trajectory(h_x0, h_us); bt.set_multipliers(None, h_mj)
+    bt.snapshot_save()
+    scal_ptr = bt.scalars_device_ptr()
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (capi.NSCALARS * B,), "typestr": "<f8", "data": (scal_ptr, False), "version": 3}
+    scal_t = torch.as_tensor(_Holder(), device=torch.device("cuda", local))
+    gathered = torch.empty(world * capi.NSCALARS * B, dtype=torch.float64, device=scal_t.device) if world > 1 else None
+
+    def resident_step():
+        bt.snapshot_restore()
+        bt.solve(its, w.mu, read_back=False)
+        if world > 1:  # the path's only exchange: per-problem cost / merit / convergence scalars
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, scal_t)
+
+    def barrier():
+        bt.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    bt.enable_phase_timing(True)
+    l0 = bt.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        resident_step()
+    ev1.record(stream)
+    barrier()
+    launches = bt.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    phases = bt.phase_times()
+    bt.enable_phase_timing(False)
+    sc = bt.get_scalars()
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e leg (host buffers in, results out), wall clock bracketed by synchronisation
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sc_e2e, _ = e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=scal_t.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tt[0]), float(tt[1])
+    if rank == 0:
+        knots_per_step = world * B * T * its
+        value = knots_per_step * args.steps / (ms * 1e-3)
+        e2e_val = knots_per_step * args.steps / (e2e_ms * 1e-3)
+        hbm_peak, peak_src = read_peaks()
+        lin_b, bwd_b = algorithmic_bytes_per_knot(w)
+        n_lin = n_bwd = (its + 1) * args.steps  # launches in the timed region (incl. the warm-up pass of every solve)
+        kern = {
+            "linearize": {"ms_avg": phases["linearize"] / n_lin, "alg_bytes": lin_b * B * T},
+            "backward": {"ms_avg": phases["backward"] / n_bwd, "alg_bytes": bwd_b * B * T},
+            "forward": {"ms_avg": phases["forward"] / n_bwd, "alg_bytes": None},
+        }
+        dom = max(("linearize", "backward", "forward"), key=lambda k: phases[k])
+        share = {k: phases[k] / max(sum(phases.values()), 1e-9) for k in phases}
+        rk = kern[dom if kern[dom]["alg_bytes"] else "backward"]
+        rname = dom if kern[dom]["alg_bytes"] else "backward"
+        achieved = rk["alg_bytes"] / (rk["ms_avg"] * 1e-3) / 1e9
+        fp64_peak = capi.measure_fp64_peak(local)
+        line = {
+            "metric": METRIC, "value": value, "unit": "knots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "ddp_iterations_per_sec": world * B * its * args.steps / (ms * 1e-3),
+            "config": {"workload": w.name, "problems_per_gpu": B, "horizon": T, "iterations_per_step": its, "nx": w.nx, "nu": w.nu,
+                       "hess_mode": "fd_of_jacobians" if w.hess_mode == 0 else "fd_of_values", "mu": w.mu,
+                       "l2": "working set (derivative slabs %.2f GB per GPU) is larger than L2" % (lin_b * B * T / 1e9),
+                       "parallelism": f"dp{world} (independent problem shards, NCCL gathers per-problem scalars only)"},
+            "e2e": {"value": e2e_val, "unit": "knots/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps, "timer": "wall clock between synchronisations"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": rname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic bytes per launch (BASELINE.md s3) / mean CUDA-event launch duration in the timed region"},
+            "kernels": {k: {"ms_avg": v["ms_avg"], "share_of_step": share[k],
+                            "hbm_gbs": (v["alg_bytes"] / (v["ms_avg"] * 1e-3) / 1e9) if v["alg_bytes"] else None} for k, v in kern.items()},
+            "fp64_peak_tflops_measured": fp64_peak,
+            "rollouts_per_iteration": float(sc["rollouts"].mean() / its), "backward_restarts_per_problem": float(sc["restarts"].mean()),
+            "opt_constr_median": float(np.median(sc["opt_constr"])),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            import oracle_lib as ol
+            nthreads = os.cpu_count() or 1
+            nprob = args.cpu_sample or calibrate_cpu_sample(ol, w, nthreads, 10.0)
+            gs = w.generate(B=nprob)
+            sec, info = ol.solve_batch(w, gs, nprob, nthreads, its, w.mu)
+            line["cpu_baseline"] = {"value": nprob * T * its / sec, "unit": "knots/s", "cores": nthreads, "kind": "port",
+                                    "sample": f"{nprob} of {B} problems x {T} knots x {its} iterations, OpenMP over problems, {sec:.1f} s"}
+        print(json.dumps(line), flush=True)
+    bt.close()
+    for p in pins:
+        capi.host_free(p)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,8 @@ EXPORTS = ["ddpb_model_create", "ddpb_model_destroy", "ddpb_batch_create", "ddpb
            "ddpb_set_feedback", "ddpb_get_feedback", "ddpb_set_derivatives", "ddpb_get_derivatives", "ddpb_set_scalar",
            "ddpb_get_scalars", "ddpb_scalars_device_ptr", "ddpb_compute_derivatives", "ddpb_backward_pass", "ddpb_forward_pass",
            "ddpb_cost_seq_aug", "ddpb_optimality", "ddpb_solve", "ddpb_solve_async", "ddpb_batch_dims", "ddpb_launch_count",
-           "ddpb_phase_times", "ddpb_enable_phase_timing"]
+           "ddpb_phase_times", "ddpb_enable_phase_timing", "ddpb_snapshot_save", "ddpb_snapshot_restore",
+           "ddpb_measure_fp64_peak"]
 
 
 class DdpbError(RuntimeError):
@@ -280,6 +281,12 @@ class Batch(BatchBase):
         _check(lib().ddpb_solve(self._h, C.byref(sp), _d(out)))
         return {nm: out[i].copy() for i, nm in enumerate(SCALAR_FIELDS)}
 
+    def snapshot_save(self):
+        _check(lib().ddpb_snapshot_save(self._h))
+
+    def snapshot_restore(self):
+        _check(lib().ddpb_snapshot_restore(self._h))
+
     # ---- introspection ----
     def launch_count(self):
         return int(lib().ddpb_launch_count(self._h))
@@ -291,3 +298,21 @@ class Batch(BatchBase):
         ms = (C.c_float * 4)()
         _check(lib().ddpb_phase_times(self._h, ms))
         return dict(linearize=ms[0], backward=ms[1], forward=ms[2], other=ms[3])
+
+
+def measure_fp64_peak(device=0):
+    v = C.c_double()
+    _check(lib().ddpb_measure_fp64_peak(device, C.byref(v)))
+    return v.value
+
+
+def host_alloc(nbytes):
+    """Pinned host buffer (numpy float64 view) for the H2D / D2H transfers."""
+    p = C.c_void_p()
+    _check(lib().ddpb_host_alloc(C.byref(p), C.c_ulonglong(nbytes)))
+    arr = np.ctypeslib.as_array(C.cast(p, _dp), shape=(nbytes // 8,))
+    return arr, p
+
+
+def host_free(p):
+    _check(lib().ddpb_host_free(p))

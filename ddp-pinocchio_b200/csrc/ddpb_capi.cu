@@ -27,6 +27,21 @@ __global__ void post_forward_kernel(const __grid_constant__ BatchDev bd) {
   if (b >= bd.B) return;
   post_forward_problem(bd, b);
 }
+// 16 independent FMA chains per thread: saturates the FP64 pipe
+__global__ void fp64_peak_kernel(double* out, int iters) {
+  double a[16];
+  const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-9 * blockIdx.x;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = k * 0.5;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
 __global__ void scalar_copy_kernel(double* scal, int B, int dst, int src) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) scal[(size_t)dst * B + b] = scal[(size_t)src * B + b];
@@ -111,6 +126,7 @@ struct ddpb_batch {
   double* stage = nullptr;
   size_t stage_bytes = 0;
   double* h_stage = nullptr;  // pinned bounce buffer for small scalar traffic
+  double* snap = nullptr;     // device-resident snapshot: xs | us | m_origin | m_val | m_jac
   unsigned long long launches = 0;
   bool timing = false;
   std::vector<PhaseEv> events;
@@ -591,6 +607,64 @@ int ddpb_optimality(ddpb_batch* h, double* opt_obj, double* opt_constr) {
   if (opt_obj) CU(cudaMemcpyAsync(opt_obj, h->bd.scal + (size_t)S_OPT_OBJ * B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (opt_constr) CU(cudaMemcpyAsync(opt_constr, h->bd.scal + (size_t)S_OPT_CONSTR * B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+
+static size_t snap_layout(const BatchDev& bd, size_t* off) {
+  const size_t B = bd.B, T = bd.T, nx = bd.nx, nu = bd.nu, net = bd.ne_total;
+  off[0] = 0; off[1] = off[0] + (T + 1) * nx * B; off[2] = off[1] + T * nu * B; off[3] = off[2] + T * nx * B;
+  off[4] = off[3] + net * B; off[5] = off[4] + net * nx * B;
+  return off[5];
+}
+int ddpb_snapshot_save(ddpb_batch* h) {
+  ENTER(h);
+  const BatchDev& bd = h->bd;
+  size_t off[6];
+  const size_t total = snap_layout(bd, off);
+  if (!h->snap) { int rc = dev_alloc(h, &h->snap, total); if (rc) return rc; }
+  double* src[5] = {bd.xs, bd.us, bd.m_origin, bd.m_val, bd.m_jac};
+  for (int k = 0; k < 5; ++k)
+    if (off[k + 1] > off[k]) CU(cudaMemcpyAsync(h->snap + off[k], src[k], (off[k + 1] - off[k]) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+int ddpb_snapshot_restore(ddpb_batch* h) {
+  ENTER(h);
+  const BatchDev& bd = h->bd;
+  if (!h->snap) return fail(DDPB_ERR_INVALID, "no snapshot saved");
+  size_t off[6];
+  snap_layout(bd, off);
+  double* dst[5] = {bd.xs, bd.us, bd.m_origin, bd.m_val, bd.m_jac};
+  for (int k = 0; k < 5; ++k)
+    if (off[k + 1] > off[k]) CU(cudaMemcpyAsync(dst[k], h->snap + off[k], (off[k + 1] - off[k]) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  // the new-trajectory storage is a clone of the trajectory (ddp.hpp:752)
+  CU(cudaMemcpyAsync(bd.xs_new, h->snap + off[0], (off[1] - off[0]) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(bd.us_new, h->snap + off[1], (off[2] - off[1]) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return DDPB_OK;
+}
+int ddpb_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(DDPB_ERR_INVALID, "null output");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr;
+  CU(cudaMalloc((void**)&d, sizeof(double)));
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CU(cudaEventRecord(a));
+    fp64_peak_kernel<<<blocks, threads>>>(d, iters);
+    CU(cudaEventRecord(b));
+    CU(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    const double tf = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  *tflops = best;
   return DDPB_OK;
 }
 

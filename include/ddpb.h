@@ -152,6 +152,13 @@ int ddpb_solve(ddpb_batch* b, const ddpb_solver_params* p, double* scalars_out /
 /* same, without the final synchronisation / read-back (for stream-ordered use and CUDA-event timing) */
 int ddpb_solve_async(ddpb_batch* b, const ddpb_solver_params* p);
 
+/* ---- device-resident restart (bench / repeated solves without host traffic) ------------------ */
+/* keep a device-side copy of the current trajectory and multipliers / copy it back */
+int ddpb_snapshot_save(ddpb_batch* b);
+int ddpb_snapshot_restore(ddpb_batch* b);
+/* FP64 FMA micro-benchmark on `device` (2 flops per DFMA), TFLOP/s: the denominator of the FP64 roofline */
+int ddpb_measure_fp64_peak(int device, double* tflops);
+
 /* ---- introspection ----------------------------------------------------------------------- */
 int ddpb_batch_dims(const ddpb_batch* b, int* out /* nq, nx, ndx, nu, ne_total, T, B */);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */

@@ -171,7 +171,7 @@ def check_solve(make, w, iters):
     g = w.generate()
     bt = make(w)
     bt.set_targets(g["targets"])
-    bt.make_trajectory(g["x0"])
+    bt.make_trajectory(g["x0"], g["us"])
     bt.set_multipliers(None, g["mult_jac"])
     sc = bt.solve(iters, w.mu)
     xs, us = bt.get_trajectory()

@@ -54,7 +54,7 @@ def test_gpu_matches_cpu_emulation_of_same_kernels():
     outs = []
     for mk in (make, he.EmuBatch.from_workload):
         bt = mk(w)
-        bt.set_targets(g["targets"]); bt.make_trajectory(g["x0"]); bt.compute_derivatives()
+        bt.set_targets(g["targets"]); bt.make_trajectory(g["x0"], g["us"]); bt.compute_derivatives()
         outs.append(bt.get_derivatives(["fx", "fu", "f_val", "eq_x"]))
         bt.close()
     for f in outs[0]:

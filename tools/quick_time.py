@@ -12,7 +12,7 @@ for name, B in [(a.split(":")[0], int(a.split(":")[1]) if ":" in a else None) fo
     bt = capi.Batch.from_workload(w)
     bt.set_targets(g["targets"])
     for rep in range(2):
-        bt.make_trajectory(g["x0"]); bt.set_multipliers(None, g["mult_jac"])
+        bt.make_trajectory(g["x0"], g["us"]); bt.set_multipliers(None, g["mult_jac"])
         bt.enable_phase_timing(True)
         t0 = time.time(); sc = bt.solve(w.iterations, w.mu); wall = time.time() - t0
         ph = bt.phase_times()
