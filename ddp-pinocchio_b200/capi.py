@@ -37,7 +37,7 @@ class ModelDescC(C.Structure):
 
 class ParamsC(C.Structure):
     _fields_ = [("dt", C.c_double), ("c", C.c_double), ("hess_mode", C.c_int), ("eq_kind", C.c_int), ("frame_id", C.c_int),
-                ("frame_jac_mode", C.c_int)]
+                ("frame_jac_mode", C.c_int), ("max_backward_restarts", C.c_int)]
 
 
 class SolverParamsC(C.Structure):
@@ -122,14 +122,15 @@ class BatchBase:
 class Batch(BatchBase):
     """B independent DDP problems resident on one GPU (ddpb_batch)."""
 
-    def __init__(self, model, B, T, ne_per_knot=None, dt=0.01, c=1.0, hess_mode=0, eq_kind=0, frame_id=0, jac_mode=0, device=0):
+    def __init__(self, model, B, T, ne_per_knot=None, dt=0.01, c=1.0, hess_mode=0, eq_kind=0, frame_id=0, jac_mode=0, device=0,
+                 max_restarts=0):
         L = lib()
         self._keep = []
         self._init_dims(model, B, T, ne_per_knot, eq_kind)
         md = model_desc_c(model, self._keep)
         self._m = C.c_void_p()
         _check(L.ddpb_model_create(C.byref(md), C.byref(self._m)))
-        pr = ParamsC(dt, c, hess_mode, eq_kind, frame_id, jac_mode)
+        pr = ParamsC(dt, c, hess_mode, eq_kind, frame_id, jac_mode, max_restarts)
         self._h = C.c_void_p()
         rc = L.ddpb_batch_create(self._m, B, T, _i(self.ne), C.byref(pr), device, C.byref(self._h))
         if rc != 0:
@@ -138,9 +139,9 @@ class Batch(BatchBase):
             _check(rc)
 
     @classmethod
-    def from_workload(cls, w, B=None, device=0):
+    def from_workload(cls, w, B=None, device=0, max_restarts=None):
         return cls(w.model, w.B if B is None else B, w.T, w.ne_per_knot(), dt=w.dt, c=w.c, hess_mode=w.hess_mode, eq_kind=w.eq_kind,
-                   frame_id=w.frame, jac_mode=w.jac_mode, device=device)
+                   frame_id=w.frame, jac_mode=w.jac_mode, device=device, max_restarts=w.max_restarts if max_restarts is None else max_restarts)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -255,6 +255,11 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       ex.sync();
     }
     if (!failed) success = true;
+    else if (bd.max_restarts > 0 && (restarts > bd.max_restarts || !(mu < 1.79e308))) {
+      // guarded mode: this problem's Q_uu cannot be made positive definite by the reference's mu/reg schedule
+      if (tid == 0) bd.scal[(size_t)S_STATUS * B + b] = 2.0;
+      break;
+    }
   }
   if (tid == 0) {
     bd.scal[(size_t)S_MU * B + b] = mu;

@@ -51,6 +51,7 @@ struct BatchDev {
   int B, T, n, nx, nu;         // nx = ndx = 2n, nu = n
   int hess_mode, eq_kind, frame_id, jac_mode;
   int ne_max, ne_total;
+  int max_restarts, pad_;             // 0 = unbounded restarts (reference behaviour)
   double dt, c;
   double *xs, *us, *xs_new, *us_new;  // [(T+1)][nx][B], [T][nu][B]
   double* targets;                    // [ne_total][B]

@@ -343,6 +343,10 @@ DDPB_HD void post_forward_problem(const BatchDev& bd, int b) {
   const int B = bd.B;
   if (bd.scal[(size_t)S_STATUS * B + b] != 0.0) return;
   double reg = bd.scal[(size_t)S_REG * B + b];
+  if (bd.max_restarts > 0) {
+    const double merit = bd.scal[(size_t)S_MERIT * B + b], mu = bd.scal[(size_t)S_MU * B + b];
+    if (!(merit == merit) || !(fabs(merit) < 1.79e308) || !(mu < 1.79e308)) { bd.scal[(size_t)S_STATUS * B + b] = 2.0; return; }
+  }
   if (bd.scal[(size_t)S_STEP * B + b] >= 0.5) {
     reg /= 2.0;
     if (reg < 1e-5) reg = 0.0;

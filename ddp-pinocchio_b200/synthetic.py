@@ -48,6 +48,9 @@ class Workload:
     # or "hold" (static gravity compensation at q0, so a 1-2 s horizon does not start from a free fall)
     init_controls: str = "hold"
     v0_scale: float = 0.0
+    # guarded mode (ddpb_params.max_backward_restarts): a problem whose backward pass needs more than this many
+    # mu-doubling restarts is marked diverged instead of looping to mu = inf (0 = reference behaviour)
+    max_restarts: int = 64
     target_offset: float = 1.0
 
     @property

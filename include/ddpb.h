@@ -72,6 +72,11 @@ typedef struct ddpb_params {
   int eq_kind;        /* ddpb_eq_kind */
   int frame_id;       /* DDPB_EQ_SPATIAL: constrained frame (test/pinocchio_spatial_eq_ddp.cpp:81) */
   int frame_jac_mode; /* ddpb_frame_jac_mode */
+  /* 0 = the reference's behaviour: after a failed Cholesky the backward pass doubles mu and restarts, without
+   * bound (ddp_bwd.ipp:105-132), and a problem whose mu overflowed keeps producing NaN trajectories.
+   * N > 0 = guarded mode: a problem that needs more than N restarts in ONE backward pass, or whose mu / merit
+   * stop being finite, gets status 2 (diverged) and is left untouched from then on. */
+  int max_backward_restarts;
 } ddpb_params;
 
 /* solver_parameters_t (ddp.hpp:42-50) */
@@ -93,7 +98,7 @@ enum ddpb_scalar_field {
   DDPB_S_COST,       /* sum_t l(t,x,u) of the current trajectory */
   DDPB_S_MERIT,      /* sum_t cost_seq_aug of the accepted trajectory (ddp.hpp:699-735) */
   DDPB_S_ITERATIONS, /* DDP iterations completed */
-  DDPB_S_STATUS,     /* 0 running / max iterations, 1 optimum attained */
+  DDPB_S_STATUS,     /* 0 running / max iterations, 1 optimum attained, 2 diverged (guarded mode only) */
   DDPB_S_ROLLOUTS,   /* line-search rollouts (cumulative) */
   DDPB_S_RESTARTS,   /* backward-pass restarts after a failed Cholesky (cumulative) */
   DDPB_S_MULT_UPDATES,

@@ -876,6 +876,7 @@ template <class S> struct Problem {
   S c = S(1);                      // cost weight, l = c/2 |u|^2 (problem.hpp:936-942)
   int eq_kind = EQ_NONE;
   int frame = 0, jac_mode = FJ_WORLD;
+  int max_restarts = 0;            // guarded mode of the product (ddpb_params.max_backward_restarts); 0 = reference behaviour
   Targets<S> targets;              // base indices [2, T+2)
   // constraint chain advance(advance(inner))
   Fn<S>* inner = nullptr;
@@ -1002,7 +1003,7 @@ template <class S> struct AffineSeq {
 // ----------------------------------------------------------------------------------
 // backward_pass (ddp_bwd.ipp:9-155)
 // ----------------------------------------------------------------------------------
-template <class S> struct BwdResult { S mu, reg; int restarts; };
+template <class S> struct BwdResult { S mu, reg; int restarts; bool diverged; };
 
 // in-place lower Cholesky (Eigen::LLT unblocked kernel semantics: fails when a pivot <= 0)
 template <class S> inline bool llt_inplace(S* A, int n) {  // col-major, lower
@@ -1040,7 +1041,9 @@ inline BwdResult<S> backward_pass(const Problem<S>& p, const Derivs<S>& d, const
   std::vector<S> Vxx(nd * nd), Vx(nd), Qx(nd), Qu(nu), Qxx(nd * nd), Quu(nu * nu), Qux(nu * nd), tmpM(nd * nd), A(nu * nu), rhs(nu);
   int restarts = 0;
   bool success = false;
+  bool diverged = false;
   while (!success) {
+    bool failed = false;
     for (int k = 0; k < nd * nd; ++k) Vxx[k] = d.lfxx[k];
     for (int k = 0; k < nd; ++k) Vx[k] = d.lfx[k];
     for (int t = T - 1; t >= 0; --t) {
@@ -1161,6 +1164,7 @@ inline BwdResult<S> backward_pass(const Problem<S>& p, const Derivs<S>& d, const
         mu *= S(2);
         reg *= S(2);
         ++restarts;
+        failed = true;
         break;
       }
       for (int k = 0; k < nx; ++k) fb.origin[t * nx + k] = xs[t * nx + k];
@@ -1188,8 +1192,9 @@ inline BwdResult<S> backward_pass(const Problem<S>& p, const Derivs<S>& d, const
         }
       if (t == 0) success = true;
     }
+    if (failed && p.max_restarts > 0 && (restarts > p.max_restarts || !(mu < S(1.79e308)))) { diverged = true; break; }
   }
-  return {mu, reg, restarts};
+  return {mu, reg, restarts, diverged};
 }
 
 // ----------------------------------------------------------------------------------
@@ -1212,7 +1217,7 @@ inline void cost_seq_aug(const Problem<S>& p, S* out /* T+1 */, const S* xs, con
   out[T] = S(0);  // lf = 0 (problem.hpp:932-935)
 }
 
-template <class S> struct FwdResult { S step; int rollouts; };
+template <class S> struct FwdResult { S step; int rollouts; S merit; };
 
 template <class S>
 inline FwdResult<S> forward_pass(const Problem<S>& p, S* xs_new, S* us_new, const S* xs, const S* us, const AffineSeq<S>& mults,
@@ -1223,6 +1228,7 @@ inline FwdResult<S> forward_pass(const Problem<S>& p, S* xs_new, S* us_new, cons
   S step = S(1);
   bool success = false;
   int rollouts = 0;
+  S merit = S(0);
   while (!success) {
     if (step < S(1e-10)) break;
     ++rollouts;
@@ -1241,14 +1247,15 @@ inline FwdResult<S> forward_pass(const Problem<S>& p, S* xs_new, S* us_new, cons
     if (do_linesearch) {
       cost_seq_aug(p, c_new.data(), xs_new, us_new, mults, mu);
       S sum = S(0);
-      for (int t = 0; t <= T; ++t) sum += c_new[t] - c_old[t];
+      merit = S(0);
+      for (int t = 0; t <= T; ++t) { sum += c_new[t] - c_old[t]; merit += c_new[t]; }
       if (sum <= S(0)) success = true;
       else step *= S(0.5);
     } else {
       success = true;
     }
   }
-  return {step, rollouts};
+  return {step, rollouts, merit};
 }
 
 // ----------------------------------------------------------------------------------
@@ -1394,10 +1401,11 @@ inline void solve(const Problem<S>& p, const SolverParams<S>& sp, const S* xs0, 
   compute_derivatives(p, d, xs.data(), us.data());
   BwdResult<S> b = backward_pass(p, d, xs.data(), mults, fb, reg, mu);
   mu = b.mu;  // reg from the warm-up pass is NOT taken (ddp.hpp:771)
-  forward_pass(p, xs_new.data(), us_new.data(), xs.data(), us.data(), mults, fb, mu, true);
   R.status = 0;
+  if (b.diverged) R.status = 2;
+  else forward_pass(p, xs_new.data(), us_new.data(), xs.data(), us.data(), mults, fb, mu, true);
   int iter = 0;
-  for (; iter < sp.max_iterations; ++iter) {
+  for (; iter < sp.max_iterations && R.status != 2; ++iter) {
     IterLog<S> lg{};
     int rv = update_derivatives(p, d, fb, mults, xs.data(), us.data(), mu, w, n, sp.thr, &lg.opt_obj, &lg.opt_constr);
     lg.mult_update = rv;
@@ -1416,7 +1424,11 @@ inline void solve(const Problem<S>& p, const SolverParams<S>& sp, const S* xs0, 
     mu = b.mu;
     reg = b.reg;
     lg.restarts = b.restarts;
+    if (b.diverged) { R.status = 2; R.log.push_back(lg); break; }
     FwdResult<S> f = forward_pass(p, xs_new.data(), us_new.data(), xs.data(), us.data(), mults, fb, mu, true);
+    if (p.max_restarts > 0 && (!(f.merit == f.merit) || !(f.merit < S(1.79e308)) || !(-f.merit < S(1.79e308)) || !(mu < S(1.79e308)))) {
+      R.status = 2; R.log.push_back(lg); break;  // guarded mode: the trial trajectory is not swapped in
+    }
     if (f.step >= S(0.5)) {
       reg /= S(2);
       if (reg < S(1e-5)) reg = S(0);

@@ -41,6 +41,7 @@ struct orc_problem_desc {
   int eq_kind, frame, jac_mode;
   const int* ne_per_knot;         // T (knot t constrains the state two steps later)
   const double* targets;          // sum(ne) packed per knot
+  int max_restarts;               // guarded mode (0 = reference behaviour)
 };
 struct orc_derivs {
   double *lfx, *lfxx, *lx, *lu, *lxx, *lux, *luu, *f_val, *fx, *fu, *fxx, *fux, *fuu, *eq_val, *eq_x, *eq_u, *eq_xx, *eq_ux, *eq_uu;
@@ -86,6 +87,7 @@ template <class S> static void fill_problem(Problem<S>& p, const orc_model_desc*
   p.eq_kind = d->eq_kind;
   p.frame = d->frame;
   p.jac_mode = d->jac_mode;
+  p.max_restarts = d->max_restarts;
   p.targets.t_begin = 2;
   p.targets.t_end = d->T + 2;
   p.targets.ne.assign(d->T, 0);

@@ -63,6 +63,7 @@ void* emu_create(const ddpb_model_desc* d, int B, int T, const int* ne_per_knot,
   bd.B = B; bd.T = T; bd.n = n; bd.nx = 2 * n; bd.nu = n;
   bd.hess_mode = p->hess_mode; bd.eq_kind = p->eq_kind; bd.frame_id = p->frame_id; bd.jac_mode = p->frame_jac_mode;
   bd.dt = p->dt; bd.c = p->c;
+  bd.max_restarts = p->max_backward_restarts < 0 ? 0 : p->max_backward_restarts;
   h->ne.assign(T, 0); h->eq_off.assign(T + 1, 0); h->slab_off.assign(T + 1, 0);
   for (int t = 0; t < T; ++t) {
     const int ne = (p->eq_kind == DDPB_EQ_NONE || !ne_per_knot) ? 0 : ne_per_knot[t];

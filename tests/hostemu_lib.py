@@ -38,18 +38,19 @@ def lib():
 
 
 class EmuBatch(capi.BatchBase):
-    def __init__(self, model, B, T, ne_per_knot=None, dt=0.01, c=1.0, hess_mode=0, eq_kind=0, frame_id=0, jac_mode=0, device=0):
+    def __init__(self, model, B, T, ne_per_knot=None, dt=0.01, c=1.0, hess_mode=0, eq_kind=0, frame_id=0, jac_mode=0, device=0,
+                 max_restarts=0):
         self._keep = []
         self._init_dims(model, B, T, ne_per_knot, eq_kind)
         md = capi.model_desc_c(model, self._keep)
-        pr = capi.ParamsC(dt, c, hess_mode, eq_kind, frame_id, jac_mode)
+        pr = capi.ParamsC(dt, c, hess_mode, eq_kind, frame_id, jac_mode, max_restarts)
         self._h = C.c_void_p(lib().emu_create(C.byref(md), B, T, self.ne.ctypes.data_as(C.POINTER(C.c_int)), C.byref(pr)))
         assert self._h.value, "emu_create failed"
 
     @classmethod
-    def from_workload(cls, w, B=None, device=0):
+    def from_workload(cls, w, B=None, device=0, max_restarts=None):
         return cls(w.model, w.B if B is None else B, w.T, w.ne_per_knot(), dt=w.dt, c=w.c, hess_mode=w.hess_mode, eq_kind=w.eq_kind,
-                   frame_id=w.frame, jac_mode=w.jac_mode)
+                   frame_id=w.frame, jac_mode=w.jac_mode, max_restarts=w.max_restarts if max_restarts is None else max_restarts)
 
     def close(self):
         if self._h:

@@ -21,7 +21,7 @@ class ModelDescC(C.Structure):
 
 class ProblemDescC(C.Structure):
     _fields_ = [("T", C.c_int), ("dt", C.c_double), ("c", C.c_double), ("second_order_finite_diff", C.c_int), ("eq_kind", C.c_int),
-                ("frame", C.c_int), ("jac_mode", C.c_int), ("ne_per_knot", _ip), ("targets", _dp)]
+                ("frame", C.c_int), ("jac_mode", C.c_int), ("ne_per_knot", _ip), ("targets", _dp), ("max_restarts", C.c_int)]
 
 
 class DerivsC(C.Structure):
@@ -86,14 +86,15 @@ def model_desc_c(m, keep):
 class Oracle:
     """One single-problem instance of the reference path (model + horizon + constraint)."""
 
-    def __init__(self, model, T, dt=0.01, c=1.0, hess_mode=0, eq_kind=0, frame=0, jac_mode=0, ne_per_knot=None, targets=None):
+    def __init__(self, model, T, dt=0.01, c=1.0, hess_mode=0, eq_kind=0, frame=0, jac_mode=0, ne_per_knot=None, targets=None,
+                 max_restarts=0):
         self._keep = []
         self.model = model
         md = model_desc_c(model, self._keep)
         ne = np.zeros(T, dtype=np.int32) if ne_per_knot is None else np.ascontiguousarray(ne_per_knot, dtype=np.int32)
         tg = np.zeros(max(int(ne.sum()), 1)) if targets is None else np.ascontiguousarray(targets, dtype=np.float64).ravel()
         self._keep += [ne, tg]
-        pd = ProblemDescC(T, dt, c, 1 if hess_mode else 0, eq_kind, frame, jac_mode, _i(ne), _d(tg))
+        pd = ProblemDescC(T, dt, c, 1 if hess_mode else 0, eq_kind, frame, jac_mode, _i(ne), _d(tg), max_restarts)
         self._md, self._pd = md, pd
         self.h = C.c_void_p(lib().orc_create(C.byref(md), C.byref(pd)))
         dims = np.zeros(6, dtype=np.int32)
@@ -230,7 +231,7 @@ class Oracle:
 def from_workload(w, targets, T=None):
     """Oracle instance for one problem of a synthetic Workload (ddp_pinocchio_b200.synthetic)."""
     return Oracle(w.model, w.T if T is None else T, dt=w.dt, c=w.c, hess_mode=w.hess_mode, eq_kind=w.eq_kind, frame=w.frame,
-                  jac_mode=w.jac_mode, ne_per_knot=w.ne_per_knot(), targets=targets)
+                  jac_mode=w.jac_mode, ne_per_knot=w.ne_per_knot(), targets=targets, max_restarts=w.max_restarts)
 
 
 def solve_batch(w, data, nprob, nthreads, max_iter, mu, reg=0.0, thr=0.0, want_traj=False):
@@ -238,7 +239,7 @@ def solve_batch(w, data, nprob, nthreads, max_iter, mu, reg=0.0, thr=0.0, want_t
     keep = []
     md = model_desc_c(w.model, keep)
     ne = np.ascontiguousarray(w.ne_per_knot(), dtype=np.int32)
-    pd = ProblemDescC(w.T, w.dt, w.c, 1 if w.hess_mode else 0, w.eq_kind, w.frame, w.jac_mode, _i(ne), None)
+    pd = ProblemDescC(w.T, w.dt, w.c, 1 if w.hess_mode else 0, w.eq_kind, w.frame, w.jac_mode, _i(ne), None, w.max_restarts)
     nx, nu, T = w.nx, w.nu, w.T
     x0 = data["x0"][:nprob]
     # zero-control initial trajectory per problem, rolled out by the oracle itself (make_trajectory)
