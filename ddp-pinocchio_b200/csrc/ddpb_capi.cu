@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -333,8 +334,12 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   CU(cudaHostAlloc((void**)&h->h_stage, (size_t)NSCALARS * B * sizeof(double), cudaHostAllocDefault));
   // launch geometry
   const bool fdv = p->hess_mode == DDPB_HESS_FD_VALUES;
-  h->lin_threads = n <= 2 ? 32 : (n <= 4 ? (fdv ? 128 : 64) : (fdv ? 256 : 128));
-  h->bwd_threads = n <= 2 ? 32 : (n <= 4 ? 64 : 128);
+  // measured on B200 (tools/sweep_geometry.sh, profiles/): small CTAs keep more knots / problems resident per SM
+  h->lin_threads = n <= 2 ? 32 : (fdv ? (n <= 4 ? 128 : 256) : 64);
+  h->bwd_threads = n <= 2 ? 32 : 64;
+  // development knobs (launch geometry sweeps); not part of the interface
+  if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->lin_threads = v; }
+  if (const char* e = getenv("DDPB_BWD_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->bwd_threads = v; }
   DISPATCH(h->mt, { h->lin_smem = L::lin_smem_bytes(p->hess_mode, bd.ne_max); });
   if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) { ddpb_batch_destroy(h); return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory"); }
   DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });

@@ -50,7 +50,7 @@ class Workload:
     v0_scale: float = 0.0
     # guarded mode (ddpb_params.max_backward_restarts): a problem whose backward pass needs more than this many
     # mu-doubling restarts is marked diverged instead of looping to mu = inf (0 = reference behaviour)
-    max_restarts: int = 64
+    max_restarts: int = 10
     target_offset: float = 1.0
 
     @property

@@ -1,0 +1,47 @@
+"""world_size-2 gloo test of the multi-rank host logic (sharding + scalar gather); the GPU path uses the same
+functions over NCCL (bench.py)."""
+import os
+
+import numpy as np
+import pytest
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import ddpb_loader
+    ddpb_loader.load()
+    from ddp_pinocchio_b200 import distributed as D, synthetic as S
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    total = 7
+    lo, hi = D.shard_range(total, rank, world)
+    w = S.workload("c2", B=total, T=6)
+    g_all = w.generate()
+    g_loc = w.generate(B=hi - lo, first_problem=lo)
+    assert np.array_equal(g_loc["x0"], g_all["x0"][lo:hi])        # shards of one global batch
+    local = torch.tensor(np.stack([np.arange(lo, hi, dtype=float) + 100 * f for f in range(3)]))
+    out = D.gather_scalars(local, world, rank, dist, max_per_rank=4)
+    ok = D.all_converged(torch.tensor([1.0] * (hi - lo)) if rank == 0 else torch.tensor([0.0] * (hi - lo)), dist, world)
+    q.put((rank, out.numpy(), ok))
+    dist.destroy_process_group()
+
+
+def test_shard_and_gather_gloo():
+    import torch.multiprocessing as mp
+    from ddp_pinocchio_b200 import distributed as D
+    assert [D.shard_range(7, r, 2) for r in range(2)] == [(0, 4), (4, 7)]
+    assert [D.shard_range(8192, r, 8) for r in range(8)][-1] == (7168, 8192)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    for rank, out, ok in res:
+        assert out.shape == (3, 7)
+        assert np.array_equal(out[0], np.arange(7.0)) and np.array_equal(out[2], np.arange(7.0) + 200)
+        assert ok is False

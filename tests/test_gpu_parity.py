@@ -59,3 +59,51 @@ def test_gpu_matches_cpu_emulation_of_same_kernels():
         bt.close()
     for f in outs[0]:
         assert pc.relerr(outs[0][f], outs[1][f]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4", "c5"])
+def test_against_committed_golden_vectors(name):
+    """CUDA path vs tests/golden/*.npz (made by tests/golden/make_golden.py from the oracle)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}.npz"))
+    w = pc.S.workload(name, B=2, T=int(z["xs0_0"].shape[0]) - 1)
+    bt = make(w)
+    bt.set_targets(z["targets"]); bt.make_trajectory(z["x0"], z["us0"]); bt.set_multipliers(None, z["mult_jac"])
+    xs, _ = bt.get_trajectory()
+    bt.compute_derivatives()
+    D = bt.get_derivatives(["f_val", "fx", "fu", "eq_val", "eq_x", "eq_u"])
+    for b in range(2):
+        assert pc.relerr(xs[b], z[f"xs0_{b}"]) < pc.TOL_ROLLOUT
+        for f in D:
+            assert pc.relerr(D[f][b], z[f"{f}_{b}"]) < pc.TOL_FIRST, f
+    bt.solve(int(z["iters"]), float(z["mu"]))
+    xs, us = bt.get_trajectory()
+    for b in range(2):
+        assert pc.relerr(xs[b], z[f"xs_{b}"]) < 1e-5
+    bt.close()
+
+
+def test_full_size_properties_c3():
+    """BASELINE.json sizes (1024 x 100, 6R): size-independent properties instead of an oracle run --
+    identical problems give identical results wherever they sit in the batch, the rollout reproduces x_{t+1} = f(x_t,u_t)
+    of the derivative slabs bit for bit, top rows of the FD tensors are exactly zero, guarded status words are set."""
+    w = pc.S.workload("c3")
+    g = w.generate()
+    for k in ("x0", "us", "targets", "mult_jac"):   # problems 0 and 777 become copies of problem 5
+        g[k][0] = g[k][5]; g[k][777] = g[k][5]
+    bt = make(w)
+    bt.set_targets(g["targets"]); bt.make_trajectory(g["x0"], g["us"]); bt.set_multipliers(None, g["mult_jac"])
+    xs, us = bt.get_trajectory()
+    bt.compute_derivatives()
+    D = bt.get_derivatives(["f_val", "fxx", "fuu", "fx"])
+    n, nd = w.n, w.ndx
+    assert np.array_equal(D["f_val"].reshape(w.B, w.T, w.nx), xs[:, 1:, :])          # f(x_t,u_t) == x_{t+1} of the rollout
+    fxx = D["fxx"].reshape(w.B, w.T, nd, nd, nd)                                      # [.., j(right), i(left), k(out)]
+    assert not fxx[..., :n].any() and fxx[..., n:].any()                              # rows k < n are exact zeros
+    assert not D["fuu"].any()                                                         # same q => same M^-1 => exact zeros
+    sc = bt.solve(3, w.mu)
+    xs2, us2 = bt.get_trajectory()
+    assert np.array_equal(xs2[0], xs2[5]) and np.array_equal(xs2[777], xs2[5]) and np.array_equal(us2[0], us2[5])
+    assert np.isfinite(xs2[sc["status"] == 0]).all() and (sc["iterations"][sc["status"] == 0] == 3).all()
+    assert (sc["status"] == 2).sum() <= w.B // 50
+    bt.close()
