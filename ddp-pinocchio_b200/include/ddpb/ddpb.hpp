@@ -1,0 +1,171 @@
+// ddpb.hpp -- C++ host-side mirror of the reference's operator interface for the batched hot path.
+//
+// The reference is a header-only C++14 template library; its "plugin API" for this path is the trio of
+// duck-typed concepts Model / Dynamics+Constraint / Problem consumed by ddp_solver_t
+// (/root/reference/include/ddp/problem.hpp:343-525, 527-864, 872-1150; ddp.hpp:300-869).  This header keeps
+// the same names, argument meaning and defaults, but every object describes a BATCH of independent
+// problems and every hot call forwards to the C ABI of include/ddpb.h (libddpb.so, CUDA, sm_100a).
+// It depends on nothing but the C ABI and the standard library (no Eigen / fmt / Boost).
+//
+// Error convention: the reference terminates on precondition violations (DDP_ASSERT -> std::terminate,
+// src/lib.cpp:107-110); here a failing C-ABI call throws ddpb::error carrying ddpb_last_error().
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../../include/ddpb.h"
+
+namespace ddpb {
+
+using index_t = long;  // ddp::index_t
+
+struct error : std::runtime_error {
+  int code;
+  error(int c, const char* what) : std::runtime_error(std::string("ddpb: ") + what), code(c) {}
+};
+inline void check(int rc) {
+  if (rc != DDPB_OK) throw error(rc, ddpb_last_error());
+}
+
+enum struct method { primal, primal_dual_constant_multipliers, primal_dual_affine_multipliers };  // ddp.hpp:18-22
+
+// solver_parameters_t (ddp.hpp:42-50)
+template <typename Scalar> struct solver_parameters_t {
+  index_t max_iterations;
+  Scalar optimality_stopping_threshold;
+  Scalar mu, reg, w, n;
+};
+
+// Model concept: pinocchio::model_t / pendulum_model_t.  Owns a ddpb_model (move-only, like the reference's
+// pimpl, pinocchio_model.hpp:71-75).
+struct model_t {
+  using scalar_t = double;
+  ddpb_model* h = nullptr;
+  int nq = 0;
+  int frames = 0;
+  explicit model_t(const ddpb_model_desc& d) {
+    check(ddpb_model_create(&d, &h));
+    nq = d.kind == DDPB_MODEL_PENDULUM ? 1 : d.n_joints;
+    frames = d.n_frames;
+  }
+  // pendulum_model_t{mass, length} (pendulum_model.hpp:29)
+  static model_t pendulum(double mass, double length) {
+    ddpb_model_desc d{};
+    d.kind = DDPB_MODEL_PENDULUM; d.pend_mass = mass; d.pend_length = length; d.gravity[2] = -9.81;
+    return model_t(d);
+  }
+  model_t(model_t&& o) noexcept : h(o.h), nq(o.nq), frames(o.frames) { o.h = nullptr; }
+  model_t(const model_t&) = delete;
+  model_t& operator=(const model_t&) = delete;
+  ~model_t() { ddpb_model_destroy(h); }
+  index_t configuration_dim() const { return nq; }
+  index_t tangent_dim() const { return nq; }
+  index_t n_frames() const { return frames; }
+};
+
+// dynamics_t{model, dt, second_order_finite_diff = true} (problem.hpp:522-524)
+struct dynamics_t {
+  model_t const& m_model;
+  double dt;
+  bool second_order_finite_diff = true;
+  index_t state_dim() const { return 2 * m_model.nq; }
+  index_t dstate_dim() const { return 2 * m_model.nq; }
+  index_t control_dim(index_t) const { return m_model.nq; }
+};
+
+// Constraint concept.  The reference composes constraint_advance_time(constraint_advance_time(c)) around a
+// config_constraint_t or spatial_constraint_t (test/pinocchio_ddp.cpp:61-68); the batch path implements exactly
+// that composition, so the constraint is described by its kind, its target rows per BASE index t in
+// [2, T+2) (the reference's eq_idx, test/pendulum_ddp.cpp:37-47) and, for the spatial one, the frame.
+struct constraint_t {
+  int kind = DDPB_EQ_NONE;          // DDPB_EQ_CONFIG | DDPB_EQ_SPATIAL
+  std::vector<int> rows;            // rows[t - 2] for base index t in [2, T+2)
+  int frame_id = 0;
+  int frame_jac_mode = DDPB_FJ_WORLD;
+  static constraint_t config_terminal(index_t horizon, int nq) {  // range_row_filter(idx, T, T+1)
+    constraint_t c; c.kind = DDPB_EQ_CONFIG; c.rows.assign(horizon, 0); c.rows[horizon - 2] = nq; return c;
+  }
+  static constraint_t config_every_knot(index_t horizon, int nq) {  // vec_regular_indexer(2, T+2, nq)
+    constraint_t c; c.kind = DDPB_EQ_CONFIG; c.rows.assign(horizon, nq); return c;
+  }
+  static constraint_t spatial_terminal(index_t horizon, int frame) {
+    constraint_t c; c.kind = DDPB_EQ_SPATIAL; c.rows.assign(horizon, 0); c.rows[horizon - 2] = 3; c.frame_id = frame; return c;
+  }
+  // eq_dim(t) of the doubly advanced constraint (problem.hpp:553): rows the base indexer has at t + 2
+  int eq_dim(index_t t) const { return rows[static_cast<std::size_t>(t)]; }
+};
+
+// problem_t{begin, end, c, dynamics, constraint} (problem.hpp:1145-1149); c defaults to 1e2 there.
+struct problem_t {
+  index_t m_begin, m_end;
+  double c = 1e2;
+  dynamics_t m_dynamics;
+  constraint_t m_constraint;
+  index_t horizon() const { return m_end - m_begin; }
+};
+
+// per-problem scalars returned by solve (replaces the reference's stdout / log files, ddp.hpp:651-671)
+struct scalars_t {
+  int B = 0;
+  std::vector<double> data;  // [DDPB_NSCALARS][B]
+  double at(int field, int b) const { return data[static_cast<std::size_t>(field) * B + b]; }
+};
+
+// ddp_solver_t<Problem> for a batch of B problems that share `prob`'s structure (ddp.hpp:300-869).
+struct ddp_solver_t {
+  problem_t const& prob;
+  int B;
+  ddpb_batch* h = nullptr;
+  int nx, nu, T;
+
+  ddp_solver_t(problem_t const& p, int batch, int device = 0, int max_backward_restarts = 0)
+      : prob(p), B(batch), nx(int(p.m_dynamics.state_dim())), nu(p.m_dynamics.m_model.nq), T(int(p.horizon())) {
+    ddpb_params pr{};
+    pr.dt = p.m_dynamics.dt; pr.c = p.c;
+    pr.hess_mode = p.m_dynamics.second_order_finite_diff ? DDPB_HESS_FD_VALUES : DDPB_HESS_FD_JACOBIANS;
+    pr.eq_kind = p.m_constraint.kind; pr.frame_id = p.m_constraint.frame_id; pr.frame_jac_mode = p.m_constraint.frame_jac_mode;
+    pr.max_backward_restarts = max_backward_restarts;
+    check(ddpb_batch_create(p.m_dynamics.m_model.h, B, T, p.m_constraint.kind == DDPB_EQ_NONE ? nullptr : p.m_constraint.rows.data(), &pr,
+                            device, &h));
+  }
+  ddp_solver_t(const ddp_solver_t&) = delete;             // non-copyable, non-movable like the reference (ddp.hpp:737-741)
+  ddp_solver_t& operator=(const ddp_solver_t&) = delete;
+  ~ddp_solver_t() { ddpb_batch_destroy(h); }
+
+  int ne_total() const { int s = 0; for (int r : prob.m_constraint.rows) s += r; return prob.m_constraint.kind == DDPB_EQ_NONE ? 0 : s; }
+
+  // make_trajectory(control generator) (ddp.hpp:392-402): x0 [B][nx]; us [B][T*nu] or nullptr for the zero-control generator
+  void make_trajectory(const double* x0, const double* us = nullptr) { check(ddpb_make_trajectory(h, x0, us)); }
+  void set_targets(const double* targets) { check(ddpb_set_targets(h, targets)); }
+  // zero_multipliers<M>() + the (seeded) jac initialisation of solve (ddp.hpp:759-764)
+  void set_multipliers(const double* val, const double* jac) { check(ddpb_set_multipliers(h, val, jac)); }
+
+  // problem_t::compute_derivatives (problem.hpp:956)
+  void compute_derivatives() { check(ddpb_compute_derivatives(h)); }
+  // backward_pass<M>(ctrl_fb, traj, mults, reg, mu, derivs) -> {feedback, mu, reg}  (ddp.hpp:845-853); per-problem mu / reg
+  void backward_pass(std::vector<double>& mu, std::vector<double>& reg) { check(ddpb_backward_pass(h, mu.data(), reg.data())); }
+  // forward_pass<M>(new_traj, traj, mults, bres, do_linesearch = true) -> step (ddp.hpp:855-862)
+  std::vector<double> forward_pass() { std::vector<double> s(B); check(ddpb_forward_pass(h, s.data())); return s; }
+
+  // solve<M>(solver_parameters, initial_trajectory) (ddp.hpp:744-748); the trajectory / feedback stay on the device,
+  // read them with trajectory() / feedback()
+  template <method M = method::primal_dual_affine_multipliers> scalars_t solve(solver_parameters_t<double> sp) {
+    static_assert(M == method::primal_dual_affine_multipliers, "only the method the reference instantiates is provided");
+    ddpb_solver_params p{int(sp.max_iterations), sp.optimality_stopping_threshold, sp.mu, sp.reg, sp.w, sp.n};
+    scalars_t s; s.B = B; s.data.resize(static_cast<std::size_t>(DDPB_NSCALARS) * B);
+    check(ddpb_solve(h, &p, s.data.data()));
+    return s;
+  }
+  void trajectory(std::vector<double>& xs, std::vector<double>& us) {
+    xs.resize(static_cast<std::size_t>(B) * (T + 1) * nx); us.resize(static_cast<std::size_t>(B) * T * nu);
+    check(ddpb_get_trajectory(h, xs.data(), us.data()));
+  }
+  void feedback(std::vector<double>& k, std::vector<double>& K) {
+    k.resize(static_cast<std::size_t>(B) * T * nu); K.resize(static_cast<std::size_t>(B) * T * nu * nx);
+    check(ddpb_get_feedback(h, nullptr, k.data(), K.data()));
+  }
+};
+
+}  // namespace ddpb

@@ -1,0 +1,33 @@
+"""The C++ host facade (ddp-pinocchio_b200/include/ddpb/ddpb.hpp) compiles as C++14 against nothing but the C ABI,
+and the reference-style pendulum main runs (GPU) or fails loudly (no GPU)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "ddp-pinocchio_b200")
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "pendulum_ddp")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-I", os.path.join(PKG, "include"), os.path.join(ROOT, "tests", "cpp", "pendulum_ddp.cpp"),
+                           "-L", PKG, "-lddpb", f"-Wl,-rpath,{PKG}", "-o", exe])
+    return exe
+
+
+def test_facade_compiles_and_fails_loudly_without_gpu(tmp_path, pkg):
+    import torch
+    exe = _build(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_style_pendulum_main(tmp_path, pkg):
+    exe = _build(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "problem 0: q_T = 3.1" in r.stdout
