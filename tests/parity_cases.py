@@ -126,12 +126,18 @@ def check_backward(make, w):
                 assert np.array_equal(D[f][b], ds[b][f]), f"slab round trip {f}"
     restarts_seen = 0
     for mu, reg in [(1e4, 0.0), (1e-3, 0.0), (10.0, 1.0)]:
+        bt.set_scalar("status", 0.0)
         mu_e, reg_e = bt.backward_pass(mu, reg)
         _, k, K = bt.get_feedback()
+        status = bt.get_scalars()["status"]
         for b in range(w.B):
             ko, Ko, muo, rego, rs = orcs[b].backward_pass(ds[b], xs[b], mval[b], mjac[b], reg, mu)
             restarts_seen += rs
             assert mu_e[b] == muo and reg_e[b] == rego, (mu_e[b], muo, reg_e[b], rego)
+            if w.max_restarts and rs > w.max_restarts:
+                assert status[b] == 2.0   # guarded mode: diverged, the feedback of the aborted pass is undefined
+                continue
+            assert status[b] == 0.0
             assert relerr(k[b], ko) < TOL_GAINS and relerr(K[b], Ko) < TOL_GAINS, (relerr(k[b], ko), relerr(K[b], Ko))
     bt.close()
     return restarts_seen
@@ -147,6 +153,7 @@ def check_forward(make, w):
     bt.set_derivatives({f: np.stack([ds[b][f] for b in range(w.B)]) for f in ol.DERIV_FIELDS})
     mu_e, reg_e = bt.backward_pass(w.mu, 0.0)
     bt.set_scalar("mu", mu_e)
+    bt.set_scalar("status", 0.0)
     step = bt.forward_pass()
     xn, un = bt.get_new_trajectory()
     _, k, K = bt.get_feedback()
