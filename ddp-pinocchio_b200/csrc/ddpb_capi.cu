@@ -133,7 +133,7 @@ struct ddpb_batch {
   std::vector<PhaseEv> events;
   float phase_ms[4] = {0, 0, 0, 0};
   size_t lin_smem = 0;
-  int lin_threads = 128, bwd_threads = 128;
+  int lin_threads = 128, bwd_threads = 128, lin_kpb = 1;
   size_t bwd_smem = 0;
 };
 
@@ -190,8 +190,19 @@ static int check_launch(ddpb_batch* h, const char* what) {
 
 static int launch_linearize(ddpb_batch* h) {
   PhaseScope ps(h, 0);
-  DISPATCH(h->mt, L::linearize(h->model, h->bd, h->lin_threads, h->lin_smem, h->stream));
-  return check_launch(h, "linearize");
+  // one launch per maximal run of knots with the same number of equality rows: shared memory (and with it the
+  // number of resident CTAs) is sized for the run, not for the most constrained knot of the horizon
+  const int T = h->bd.T;
+  int t0 = 0;
+  while (t0 < T) {
+    int t1 = t0 + 1;
+    while (t1 < T && h->ne[t1] == h->ne[t0]) ++t1;
+    DISPATCH(h->mt, L::linearize(h->model, h->bd, h->lin_threads, h->lin_kpb, t0, t1, h->ne[t0], h->stream));
+    int rc = check_launch(h, "linearize");
+    if (rc) return rc;
+    t0 = t1;
+  }
+  return DDPB_OK;
 }
 static int launch_backward(ddpb_batch* h) {
   PhaseScope ps(h, 1);
@@ -206,6 +217,7 @@ static int launch_forward(ddpb_batch* h) {
 static int launch_al_update(ddpb_batch* h, double thr) {
   PhaseScope ps(h, 3);
   DISPATCH(h->mt, L::al_update(h->bd, thr, h->stream));
+  h->launches += 3;  // origin update, decision sweep, multiplier update, second sweep
   return check_launch(h, "al_update");
 }
 static int launch_simple(ddpb_batch* h, int which) {  // 0 post_forward
@@ -335,12 +347,15 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   // launch geometry
   const bool fdv = p->hess_mode == DDPB_HESS_FD_VALUES;
   // measured on B200 (tools/sweep_geometry.sh, profiles/): small CTAs keep more knots / problems resident per SM
-  h->lin_threads = n <= 2 ? 32 : (fdv ? (n <= 4 ? 128 : 256) : 64);
-  h->bwd_threads = n <= 2 ? 32 : 64;
+  h->lin_threads = fdv ? (n <= 2 ? 32 : (n <= 4 ? 128 : 256)) : 64;
+  h->bwd_threads = 32;  // one warp per problem (backward.cuh)
   // development knobs (launch geometry sweeps); not part of the interface
   if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->lin_threads = v; }
-  if (const char* e = getenv("DDPB_BWD_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->bwd_threads = v; }
-  DISPATCH(h->mt, { h->lin_smem = L::lin_smem_bytes(p->hess_mode, bd.ne_max); });
+
+  // problems per CTA of the linearization: small models leave most lanes of a one-knot CTA idle
+  h->lin_kpb = fdv ? 1 : (n <= 1 ? 16 : (n == 2 ? 8 : (n <= 4 ? 2 : 1)));
+  if (const char* e = getenv("DDPB_LIN_KPB")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->lin_kpb = v; }
+  DISPATCH(h->mt, { h->lin_smem = L::lin_smem_bytes(p->hess_mode, bd.ne_max) * h->lin_kpb; });
   if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) { ddpb_batch_destroy(h); return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory"); }
   DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });
   DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(); });

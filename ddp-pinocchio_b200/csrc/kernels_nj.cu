@@ -6,29 +6,37 @@
 #include "forward.cuh"
 #include "launch.cuh"
 #include "linearize.cuh"
+#include "outer_warp.cuh"
 
 namespace ddpb {
 
 constexpr int KNJ = DDPB_NJ;
 
 #if DDPB_NJ > 0
-template <int NJ> __global__ void __launch_bounds__(256) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd) {
+// grid: (knots t0..t1-1) x (groups of `kpb` consecutive problems); all knots of a launch have the same ne
+template <int NJ> __global__ void __launch_bounds__(256) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
+                                                                          int t0, int kpb, int ne_sm) {
   extern __shared__ __align__(16) double sm[];
-  const int b = blockIdx.x % bd.B, t = blockIdx.x / bd.B;
-  if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
-  linearize_knot<NJ>(m, bd, b, t, sm, DevExec{});
+  const int groups = (bd.B + kpb - 1) / kpb;
+  const int t = t0 + blockIdx.x / groups, b0 = (blockIdx.x % groups) * kpb;
+  const int nk = min(kpb, bd.B - b0);
+  bool any = false;
+  for (int k = 0; k < nk; ++k) any = any || bd.scal[(size_t)S_STATUS * bd.B + b0 + k] == 0.0;
+  if (!any) return;  // every problem of the group is frozen (converged / diverged)
+  linearize_group<NJ>(m, bd, t, b0, nk, ne_sm, sm, DevExec{});
 }
-template <int NJ> __global__ void __launch_bounds__(256) backward_kernel(const __grid_constant__ BatchDev bd) {
+// one warp (= one CTA of 32 threads) per problem; enough CTAs per SM that a whole batch is resident in one wave
+template <int NJ> __global__ void __launch_bounds__(32, NJ <= 2 ? 28 : (NJ <= 4 ? 16 : 8)) backward_kernel(const __grid_constant__ BatchDev bd) {
   extern __shared__ __align__(16) double sm[];
   const int b = blockIdx.x;
   if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
-  backward_problem<NJ>(bd, b, sm, DevExec{});
+  backward_problem<NJ, 32>(bd, b, sm, DevExec{});
 }
 #else
-template <int NJ> __global__ void linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd) {
+template <int NJ> __global__ void linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, int t0, int t1) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)bd.B * bd.T) return;
-  const int b = (int)(i % bd.B), t = (int)(i / bd.B);
+  if (i >= (size_t)bd.B * (t1 - t0)) return;
+  const int b = (int)(i % bd.B), t = t0 + (int)(i / bd.B);
   if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
   linearize_pendulum(m, bd, b, t);
 }
@@ -50,15 +58,28 @@ template <int NJ> __global__ void cost_kernel(const __grid_constant__ ModelDev m
   const double plain = cost_seq_problem<NJ>(m, bd, b, costs, bd.scal[(size_t)S_MU * bd.B + b]);
   bd.scal[(size_t)S_COST * bd.B + b] = plain;
 }
-template <int NJ> __global__ void al_update_kernel(const __grid_constant__ BatchDev bd, double thr) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// outer-loop sweeps (outer_warp.cuh): per-(knot, problem) kernels and one-warp-per-problem adjoint recursion
+template <int NJ> __global__ void origin_update_kernel(const __grid_constant__ BatchDev bd) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)bd.B * bd.T) return;
+  origin_update_knot<NJ>(bd, (int)(i % bd.B), (int)(i / bd.B));
+}
+template <int NJ> __global__ void mult_update_kernel(const __grid_constant__ BatchDev bd) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)bd.B * bd.T) return;
+  mult_update_knot<NJ>(bd, (int)(i % bd.B), (int)(i / bd.B));
+}
+template <int NJ> __global__ void al_decide_kernel(const __grid_constant__ BatchDev bd, double thr, int phase) {
+  const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (b >= bd.B) return;
-  al_update_problem<NJ>(bd, b, thr);
+  al_decide_warp<NJ>(bd, b, thr, phase);
 }
 template <int NJ> __global__ void optimality_kernel(const __grid_constant__ BatchDev bd) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (b >= bd.B) return;
-  bd.scal[(size_t)S_OPT_OBJ * bd.B + b] = optimality_obj_problem<NJ>(bd, b, bd.scal[(size_t)S_MU * bd.B + b]);
+  const double oo = optimality_obj_warp<NJ>(bd, b, bd.scal[(size_t)S_MU * bd.B + b]);
+  if ((threadIdx.x & 31) != 0) return;
+  bd.scal[(size_t)S_OPT_OBJ * bd.B + b] = oo;
   bd.scal[(size_t)S_OPT_CONSTR * bd.B + b] = optimality_constr_problem<NJ>(bd, b);
 }
 
@@ -89,13 +110,15 @@ template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
   return cudaSuccess;
 #endif
 }
-template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
+template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, int threads, int kpb, int t0, int t1, int ne_sm, cudaStream_t s) {
 #if DDPB_NJ > 0
-  linearize_kernel<KNJ><<<(unsigned)((size_t)bd.B * bd.T), threads, smem, s>>>(m, bd);
+  const size_t smem = lin_smem_bytes(bd.hess_mode, ne_sm) * kpb;
+  const int groups = (bd.B + kpb - 1) / kpb;
+  linearize_kernel<KNJ><<<(unsigned)((size_t)groups * (t1 - t0)), threads, smem, s>>>(m, bd, t0, kpb, ne_sm);
 #else
-  (void)threads; (void)smem;
-  const size_t n = (size_t)bd.B * bd.T;
-  linearize_kernel<KNJ><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(m, bd);
+  (void)threads; (void)kpb; (void)ne_sm;
+  const size_t n = (size_t)bd.B * (t1 - t0);
+  linearize_kernel<KNJ><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(m, bd, t0, t1);
 #endif
 }
 template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
@@ -115,10 +138,15 @@ template <> void Launch<KNJ>::cost(const ModelDev& m, const BatchDev& bd, double
   cost_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs);
 }
 template <> void Launch<KNJ>::al_update(const BatchDev& bd, double thr, cudaStream_t s) {
-  al_update_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(bd, thr);
+  const size_t nkb = (size_t)bd.B * bd.T;
+  const unsigned wblocks = (unsigned)(((size_t)bd.B * 32 + 127) / 128);
+  origin_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
+  al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 0);
+  mult_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
+  al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 1);
 }
 template <> void Launch<KNJ>::optimality(const BatchDev& bd, cudaStream_t s) {
-  optimality_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(bd);
+  optimality_kernel<KNJ><<<(unsigned)(((size_t)bd.B * 32 + 127) / 128), 128, 0, s>>>(bd);
 }
 
 }  // namespace ddpb

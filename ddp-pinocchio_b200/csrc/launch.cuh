@@ -12,7 +12,8 @@ template <int NJ> struct Launch {
   static size_t lin_smem_bytes(int hess_mode, int ne_max);
   static size_t bwd_smem_bytes();
   static cudaError_t prepare(size_t lin_smem);
-  static void linearize(const ModelDev& m, const BatchDev& bd, int threads, size_t smem, cudaStream_t s);
+  // knots [t0, t1) (all with the same number of equality rows <= ne_sm), kpb problems per CTA
+  static void linearize(const ModelDev& m, const BatchDev& bd, int threads, int kpb, int t0, int t1, int ne_sm, cudaStream_t s);
   static void backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s);
   static void forward(const ModelDev& m, const BatchDev& bd, double* costs_old, cudaStream_t s);
   static void rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s);

@@ -71,48 +71,50 @@ template <int NJ> struct LinPlan {
   DDPB_HD double eps() const { return mode == HESS_FD_JACOBIANS ? 1.4901161193847656e-08 /* 2^-26 */ : 1.220703125e-04 /* 2^-13 */; }
 };
 
+// One CTA linearizes `nk` consecutive problems b0 .. b0+nk-1 of knot t (same t => same number of equality
+// rows, adjacent records in HBM).  `ne_sm` is the row count the shared-memory plan was sized for (>= ne(t)).
 template <int NJ, class Ex>
-DDPB_HD void linearize_knot(const ModelDev& m, const BatchDev& bd, int b, int t, double* sm, const Ex& ex) {
+DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b0, int nk, int ne_sm, double* sm_all, const Ex& ex) {
   constexpr int n = NJ, nd = 2 * NJ, nu = NJ, nx = 2 * NJ, N = 3 * NJ;
   using Q = QRec<NJ>;
   using V = VRec<NJ>;
   const int B = bd.B;
   const int ne = bd.ne[t];
   LinPlan<NJ> pl;
-  pl.init(bd.hess_mode, bd.ne_max, ne);
+  pl.init(bd.hess_mode, ne_sm, ne);
   const double eps = pl.eps();
   const double dt = bd.dt;
-  double* base = sm + pl.o_base;
-  double* tgt = sm + pl.o_tgt;
-  double* qrec = sm + pl.o_qrec;
-  double* vrec = sm + pl.o_vrec;
-  double* fval = sm + pl.o_fval;
-  double* eqv = sm + pl.o_eqv;
-  double* Jsm = sm + pl.o_J;
-  double* eqxu = sm + pl.o_eqxu;
   const int tid = ex.tid(), nthr = ex.nthr();
+  const size_t KS = (size_t)pl.total;  // shared-memory stride between the knots of this CTA
+#define SM(kk, off) (sm_all + (size_t)(kk) * KS + (off))
 
   // phase 0: stage x_t, u_t and the target
-  for (int e = tid; e < N + ne; e += nthr) {
-    if (e < nx) base[e] = bd.xs[((size_t)t * nx + e) * B + b];
-    else if (e < N) base[e] = bd.us[((size_t)t * nu + (e - nx)) * B + b];
-    else tgt[e - N] = bd.targets[((size_t)bd.eq_off[t] + (e - N)) * B + b];
+  for (int idx = tid; idx < nk * (N + ne); idx += nthr) {
+    const int kk = idx / (N + ne), e = idx - kk * (N + ne), b = b0 + kk;
+    if (e < nx) SM(kk, pl.o_base)[e] = bd.xs[((size_t)t * nx + e) * B + b];
+    else if (e < N) SM(kk, pl.o_base)[e] = bd.us[((size_t)t * nu + (e - nx)) * B + b];
+    else SM(kk, pl.o_tgt)[e - N] = bd.targets[((size_t)bd.eq_off[t] + (e - N)) * B + b];
   }
   ex.sync();
 
   // phase 1: q-only data for every distinct configuration
-  for (int s = tid; s < pl.NQ; s += nthr) {
+  for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
+    const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
+    const double* base = SM(kk, pl.o_base);
     int i, j;
     pl.qset_pert(s, &i, &j);
     double q[NJ];
 #pragma unroll
     for (int k = 0; k < NJ; ++k) q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
-    q_task<NJ>(m, q, qrec + (size_t)s * Q::SIZE);
+    q_task<NJ>(m, q, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
   }
   ex.sync();
 
   // phase 2: accelerations (and body data where tangents are needed) at every evaluation point
-  for (int p = tid; p < pl.P; p += nthr) {
+  for (int idx = tid; idx < nk * pl.P; idx += nthr) {
+    const int kk = idx / pl.P, p = idx - kk * pl.P;
+    const double* base = SM(kk, pl.o_base);
+    double* fval = SM(kk, pl.o_fval);
     int i, j;
     pl.point_pert(p, &i, &j);
     double q[NJ], qd[NJ], tau[NJ], qdd[NJ];
@@ -122,7 +124,7 @@ DDPB_HD void linearize_knot(const ModelDev& m, const BatchDev& bd, int b, int t,
       qd[k] = base[n + k] + ((n + k == i || n + k == j) ? eps : 0.0);
       tau[k] = base[2 * n + k] + ((2 * n + k == i || 2 * n + k == j) ? eps : 0.0);
     }
-    v_task<NJ>(m, qrec + (size_t)pl.point_qset(p) * Q::SIZE, qd, tau, qdd, p < pl.NT ? vrec + (size_t)p * V::SIZE : nullptr);
+    v_task<NJ>(m, SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, qd, tau, qdd, p < pl.NT ? SM(kk, pl.o_vrec) + (size_t)p * V::SIZE : nullptr);
     // dynamics_t::eval_to (problem.hpp:441-461): v_out = dt v ; q_out = q + v_out ; v_out = v + acc dt
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
@@ -137,20 +139,24 @@ DDPB_HD void linearize_knot(const ModelDev& m, const BatchDev& bd, int b, int t,
   {
     const int n_tan = pl.NT * 2 * NJ;
     const int n_minv = (pl.mode == HESS_FD_JACOBIANS ? pl.NQ : 1) * NJ;
-    for (int task = tid; task < n_tan + n_minv; task += nthr) {
+    // tangent tasks of all knots first (j-major inside a knot), then the M^-1 tasks
+    for (int idx = tid; idx < nk * (n_tan + n_minv); idx += nthr) {
       double col[NJ];
-      if (task < n_tan) {
-        const int j = task / (2 * pl.NT), rem = task - j * 2 * pl.NT;
-        const int wrt = rem / pl.NT, p = rem - wrt * pl.NT;
-        double* vr = vrec + (size_t)p * V::SIZE;
-        tangent_col<NJ>(m, qrec + (size_t)pl.point_qset(p) * Q::SIZE, vr, j, wrt, col);
+      if (idx < nk * n_tan) {
+        // order: j slowest so that the threads of a warp share the loop bounds of tangent_col
+        const int j = idx / (nk * 2 * pl.NT), rem = idx - j * nk * 2 * pl.NT;
+        const int kk = rem / (2 * pl.NT), rem2 = rem - kk * 2 * pl.NT;
+        const int wrt = rem2 / pl.NT, p = rem2 - wrt * pl.NT;
+        double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
+        tangent_col<NJ>(m, SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, vr, j, wrt, col);
         double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
 #pragma unroll
         for (int k = 0; k < NJ; ++k) dst[k] = col[k];
       } else {
-        const int r = task - n_tan;
-        const int c = r % NJ, s = r / NJ;
-        double* qr = qrec + (size_t)s * Q::SIZE;
+        const int r = idx - nk * n_tan;
+        const int kk = r / n_minv, r2 = r - kk * n_minv;
+        const int c = r2 % NJ, s = r2 / NJ;
+        double* qr = SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE;
         minv_col<NJ>(m, qr, c, col);
 #pragma unroll
         for (int k = 0; k < NJ; ++k) qr[Q::MINV + c * NJ + k] = col[k];
@@ -161,12 +167,13 @@ DDPB_HD void linearize_knot(const ModelDev& m, const BatchDev& bd, int b, int t,
 
   // phase 4: da/dq = -M^-1 dtau/dq, da/dv = -M^-1 dtau/dv, already scaled into the bottom blocks of
   // fx (problem.hpp:495-502): DQ <- dt * da/dq ; DV <- dt * da/dv + I
-  for (int task = tid; task < pl.NT * 2 * NJ; task += nthr) {
+  for (int idx = tid; idx < nk * pl.NT * 2 * NJ; idx += nthr) {
+    const int kk = idx / (pl.NT * 2 * NJ), task = idx - kk * pl.NT * 2 * NJ;
     const int p = task / (2 * NJ), rem = task - p * 2 * NJ;
     const int wrt = rem / NJ, c = rem - wrt * NJ;
-    double* vr = vrec + (size_t)p * V::SIZE;
+    double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
     double* colp = vr + (wrt ? V::DV : V::DQ) + c * NJ;
-    const double* Mi = qrec + (size_t)pl.point_qset(p) * Q::SIZE + Q::MINV;
+    const double* Mi = SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE + Q::MINV;
     double src[NJ], dst[NJ];
 #pragma unroll
     for (int k = 0; k < NJ; ++k) src[k] = colp[k];
@@ -183,120 +190,87 @@ DDPB_HD void linearize_knot(const ModelDev& m, const BatchDev& bd, int b, int t,
   }
   ex.sync();
 
-  // element accessors of fx / fu at point p (p < NT)
-  auto fx_at = [&](int p, int r, int c) -> double {
+  // element accessors of fx / fu at point p (p < NT) of knot kk
+  auto fx_at = [&](int kk, int p, int r, int c) -> double {
     if (r < n) return c < n ? (r == c ? 1.0 : 0.0) : (r == c - n ? dt : 0.0);
-    const double* vr = vrec + (size_t)p * V::SIZE;
+    const double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
     return c < n ? vr[V::DQ + c * NJ + (r - n)] : vr[V::DV + (c - n) * NJ + (r - n)];
   };
-  auto fu_at = [&](int p, int r, int c) -> double {
+  auto fu_at = [&](int kk, int p, int r, int c) -> double {
     if (r < n) return 0.0;
-    return qrec[(size_t)pl.point_qset(p) * Q::SIZE + Q::MINV + c * NJ + (r - n)] * dt;
+    return SM(kk, pl.o_qrec)[(size_t)pl.point_qset(p) * Q::SIZE + Q::MINV + c * NJ + (r - n)] * dt;
   };
 
-  // phase 5: the doubly advanced equality constraint at every point
-  if (ne > 0) {
-    for (int p = tid; p < pl.P; p += nthr) {
-      // x_{t+1} = f(x,u) is fval[p]; inner eval_to: v_out = dt v ; q_out = q + v_out
-      double qnn[NJ];
+  // phase 5: the doubly advanced equality constraint at every point (empty loops when the knot has no rows)
+  for (int idx = tid; idx < (ne > 0 ? nk * pl.P : 0); idx += nthr) {
+    const int kk = idx / pl.P, p = idx - kk * pl.P;
+    const double* fval = SM(kk, pl.o_fval);
+    const double* tgt = SM(kk, pl.o_tgt);
+    double* eqv = SM(kk, pl.o_eqv);
+    // x_{t+1} = f(x,u) is fval[p]; inner eval_to: v_out = dt v ; q_out = q + v_out
+    double qnn[NJ];
 #pragma unroll
-      for (int k = 0; k < NJ; ++k) { const double vo = dt * fval[p * nx + n + k]; qnn[k] = fval[p * nx + k] + vo; }
-      if (bd.eq_kind == EQ_CONFIG) {
-        for (int r = 0; r < ne; ++r) eqv[p * bd.ne_max + r] = qnn[r] - tgt[r];
-      } else {
-        double p3[3];
-        frame_task<NJ>(m, qnn, bd.frame_id, bd.jac_mode, p3, p < pl.NT ? Jsm + p * 3 * NJ : nullptr);
-        for (int r = 0; r < ne; ++r) eqv[p * bd.ne_max + r] = p3[r] - tgt[r];
-      }
+    for (int k = 0; k < NJ; ++k) { const double vo = dt * fval[p * nx + n + k]; qnn[k] = fval[p * nx + k] + vo; }
+    if (bd.eq_kind == EQ_CONFIG) {
+      for (int r = 0; r < ne; ++r) eqv[p * ne_sm + r] = qnn[r] - tgt[r];
+    } else {
+      double p3[3];
+      frame_task<NJ>(m, qnn, bd.frame_id, bd.jac_mode, p3, p < pl.NT ? SM(kk, pl.o_J) + p * 3 * NJ : nullptr);
+      for (int r = 0; r < ne; ++r) eqv[p * ne_sm + r] = p3[r] - tgt[r];
     }
-    ex.sync();
-    // eq_x = c_x [I, dt I] fx ; eq_u = c_x [I, dt I] fu   (problem.hpp:603-604, applied twice)
-    for (int task = tid; task < pl.NT * ne * N; task += nthr) {
-      const int p = task / (ne * N), rem = task - p * ne * N;
-      const int c = rem / ne, r = rem - c * ne;
-      double acc = 0.0;
-      if (bd.eq_kind == EQ_CONFIG) {
-        if (c < nd) { acc = fx_at(p, r, c); acc += dt * fx_at(p, n + r, c); }
-        else { acc = fu_at(p, r, c - nd); acc += dt * fu_at(p, n + r, c - nd); }
-      } else {
-        const double* J = Jsm + p * 3 * NJ;
-        for (int k = 0; k < nd; ++k) {
-          const double e = k < n ? J[k * 3 + r] : J[(k - n) * 3 + r] * dt;
-          acc += e * (c < nd ? fx_at(p, k, c) : fu_at(p, k, c - nd));
-        }
-      }
-      eqxu[(size_t)p * bd.ne_max * N + c * ne + r] = acc;
-    }
-    ex.sync();
   }
+  ex.sync();
+  // eq_x = c_x [I, dt I] fx ; eq_u = c_x [I, dt I] fu   (problem.hpp:603-604, applied twice)
+  for (int idx = tid; idx < (ne > 0 ? nk * pl.NT * ne * N : 0); idx += nthr) {
+    const int kk = idx / (pl.NT * ne * N), task = idx - kk * pl.NT * ne * N;
+    const int p = task / (ne * N), rem = task - p * ne * N;
+    const int c = rem / ne, r = rem - c * ne;
+    double acc = 0.0;
+    if (bd.eq_kind == EQ_CONFIG) {
+      if (c < nd) { acc = fx_at(kk, p, r, c); acc += dt * fx_at(kk, p, n + r, c); }
+      else { acc = fu_at(kk, p, r, c - nd); acc += dt * fu_at(kk, p, n + r, c - nd); }
+    } else {
+      const double* J = SM(kk, pl.o_J) + p * 3 * NJ;
+      for (int k = 0; k < nd; ++k) {
+        const double e = k < n ? J[k * 3 + r] : J[(k - n) * 3 + r] * dt;
+        acc += e * (c < nd ? fx_at(kk, p, k, c) : fu_at(kk, p, k, c - nd));
+      }
+    }
+    SM(kk, pl.o_eqxu)[(size_t)p * ne_sm * N + c * ne + r] = acc;
+  }
+  ex.sync();
 
-  // phase 6: assemble the record and stream it out (consecutive threads -> consecutive doubles)
+  // phase 6: assemble the records and stream them out.  The nk records are adjacent in HBM, so the CTA writes
+  // one contiguous span: element e of the span belongs to knot e / L.size.
   const RecLayout L = rec_layout(nd, nu, nx, ne);
-  double* rec = slab_rec(bd, t, b, L.size);
+  double* rec0 = slab_rec(bd, t, b0, L.size);
   const double inv_eps = 1.0 / eps, inv_eps2 = 1.0 / (eps * eps);
-  for (int e = tid; e < nd; e += nthr) rec[L.lx + e] = 0.0;
-  for (int e = tid; e < nu; e += nthr) rec[L.lu + e] = bd.c * base[2 * n + e];
-  for (int e = tid; e < nd * nd; e += nthr) rec[L.lxx + e] = 0.0;
-  for (int e = tid; e < nu * nd; e += nthr) rec[L.lux + e] = 0.0;
-  for (int e = tid; e < nu * nu; e += nthr) rec[L.luu + e] = (e / nu == e % nu) ? bd.c : 0.0;
-  for (int e = tid; e < nx; e += nthr) rec[L.f + e] = fval[e];
-  for (int e = tid; e < nd * nd; e += nthr) rec[L.fx + e] = fx_at(0, e % nd, e / nd);
-  for (int e = tid; e < nd * nu; e += nthr) rec[L.fu + e] = fu_at(0, e % nd, e / nd);
-  for (int e = tid; e < ne; e += nthr) rec[L.eq + e] = eqv[e];
-  for (int e = tid; e < ne * nd; e += nthr) rec[L.eq_x + e] = eqxu[e];
-  for (int e = tid; e < ne * nu; e += nthr) rec[L.eq_u + e] = eqxu[ne * nd + e];
-
-  if (pl.mode == HESS_FD_JACOBIANS) {
-    // problem.hpp:128-145: T(k,j,idx) = (J'(k,j) - J(k,j)) / eps ; rows k < n are exact constants
-    for (int e = tid; e < nd * nd * nd; e += nthr) {
-      const int k = e % nd, j = (e / nd) % nd, i = e / (nd * nd);
-      rec[L.fxx + e] = k < n ? 0.0 : (fx_at(1 + i, k, j) - fx_at(0, k, j)) * inv_eps;
-    }
-    for (int e = tid; e < nd * nu * nd; e += nthr) {
-      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
-      rec[L.fux + e] = k < n ? 0.0 : (fu_at(1 + i, k, j) - fu_at(0, k, j)) * inv_eps;
-    }
-    for (int e = tid; e < nd * nu * nu; e += nthr) {
-      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
-      rec[L.fuu + e] = k < n ? 0.0 : (fu_at(1 + nd + i, k, j) - fu_at(0, k, j)) * inv_eps;
-    }
-    if (ne > 0) {
-      const size_t ps = (size_t)bd.ne_max * N;  // eqxu stride per point
-      for (int e = tid; e < ne * nd * nd; e += nthr) {
-        const int k = e % ne, j = (e / ne) % nd, i = e / (ne * nd);
-        rec[L.eq_xx + e] = (eqxu[(1 + i) * ps + j * ne + k] - eqxu[j * ne + k]) * inv_eps;
-      }
-      for (int e = tid; e < ne * nu * nd; e += nthr) {
-        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
-        rec[L.eq_ux + e] = (eqxu[(1 + i) * ps + (nd + j) * ne + k] - eqxu[(nd + j) * ne + k]) * inv_eps;
-      }
-      for (int e = tid; e < ne * nu * nu; e += nthr) {
-        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
-        rec[L.eq_uu + e] = (eqxu[(1 + nd + i) * ps + (nd + j) * ne + k] - eqxu[(nd + j) * ne + k]) * inv_eps;
-      }
-    }
-  } else {
-    // problem.hpp:192-296.  `val0` / `J0col` are the base value and Jacobian column accessors of the
-    // function being differentiated (f or eq); `valp` the value at point p.
-    auto diag = [&](double f1, double f0, double col) -> double {
-      double df = f1 - f0;
-      df -= eps * col;
-      df *= 2.0;
-      return df * inv_eps2;
-    };
-    auto offd = [&](double f1, double f0, double col1, double col2, double d1, double d2) -> double {
-      double df = f1 - f0;
-      df -= eps * col1;
-      df -= eps * col2;
-      df *= 2.0;
-      return 0.5 * (df * inv_eps2 - d1 - d2);
-    };
-    // generic element: output row k of function `which` (0 = f, 1 = eq), global tangent indices ga, gb
+  const size_t ps = (size_t)ne_sm * N;  // eqxu stride per point
+  auto diag = [&](double f1, double f0, double col) -> double {
+    double df = f1 - f0;
+    df -= eps * col;
+    df *= 2.0;
+    return df * inv_eps2;
+  };
+  auto offd = [&](double f1, double f0, double col1, double col2, double d1, double d2) -> double {
+    double df = f1 - f0;
+    df -= eps * col1;
+    df -= eps * col2;
+    df *= 2.0;
+    return 0.5 * (df * inv_eps2 - d1 - d2);
+  };
+  for (int idx = tid; idx < nk * L.size; idx += nthr) {
+    const int kk = idx / L.size, o = idx - kk * L.size;
+    const double* base = SM(kk, pl.o_base);
+    const double* fval = SM(kk, pl.o_fval);
+    const double* eqv = SM(kk, pl.o_eqv);
+    const double* eqxu = SM(kk, pl.o_eqxu);
+    // problem.hpp:192-296 helpers (value-based FD): row k of function `which` (0 = f, 1 = eq), global tangent indices
     auto jcol = [&](int which, int k, int g) -> double {
-      if (which == 0) return g < nd ? fx_at(0, k, g) : fu_at(0, k, g - nd);
+      if (which == 0) return g < nd ? fx_at(kk, 0, k, g) : fu_at(kk, 0, k, g - nd);
       return eqxu[g * ne + k];
     };
-    auto val = [&](int which, int p, int k) -> double { return which == 0 ? fval[p * nx + k] : eqv[p * bd.ne_max + k]; };
+    auto val = [&](int which, int p, int k) -> double { return which == 0 ? fval[p * nx + k] : eqv[p * ne_sm + k]; };
     auto hess = [&](int which, int k, int ga, int gb) -> double {
       const double f0 = val(which, 0, k);
       if (ga == gb) return diag(val(which, 1 + ga, k), f0, jcol(which, k, ga));
@@ -305,33 +279,41 @@ DDPB_HD void linearize_knot(const ModelDev& m, const BatchDev& bd, int b, int t,
       const double di = diag(val(which, 1 + i, k), f0, ci), dj = diag(val(which, 1 + j, k), f0, cj);
       return offd(val(which, 1 + N + pair_rank(i, j, N), k), f0, ci, cj, di, dj);
     };
-    for (int e = tid; e < nd * nd * nd; e += nthr) {
-      const int k = e % nd, j = (e / nd) % nd, i = e / (nd * nd);
-      rec[L.fxx + e] = hess(0, k, j, i);
+    const bool fdj = pl.mode == HESS_FD_JACOBIANS;
+    double v = 0.0;
+    if (o < L.lu) v = 0.0;                                                        // lx
+    else if (o < L.lxx) v = bd.c * base[2 * n + (o - L.lu)];                      // lu = c u
+    else if (o < L.luu) v = 0.0;                                                  // lxx, lux
+    else if (o < L.f) { const int e = o - L.luu; v = (e / nu == e % nu) ? bd.c : 0.0; }   // luu = c I
+    else if (o < L.fx) v = fval[o - L.f];
+    else if (o < L.fu) { const int e = o - L.fx; v = fx_at(kk, 0, e % nd, e / nd); }
+    else if (o < L.fxx) { const int e = o - L.fu; v = fu_at(kk, 0, e % nd, e / nd); }
+    else if (o < L.fux) {
+      const int e = o - L.fxx, k = e % nd, j = (e / nd) % nd, i = e / (nd * nd);
+      // problem.hpp:128-145: T(k,j,idx) = (J'(k,j) - J(k,j)) / eps ; rows k < n are exact constants
+      v = fdj ? (k < n ? 0.0 : (fx_at(kk, 1 + i, k, j) - fx_at(kk, 0, k, j)) * inv_eps) : hess(0, k, j, i);
+    } else if (o < L.fuu) {
+      const int e = o - L.fux, k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
+      v = fdj ? (k < n ? 0.0 : (fu_at(kk, 1 + i, k, j) - fu_at(kk, 0, k, j)) * inv_eps) : hess(0, k, nd + j, i);
+    } else if (o < L.eq) {
+      const int e = o - L.fuu, k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
+      v = fdj ? (k < n ? 0.0 : (fu_at(kk, 1 + nd + i, k, j) - fu_at(kk, 0, k, j)) * inv_eps) : hess(0, k, nd + j, nd + i);
+    } else if (o < L.eq_x) v = eqv[o - L.eq];
+    else if (o < L.eq_u) v = eqxu[o - L.eq_x];
+    else if (o < L.eq_xx) v = eqxu[ne * nd + (o - L.eq_u)];
+    else if (o < L.eq_ux) {
+      const int e = o - L.eq_xx, k = e % ne, j = (e / ne) % nd, i = e / (ne * nd);
+      v = fdj ? (eqxu[(1 + i) * ps + j * ne + k] - eqxu[j * ne + k]) * inv_eps : hess(1, k, j, i);
+    } else if (o < L.eq_uu) {
+      const int e = o - L.eq_ux, k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
+      v = fdj ? (eqxu[(1 + i) * ps + (nd + j) * ne + k] - eqxu[(nd + j) * ne + k]) * inv_eps : hess(1, k, nd + j, i);
+    } else if (o < L.eq_uu + ne * nu * nu) {
+      const int e = o - L.eq_uu, k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
+      v = fdj ? (eqxu[(1 + nd + i) * ps + (nd + j) * ne + k] - eqxu[(nd + j) * ne + k]) * inv_eps : hess(1, k, nd + j, nd + i);
     }
-    for (int e = tid; e < nd * nu * nd; e += nthr) {
-      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
-      rec[L.fux + e] = hess(0, k, nd + j, i);
-    }
-    for (int e = tid; e < nd * nu * nu; e += nthr) {
-      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
-      rec[L.fuu + e] = hess(0, k, nd + j, nd + i);
-    }
-    if (ne > 0) {
-      for (int e = tid; e < ne * nd * nd; e += nthr) {
-        const int k = e % ne, j = (e / ne) % nd, i = e / (ne * nd);
-        rec[L.eq_xx + e] = hess(1, k, j, i);
-      }
-      for (int e = tid; e < ne * nu * nd; e += nthr) {
-        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
-        rec[L.eq_ux + e] = hess(1, k, nd + j, i);
-      }
-      for (int e = tid; e < ne * nu * nu; e += nthr) {
-        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
-        rec[L.eq_uu + e] = hess(1, k, nd + j, nd + i);
-      }
-    }
+    rec0[idx] = v;
   }
+#undef SM
 }
 
 // ---- pendulum (nx = 2, nu = 1): one thread per knot, following the oracle statement by statement ----

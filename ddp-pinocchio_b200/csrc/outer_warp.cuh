@@ -1,0 +1,192 @@
+// outer_warp.cuh -- device-only, latency-oriented versions of the per-problem sweeps of the outer loop.
+// The thread-per-problem bodies in forward.cuh stay as the CPU-emulated reference of the same arithmetic
+// (tests/hostemu); these kernels split them by their parallelism:
+//   origin_update_knot   : mults/feedback re-centering (mat_seq_common.hpp:62-89) -- independent per (knot, problem)
+//   optimality_warp      : adjoint recursion of optimality_obj (ddp.hpp:575-627) -- sequential in t, one WARP per
+//                          problem: lane i < ndx owns adjoint component i, lanes ndx..ndx+nu-1 own l_u rows, the
+//                          f_x / f_u columns are read straight from the slab record (contiguous 8*ndx-byte runs) one
+//                          knot ahead, the new adjoint is exchanged with shuffles
+//   mult_update_knot     : multiplier update (ddp.hpp:686-687) -- independent per (knot, problem)
+#pragma once
+#if defined(__CUDACC__)
+#include "forward.cuh"
+
+namespace ddpb {
+
+template <int NJ> __device__ __forceinline__ void origin_update_knot(const BatchDev& bd, int b, int t) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n;
+  const int B = bd.B;
+  if (bd.scal[(size_t)S_STATUS * B + b] != 0.0) return;
+  const int ne = bd.ne[t];
+  const size_t eo = bd.eq_off[t];
+  double dxm[nd], dxf[nd];
+#pragma unroll
+  for (int k = 0; k < nd; ++k) {
+    const double xv = bd.xs[((size_t)t * nx + k) * B + b];
+    dxm[k] = xv - bd.m_origin[((size_t)t * nx + k) * B + b];
+    dxf[k] = xv - bd.fb_origin[((size_t)t * nx + k) * B + b];
+    bd.m_origin[((size_t)t * nx + k) * B + b] = xv;
+    bd.fb_origin[((size_t)t * nx + k) * B + b] = xv;
+  }
+  for (int i = 0; i < ne; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < nd; ++k) a += bd.m_jac[(eo * nd + k * ne + i) * B + b] * dxm[k];
+    bd.m_val[(eo + i) * B + b] += a;
+  }
+#pragma unroll
+  for (int i = 0; i < nu; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < nd; ++k) a += bd.fb_K[((size_t)t * nu * nd + k * nu + i) * B + b] * dxf[k];
+    bd.fb_k[((size_t)t * nu + i) * B + b] += a;
+  }
+}
+
+template <int NJ> __device__ __forceinline__ void mult_update_knot(const BatchDev& bd, int b, int t) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n;
+  const int B = bd.B;
+  if (bd.scal[(size_t)S_STATUS * B + b] != 0.0 || bd.scal[(size_t)S_FLAG * B + b] != 1.0) return;
+  const int ne = bd.ne[t];
+  if (ne == 0) return;
+  const double mu = bd.scal[(size_t)S_MU * B + b];
+  const size_t eo = bd.eq_off[t];
+  const RecLayout L = rec_layout(nd, nu, nx, ne);
+  const double* rec = slab_rec(bd, t, b, L.size);
+  for (int i = 0; i < ne; ++i) {
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < nu; ++k) a += rec[L.eq_u + k * ne + i] * bd.fb_k[((size_t)t * nu + k) * B + b];
+    bd.m_val[(eo + i) * B + b] += mu * (rec[L.eq + i] + a);
+  }
+  for (int c = 0; c < nd; ++c)
+    for (int i = 0; i < ne; ++i) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < nu; ++k) a += rec[L.eq_u + k * ne + i] * bd.fb_K[((size_t)t * nu * nd + c * nu + k) * B + b];
+      bd.m_jac[(eo * nd + c * ne + i) * B + b] += mu * (rec[L.eq_x + c * ne + i] + a);
+    }
+}
+
+// one warp: opt_obj of problem b (all lanes return the same value)
+template <int NJ> __device__ __forceinline__ double optimality_obj_warp(const BatchDev& bd, int b, double mu) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n;
+  static_assert(nd + nu <= 32, "one lane per adjoint / control component");
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int B = bd.B;
+  const bool isx = lane < nd, isu = lane >= nd && lane < nd + nu;
+  const int col = isx ? lane : lane - nd;
+  double adj[nd];
+#pragma unroll
+  for (int k = 0; k < nd; ++k) adj[k] = 0.0;  // lfx = 0
+  double retval = 0.0;
+  // column of f_x (lanes < nd) or f_u (next nu lanes) and the matching l_x / l_u entry, loaded one knot ahead
+  double cur[nd], nxt[nd], lcur = 0.0, lnxt = 0.0;
+  auto load = [&](int t, double* dst, double& l) {
+    const RecLayout L = rec_layout(nd, nu, nx, bd.ne[t]);
+    const double* rec = slab_rec(bd, t, b, L.size);
+    if (isx || isu) {
+      const double* c = rec + (isx ? L.fx : L.fu) + col * nd;
+#pragma unroll
+      for (int k = 0; k < nd; ++k) dst[k] = c[k];
+      l = rec[(isx ? L.lx : L.lu) + col];
+    }
+  };
+  load(bd.T - 1, cur, lcur);
+  for (int t = bd.T - 1; t >= 0; --t) {
+    if (t > 0) load(t - 1, nxt, lnxt);
+    const int ne = bd.ne[t];
+    double dotc = 0.0;
+#pragma unroll
+    for (int k = 0; k < nd; ++k) dotc += adj[k] * cur[k];
+    double v;
+    if (ne == 0) {
+      // lu = l_u + adj f_u ; adj' = adj f_x + l_x   (the eq terms are empty sums)
+      v = isx ? dotc + lcur : lcur + dotc;
+    } else {
+      const size_t eo = bd.eq_off[t];
+      const RecLayout L = rec_layout(nd, nu, nx, ne);
+      const double* rec = slab_rec(bd, t, b, L.size);
+      double pe[MAXE];
+      for (int i = 0; i < ne; ++i) {
+        double pv = bd.m_val[(eo + i) * B + b], a = 0.0;
+#pragma unroll
+        for (int k = 0; k < nd; ++k)
+          a += bd.m_jac[(eo * nd + k * ne + i) * B + b] * (bd.xs[((size_t)t * nx + k) * B + b] - bd.m_origin[((size_t)t * nx + k) * B + b]);
+        pe[i] = pv + a;
+      }
+      if (isu) {
+        v = lcur;
+        double a = 0.0;
+        for (int k = 0; k < ne; ++k) a += pe[k] * rec[L.eq_u + col * ne + k];
+        v += a;
+        a = 0.0;
+        for (int k = 0; k < ne; ++k) a += (mu * rec[L.eq + k]) * rec[L.eq_u + col * ne + k];
+        v += a;
+        v += dotc;
+      } else if (isx) {
+        v = dotc;
+        v += lcur;
+        double a = 0.0;
+        for (int k = 0; k < ne; ++k) a += (mu * rec[L.eq + k]) * rec[L.eq_x + col * ne + k];
+        v += a;
+        a = 0.0;
+        for (int k = 0; k < ne; ++k) a += pe[k] * rec[L.eq_x + col * ne + k];
+        v += a;
+        a = 0.0;
+        for (int k = 0; k < ne; ++k) a += rec[L.eq + k] * bd.m_jac[(eo * nd + col * ne + k) * B + b];
+        v += a;
+      } else {
+        v = 0.0;
+      }
+    }
+    // |lu|^2 in the reference's order (i = 0 .. nu-1), then the new adjoint to every lane
+    double sq = 0.0;
+#pragma unroll
+    for (int i = 0; i < nu; ++i) { const double li = __shfl_sync(FULL, v, nd + i); sq += li * li; }
+    const double nrm = sqrt(sq);
+    if (retval < nrm) retval = nrm;
+#pragma unroll
+    for (int k = 0; k < nd; ++k) adj[k] = __shfl_sync(FULL, v, k);
+#pragma unroll
+    for (int k = 0; k < nd; ++k) cur[k] = nxt[k];
+    lcur = lnxt;
+  }
+  return retval;
+}
+
+// optimality measures + the decision of update_derivatives / solve's switch (ddp.hpp:660-695, 786-802) for one problem
+// per warp.  phase 0: first sweep and decision (S_FLAG: 1 = multipliers will be updated); phase 1: after the
+// multiplier update, second sweep for the flagged problems (n = opt_obj / mu^0.1, w /= mu).
+template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev& bd, int b, double thr, int phase) {
+  const int B = bd.B;
+  const int lane = threadIdx.x & 31;
+  if (bd.scal[(size_t)S_STATUS * B + b] != 0.0) return;
+  double mu = bd.scal[(size_t)S_MU * B + b];
+  if (phase == 0) {
+    const double opt_obj = optimality_obj_warp<NJ>(bd, b, mu);
+    if (lane != 0) return;
+    const double opt_constr = optimality_constr_problem<NJ>(bd, b);
+    bd.scal[(size_t)S_OPT_OBJ * B + b] = opt_obj;
+    bd.scal[(size_t)S_OPT_CONSTR * B + b] = opt_constr;
+    double flag = 0.0;
+    if (opt_constr < thr && opt_obj < thr) {
+      bd.scal[(size_t)S_STATUS * B + b] = 1.0;  // optimum attained
+    } else if (opt_obj < bd.scal[(size_t)S_W * B + b]) {
+      if (opt_constr < bd.scal[(size_t)S_N * B + b]) flag = 1.0;
+      else bd.scal[(size_t)S_MU * B + b] = mu * 10.0;
+    }
+    bd.scal[(size_t)S_FLAG * B + b] = flag;
+  } else {
+    if (bd.scal[(size_t)S_FLAG * B + b] != 1.0) return;
+    const double oo = optimality_obj_warp<NJ>(bd, b, mu);
+    if (lane != 0) return;
+    bd.scal[(size_t)S_N * B + b] = oo / pow(mu, 0.1);
+    bd.scal[(size_t)S_W * B + b] = bd.scal[(size_t)S_W * B + b] / mu;
+    bd.scal[(size_t)S_MULT_UPDATES * B + b] += 1.0;
+  }
+}
+
+}  // namespace ddpb
+#endif

@@ -50,6 +50,8 @@ struct Emu {
     default: break;                                \
   }
 
+template <int NJ> static void backward_host(const BatchDev& bd, int b, double* sm) { backward_problem<NJ, 1>(bd, b, sm, DevExec{}); }
+
 extern "C" {
 
 void* emu_create(const ddpb_model_desc* d, int B, int T, const int* ne_per_knot, const ddpb_params* p) {
@@ -106,12 +108,18 @@ void emu_linearize(void* hv) {
     return;
   }
   EMU_NJ(h->nj, {
-    LinPlan<NJ> pl;
-    pl.init(bd.hess_mode, bd.ne_max, bd.ne_max);
-    std::vector<double> sm(pl.total);
-    for (int t = 0; t < bd.T; ++t)
-      for (int b = 0; b < bd.B; ++b)
-        if (bd.scal[(size_t)S_STATUS * bd.B + b] == 0.0) linearize_knot<NJ>(h->model, bd, b, t, sm.data(), DevExec{});
+    const int kpb = 3;  // exercise the several-knots-per-CTA path, including a ragged last group
+    for (int t = 0; t < bd.T; ++t) {
+      LinPlan<NJ> pl;
+      pl.init(bd.hess_mode, bd.ne[t], bd.ne[t]);   // shared memory sized for this knot's row count, as the launcher does
+      std::vector<double> sm((size_t)pl.total * kpb);
+      for (int b0 = 0; b0 < bd.B; b0 += kpb) {
+        const int nk = bd.B - b0 < kpb ? bd.B - b0 : kpb;
+        bool any = false;
+        for (int k = 0; k < nk; ++k) any = any || bd.scal[(size_t)S_STATUS * bd.B + b0 + k] == 0.0;
+        if (any) linearize_group<NJ>(h->model, bd, t, b0, nk, bd.ne[t], sm.data(), DevExec{});
+      }
+    }
   });
 }
 void emu_backward(void* hv) {
@@ -120,7 +128,7 @@ void emu_backward(void* hv) {
   EMU_NJ(h->nj, {
     std::vector<double> sm(BwdSmem<NJ>::SIZE);
     for (int b = 0; b < bd.B; ++b)
-      if (bd.scal[(size_t)S_STATUS * bd.B + b] == 0.0) backward_problem<NJ>(bd, b, sm.data(), DevExec{});
+      if (bd.scal[(size_t)S_STATUS * bd.B + b] == 0.0) backward_host<NJ>(bd, b, sm.data());
   });
 }
 void emu_forward(void* hv) {
