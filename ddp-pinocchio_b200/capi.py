@@ -8,7 +8,7 @@ import numpy as np
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libddpb.so")
+LIB_PATH = os.environ.get("DDPB_LIB", os.path.join(PKG_DIR, "libddpb.so"))  # DDPB_LIB: development override
 
 DERIV_FIELDS = ["lfx", "lfxx", "lx", "lu", "lxx", "lux", "luu", "f_val", "fx", "fu", "fxx", "fux", "fuu",
                 "eq_val", "eq_x", "eq_u", "eq_xx", "eq_ux", "eq_uu"]

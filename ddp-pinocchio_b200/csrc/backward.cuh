@@ -55,6 +55,8 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       const RecLayout L = rec_layout(nd, nu, nx, ne);
       const double* rec = slab_rec(bd, t, b, L.size);
       // ---- phase A: every global load of the knot, back to back -------------------------------------------
+      double xorg = 0.0;
+      if (tid < nx) xorg = bd.xs[((size_t)t * nx + tid) * B + b];
       {
         constexpr int EPT = (NTEN + BT - 1) / BT;
         constexpr int CH = EPT < 4 ? EPT : 4;  // tensor elements in flight per lane (CH * nd doubles of registers)
@@ -91,15 +93,20 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
               for (int e = tid; e < ne * nu; e += BT) sm[S::equ + e] = rec[L.eq_u + e];
             }
           }
+          double vx[nd], wacc[CH];
+#pragma unroll
+          for (int k = 0; k < nd; ++k) vx[k] = sm[S::Vx + k];
+#pragma unroll
+          for (int u = 0; u < CH; ++u) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < nd; ++k) a += vx[k] * ten[u][k];
+            wacc[u] = a;
+          }
 #pragma unroll
           for (int u = 0; u < CH; ++u) {
             const int e = tid + (u0 + u) * BT;
-            if (u0 + u < EPT && e < NTEN) {
-              double a = 0.0;
-#pragma unroll
-              for (int k = 0; k < nd; ++k) a += sm[S::Vx + k] * ten[u][k];
-              sm[S::Wf + e] = a;
-            }
+            if (u0 + u < EPT && e < NTEN) sm[S::Wf + e] = wacc[u];
           }
         }
       }
@@ -107,15 +114,22 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       // ---- phase B: tmp, tmp2, VF = V_xx f_x, VU = V_xx f_u ----------------------------------------------------
       for (int e = tid; e < ne; e += BT) sm[S::tmp + e] = sm[S::pe + e] + mu * sm[S::eqv + e];
       for (int e = tid; e < ne * nd; e += BT) sm[S::tmp2 + e] = sm[S::pex + e] + mu * sm[S::eqx + e];
-      FOR_ELEMS(e, nd * nd + nd * nu) {
-        const bool isF = e < nd * nd;
-        const int ee = isF ? e : e - nd * nd;
-        const int r = ee % nd, c = ee / nd;
-        const double* M = isF ? sm + S::fx : sm + S::fu;
-        double a = 0.0;
+      {
+        // results are kept in registers until every chain of the lane is done: a shared-memory store between two
+        // chains would order them (possible aliasing) and serialise the FMA latencies
+        constexpr int NB = nd * nd + nd * nu;
+        double acc[(NB + BT - 1) / BT];
+        FOR_ELEMS(e, NB) {
+          const bool isF = e < nd * nd;
+          const int ee = isF ? e : e - nd * nd;
+          const int r = ee % nd, c = ee / nd;
+          const double* M = isF ? sm + S::fx : sm + S::fu;
+          double a = 0.0;
 #pragma unroll
-        for (int k = 0; k < nd; ++k) a += sm[S::Vxx + k * nd + r] * M[c * nd + k];
-        sm[(isF ? S::VF : S::VU) + ee] = a;
+          for (int k = 0; k < nd; ++k) a += sm[S::Vxx + k * nd + r] * M[c * nd + k];
+          acc[u_] = a;
+        }
+        FOR_ELEMS(e, NB) sm[S::VF + e] = acc[u_];  // VF | VU are adjacent
       }
       ex.sync();
       const double* fx = sm + S::fx;
@@ -128,6 +142,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       const double* tmp = sm + S::tmp;
       const double* tmp2 = sm + S::tmp2;
       // ---- phase C: all Q elements as one task list: Q_xx | Q_ux | Q_uu | Q_x | Q_u ------------------------------
+      double qacc[(NTEN + nd + nu + BT - 1) / BT];
       FOR_ELEMS(e, NTEN + nd + nu) {
         if (e < nQxx) {
           const int r = e % nd, c = e / nd;
@@ -148,7 +163,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
             q += a;
           }
           q += sm[S::Wf + e];
-          sm[S::Qxx + e] = q;
+          qacc[u_] = q;
         } else if (e < nQxx + nQux) {
           const int ee = e - nQxx;
           const int r = ee % nu, c = ee / nu;
@@ -166,7 +181,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
             q += a;
           }
           q += sm[S::Wf + e];
-          sm[S::Qux + ee] = q;
+          qacc[u_] = q;
         } else if (e < NTEN) {
           const int ee = e - nQxx - nQux;
           const int r = ee % nu, c = ee / nu;
@@ -184,7 +199,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
             q += a;
           }
           q += sm[S::Wf + e];
-          sm[S::Quu + ee] = q;
+          qacc[u_] = q;
         } else if (e < NTEN + nd) {
           const int i = e - NTEN;
           double q = sm[S::small + i], a = 0.0;
@@ -199,7 +214,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
             for (int k = 0; k < ne; ++k) a += pex[i * ne + k] * eqv[k];
             q += a;
           }
-          sm[S::Qx + i] = q;
+          qacc[u_] = q;
         } else {
           const int i = e - NTEN - nd;
           double q = sm[S::small + nd + i], a = 0.0;
@@ -211,9 +226,11 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
             for (int k = 0; k < ne; ++k) a += equ[i * ne + k] * tmp[k];
             q += a;
           }
-          sm[S::Qu + i] = q;
+          qacc[u_] = q;
         }
       }
+      // Q_xx | Q_ux | Q_uu are adjacent in shared memory and in task-list order; Q_x | Q_u sit before them
+      FOR_ELEMS(e, NTEN + nd + nu) sm[e < NTEN ? S::Qxx + e : S::Qx + (e - NTEN)] = qacc[u_];
       ex.sync();
       // ---- phase D: Cholesky of the lower triangle of Q_uu + reg I (Eigen::LLT semantics: fail when a pivot <= 0).
       // Left-looking, column by column; the rows below the pivot are spread over lanes and every sum keeps the
@@ -287,23 +304,27 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
           }
         }
       }
-      FOR_ELEMS(e, nx) bd.fb_origin[((size_t)t * nx + e) * B + b] = bd.xs[((size_t)t * nx + e) * B + b];
+      if (tid < nx) bd.fb_origin[((size_t)t * nx + tid) * B + b] = xorg;
       ex.sync();
       // ---- phase F: V_x = Q_x + Q_ux^T k ; V_xx = Q_xx + Q_ux^T K ---------------------------------------------------
-      FOR_ELEMS(e, nd * nd + nd) {
-        if (e < nd * nd) {
-          const int r = e % nd, c = e / nd;
-          double a = 0.0;
+      {
+        double vacc[(nd * nd + nd + BT - 1) / BT];
+        FOR_ELEMS(e, nd * nd + nd) {
+          if (e < nd * nd) {
+            const int r = e % nd, c = e / nd;
+            double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < nu; ++k) a += sm[S::Qux + r * nu + k] * sm[S::KK + c * nu + k];
-          sm[S::Vxx + e] = sm[S::Qxx + e] + a;
-        } else {
-          const int i = e - nd * nd;
-          double a = 0.0;
+            for (int k = 0; k < nu; ++k) a += sm[S::Qux + r * nu + k] * sm[S::KK + c * nu + k];
+            vacc[u_] = sm[S::Qxx + e] + a;
+          } else {
+            const int i = e - nd * nd;
+            double a = 0.0;
 #pragma unroll
-          for (int k = 0; k < nu; ++k) a += sm[S::Qux + i * nu + k] * sm[S::kk + k];
-          sm[S::Vx + i] = sm[S::Qx + i] + a;
+            for (int k = 0; k < nu; ++k) a += sm[S::Qux + i * nu + k] * sm[S::kk + k];
+            vacc[u_] = sm[S::Qx + i] + a;
+          }
         }
+        FOR_ELEMS(e, nd * nd + nd) sm[S::Vxx + e] = vacc[u_];  // V_xx | V_x are adjacent
       }
       ex.sync();
     }

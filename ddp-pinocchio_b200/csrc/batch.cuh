@@ -62,6 +62,7 @@ struct BatchDev {
   const int* ne;                      // [T]
   const int* eq_off;                  // [T+1]
   const long long* slab_off;          // [T+1] prefix sums of the per-knot record sizes
+  unsigned long long* dbg;            // optional [16] per-phase cycle counters (development; nullptr = off)
 };
 
 DDPB_HD double* slab_rec(const BatchDev& bd, int t, int b, int rec_size) {
@@ -70,6 +71,22 @@ DDPB_HD double* slab_rec(const BatchDev& bd, int t, int b, int rec_size) {
 
 // ---- execution context: the same CTA body runs on the device (threads of one block) and, for the
 // CPU unit tests of tests/hostemu, as a plain sequential loop over the tasks of every phase -------
+// development aid: accumulate the cycles thread 0 of a CTA spent since *t0 into bd.dbg[slot]
+#if defined(__CUDA_ARCH__)
+#define DDPB_PHASE_MARK(bd, slot, t0)                                                            \
+  do {                                                                                           \
+    if ((bd).dbg && threadIdx.x == 0) {                                                          \
+      const long long now_ = clock64();                                                          \
+      atomicAdd((bd).dbg + (slot), (unsigned long long)(now_ - (t0)));                           \
+      (t0) = now_;                                                                               \
+    }                                                                                            \
+  } while (0)
+#define DDPB_PHASE_START(bd, t0) long long t0 = ((bd).dbg && threadIdx.x == 0) ? clock64() : 0
+#else
+#define DDPB_PHASE_MARK(bd, slot, t0) do { } while (0)
+#define DDPB_PHASE_START(bd, t0) long long t0 = 0; (void)t0
+#endif
+
 struct DevExec {
   DDPB_HD int tid() const {
 #if defined(__CUDA_ARCH__)

@@ -355,7 +355,7 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   // problems per CTA of the linearization: small models leave most lanes of a one-knot CTA idle
   h->lin_kpb = fdv ? 1 : (n <= 1 ? 16 : (n == 2 ? 8 : (n <= 4 ? 2 : 1)));
   if (const char* e = getenv("DDPB_LIN_KPB")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->lin_kpb = v; }
-  DISPATCH(h->mt, { h->lin_smem = L::lin_smem_bytes(p->hess_mode, bd.ne_max) * h->lin_kpb; });
+  DISPATCH(h->mt, { h->lin_smem = L::lin_smem_bytes(p->hess_mode, bd.ne_max, p->eq_kind) * h->lin_kpb; });
   if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) { ddpb_batch_destroy(h); return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory"); }
   DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });
   DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(); });
@@ -661,6 +661,21 @@ int ddpb_snapshot_restore(ddpb_batch* h) {
   // the new-trajectory storage is a clone of the trajectory (ddp.hpp:752)
   CU(cudaMemcpyAsync(bd.xs_new, h->snap + off[0], (off[1] - off[0]) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   CU(cudaMemcpyAsync(bd.us_new, h->snap + off[1], (off[2] - off[1]) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return DDPB_OK;
+}
+// development aid (not declared in ddpb.h): per-phase cycle counters of the linearization kernel
+int ddpb_debug_phase_cycles(ddpb_batch* h, int enable, unsigned long long* out16) {
+  ENTER(h);
+  if (enable && !h->bd.dbg) {
+    int rc = dev_alloc(h, &h->bd.dbg, 16);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(h->bd.dbg, 0, 16 * sizeof(unsigned long long), h->stream));
+  }
+  if (out16 && h->bd.dbg) {
+    CU(cudaMemcpyAsync(out16, h->bd.dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemsetAsync(h->bd.dbg, 0, 16 * sizeof(unsigned long long), h->stream));
+  }
   return DDPB_OK;
 }
 int ddpb_measure_fp64_peak(int device, double* tflops) {

@@ -14,7 +14,11 @@ constexpr int KNJ = DDPB_NJ;
 
 #if DDPB_NJ > 0
 // grid: (knots t0..t1-1) x (groups of `kpb` consecutive problems); all knots of a launch have the same ne
-template <int NJ> __global__ void __launch_bounds__(256) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
+#ifndef DDPB_LIN_LB_THREADS
+#define DDPB_LIN_LB_THREADS 256
+#define DDPB_LIN_LB_BLOCKS 1
+#endif
+template <int NJ> __global__ void __launch_bounds__(DDPB_LIN_LB_THREADS, DDPB_LIN_LB_BLOCKS) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
                                                                           int t0, int kpb, int ne_sm) {
   extern __shared__ __align__(16) double sm[];
   const int groups = (bd.B + kpb - 1) / kpb;
@@ -85,13 +89,13 @@ template <int NJ> __global__ void optimality_kernel(const __grid_constant__ Batc
 
 constexpr int TPP = 32;  // threads per block of the thread-per-problem kernels
 
-template <> size_t Launch<KNJ>::lin_smem_bytes(int hess_mode, int ne_max) {
+template <> size_t Launch<KNJ>::lin_smem_bytes(int hess_mode, int ne_max, int eq_kind) {
 #if DDPB_NJ > 0
   LinPlan<KNJ> pl;
-  pl.init(hess_mode, ne_max, ne_max);
+  pl.init(hess_mode, ne_max, ne_max, eq_kind);
   return (size_t)pl.total * sizeof(double);
 #else
-  (void)hess_mode; (void)ne_max;
+  (void)hess_mode; (void)ne_max; (void)eq_kind;
   return 0;
 #endif
 }
@@ -112,7 +116,7 @@ template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
 }
 template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, int threads, int kpb, int t0, int t1, int ne_sm, cudaStream_t s) {
 #if DDPB_NJ > 0
-  const size_t smem = lin_smem_bytes(bd.hess_mode, ne_sm) * kpb;
+  const size_t smem = lin_smem_bytes(bd.hess_mode, ne_sm, bd.eq_kind) * kpb;
   const int groups = (bd.B + kpb - 1) / kpb;
   linearize_kernel<KNJ><<<(unsigned)((size_t)groups * (t1 - t0)), threads, smem, s>>>(m, bd, t0, kpb, ne_sm);
 #else

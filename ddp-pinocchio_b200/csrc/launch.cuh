@@ -9,7 +9,7 @@
 namespace ddpb {
 
 template <int NJ> struct Launch {
-  static size_t lin_smem_bytes(int hess_mode, int ne_max);
+  static size_t lin_smem_bytes(int hess_mode, int ne_max, int eq_kind);
   static size_t bwd_smem_bytes();
   static cudaError_t prepare(size_t lin_smem);
   // knots [t0, t1) (all with the same number of equality rows <= ne_sm), kpb problems per CTA

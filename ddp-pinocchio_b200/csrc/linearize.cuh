@@ -29,13 +29,20 @@ template <int NJ> struct LinPlan {
   static constexpr int N = 3 * NJ;
   int mode, P, NQ, NT;  // evaluation points, distinct-q sets, points that need first-order data
   int ne;               // equality rows at this knot
+  bool u_points;        // whether the u-perturbed evaluation points exist
   // shared-memory offsets (doubles)
   int o_base, o_tgt, o_qrec, o_vrec, o_fval, o_eqv, o_J, o_eqxu, total;
   DDPB_HD static int points(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + N : 1 + N + N * (N - 1) / 2; }
   DDPB_HD static int qsets(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + NJ : 1 + NJ + NJ * (NJ - 1) / 2; }
-  DDPB_HD void init(int mode_, int ne_max, int ne_) {
+  // FD-of-Jacobians mode: the reference evaluates (f_x, f_u) at the u-perturbed points only to difference f_u
+  // (problem.hpp:138-145), and f_u = dt M^-1(q) cannot change when only u moves: f_uu (and eq_uu of a configuration
+  // constraint) are exact zeros there too.  Those N/3 points are therefore dropped unless a spatial constraint needs
+  // the frame Jacobian at their q_{t+2}.
+  DDPB_HD void init(int mode_, int ne_max, int ne_, int eq_kind = EQ_NONE) {
     mode = mode_; ne = ne_;
     P = points(mode); NQ = qsets(mode);
+    u_points = !(mode == HESS_FD_JACOBIANS && !(eq_kind == EQ_SPATIAL && ne_ > 0));
+    if (!u_points) P = 1 + 2 * NJ;
     NT = mode == HESS_FD_JACOBIANS ? P : 1;
     int o = 0;
     o_base = o; o += 4 * NJ;
@@ -81,13 +88,14 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   const int B = bd.B;
   const int ne = bd.ne[t];
   LinPlan<NJ> pl;
-  pl.init(bd.hess_mode, ne_sm, ne);
+  pl.init(bd.hess_mode, ne_sm, ne, bd.eq_kind);
   const double eps = pl.eps();
   const double dt = bd.dt;
   const int tid = ex.tid(), nthr = ex.nthr();
   const size_t KS = (size_t)pl.total;  // shared-memory stride between the knots of this CTA
 #define SM(kk, off) (sm_all + (size_t)(kk) * KS + (off))
 
+  DDPB_PHASE_START(bd, pc_);
   // phase 0: stage x_t, u_t and the target
   for (int idx = tid; idx < nk * (N + ne); idx += nthr) {
     const int kk = idx / (N + ne), e = idx - kk * (N + ne), b = b0 + kk;
@@ -96,6 +104,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     else SM(kk, pl.o_tgt)[e - N] = bd.targets[((size_t)bd.eq_off[t] + (e - N)) * B + b];
   }
   ex.sync();
+  DDPB_PHASE_MARK(bd, 0, pc_);
 
   // phase 1: q-only data for every distinct configuration
   for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
@@ -109,6 +118,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     q_task<NJ>(m, q, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
   }
   ex.sync();
+  DDPB_PHASE_MARK(bd, 1, pc_);
 
   // phase 2: accelerations (and body data where tangents are needed) at every evaluation point
   for (int idx = tid; idx < nk * pl.P; idx += nthr) {
@@ -134,6 +144,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     }
   }
   ex.sync();
+  DDPB_PHASE_MARK(bd, 2, pc_);
 
   // phase 3: tangent columns of inverse dynamics and columns of M^-1
   {
@@ -164,6 +175,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     }
   }
   ex.sync();
+  DDPB_PHASE_MARK(bd, 3, pc_);
 
   // phase 4: da/dq = -M^-1 dtau/dq, da/dv = -M^-1 dtau/dv, already scaled into the bottom blocks of
   // fx (problem.hpp:495-502): DQ <- dt * da/dq ; DV <- dt * da/dv + I
@@ -189,6 +201,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     for (int k = 0; k < NJ; ++k) colp[k] = dst[k];
   }
   ex.sync();
+  DDPB_PHASE_MARK(bd, 4, pc_);
 
   // element accessors of fx / fu at point p (p < NT) of knot kk
   auto fx_at = [&](int kk, int p, int r, int c) -> double {
@@ -220,6 +233,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     }
   }
   ex.sync();
+  DDPB_PHASE_MARK(bd, 5, pc_);
   // eq_x = c_x [I, dt I] fx ; eq_u = c_x [I, dt I] fu   (problem.hpp:603-604, applied twice)
   for (int idx = tid; idx < (ne > 0 ? nk * pl.NT * ne * N : 0); idx += nthr) {
     const int kk = idx / (pl.NT * ne * N), task = idx - kk * pl.NT * ne * N;
@@ -239,80 +253,120 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     SM(kk, pl.o_eqxu)[(size_t)p * ne_sm * N + c * ne + r] = acc;
   }
   ex.sync();
+  DDPB_PHASE_MARK(bd, 6, pc_);
 
-  // phase 6: assemble the records and stream them out.  The nk records are adjacent in HBM, so the CTA writes
-  // one contiguous span: element e of the span belongs to knot e / L.size.
+  // phase 6: assemble the records and stream them out, block by block.  Inside a block the element index runs
+  // fastest over consecutive threads (coalesced stores); block sizes of the dynamics part are compile-time
+  // constants, so the index arithmetic is multiplications by reciprocals, not divisions.
   const RecLayout L = rec_layout(nd, nu, nx, ne);
   double* rec0 = slab_rec(bd, t, b0, L.size);
   const double inv_eps = 1.0 / eps, inv_eps2 = 1.0 / (eps * eps);
   const size_t ps = (size_t)ne_sm * N;  // eqxu stride per point
-  auto diag = [&](double f1, double f0, double col) -> double {
-    double df = f1 - f0;
-    df -= eps * col;
-    df *= 2.0;
-    return df * inv_eps2;
-  };
-  auto offd = [&](double f1, double f0, double col1, double col2, double d1, double d2) -> double {
-    double df = f1 - f0;
-    df -= eps * col1;
-    df -= eps * col2;
-    df *= 2.0;
-    return 0.5 * (df * inv_eps2 - d1 - d2);
-  };
-  for (int idx = tid; idx < nk * L.size; idx += nthr) {
-    const int kk = idx / L.size, o = idx - kk * L.size;
-    const double* base = SM(kk, pl.o_base);
-    const double* fval = SM(kk, pl.o_fval);
-    const double* eqv = SM(kk, pl.o_eqv);
-    const double* eqxu = SM(kk, pl.o_eqxu);
-    // problem.hpp:192-296 helpers (value-based FD): row k of function `which` (0 = f, 1 = eq), global tangent indices
-    auto jcol = [&](int which, int k, int g) -> double {
-      if (which == 0) return g < nd ? fx_at(kk, 0, k, g) : fu_at(kk, 0, k, g - nd);
-      return eqxu[g * ne + k];
-    };
-    auto val = [&](int which, int p, int k) -> double { return which == 0 ? fval[p * nx + k] : eqv[p * ne_sm + k]; };
-    auto hess = [&](int which, int k, int ga, int gb) -> double {
-      const double f0 = val(which, 0, k);
-      if (ga == gb) return diag(val(which, 1 + ga, k), f0, jcol(which, k, ga));
-      const int i = ga < gb ? ga : gb, j = ga < gb ? gb : ga;
-      const double ci = jcol(which, k, i), cj = jcol(which, k, j);
-      const double di = diag(val(which, 1 + i, k), f0, ci), dj = diag(val(which, 1 + j, k), f0, cj);
-      return offd(val(which, 1 + N + pair_rank(i, j, N), k), f0, ci, cj, di, dj);
-    };
-    const bool fdj = pl.mode == HESS_FD_JACOBIANS;
-    double v = 0.0;
-    if (o < L.lu) v = 0.0;                                                        // lx
-    else if (o < L.lxx) v = bd.c * base[2 * n + (o - L.lu)];                      // lu = c u
-    else if (o < L.luu) v = 0.0;                                                  // lxx, lux
-    else if (o < L.f) { const int e = o - L.luu; v = (e / nu == e % nu) ? bd.c : 0.0; }   // luu = c I
-    else if (o < L.fx) v = fval[o - L.f];
-    else if (o < L.fu) { const int e = o - L.fx; v = fx_at(kk, 0, e % nd, e / nd); }
-    else if (o < L.fxx) { const int e = o - L.fu; v = fu_at(kk, 0, e % nd, e / nd); }
-    else if (o < L.fux) {
-      const int e = o - L.fxx, k = e % nd, j = (e / nd) % nd, i = e / (nd * nd);
-      // problem.hpp:128-145: T(k,j,idx) = (J'(k,j) - J(k,j)) / eps ; rows k < n are exact constants
-      v = fdj ? (k < n ? 0.0 : (fx_at(kk, 1 + i, k, j) - fx_at(kk, 0, k, j)) * inv_eps) : hess(0, k, j, i);
-    } else if (o < L.fuu) {
-      const int e = o - L.fux, k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
-      v = fdj ? (k < n ? 0.0 : (fu_at(kk, 1 + i, k, j) - fu_at(kk, 0, k, j)) * inv_eps) : hess(0, k, nd + j, i);
-    } else if (o < L.eq) {
-      const int e = o - L.fuu, k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
-      v = fdj ? (k < n ? 0.0 : (fu_at(kk, 1 + nd + i, k, j) - fu_at(kk, 0, k, j)) * inv_eps) : hess(0, k, nd + j, nd + i);
-    } else if (o < L.eq_x) v = eqv[o - L.eq];
-    else if (o < L.eq_u) v = eqxu[o - L.eq_x];
-    else if (o < L.eq_xx) v = eqxu[ne * nd + (o - L.eq_u)];
-    else if (o < L.eq_ux) {
-      const int e = o - L.eq_xx, k = e % ne, j = (e / ne) % nd, i = e / (ne * nd);
-      v = fdj ? (eqxu[(1 + i) * ps + j * ne + k] - eqxu[j * ne + k]) * inv_eps : hess(1, k, j, i);
-    } else if (o < L.eq_uu) {
-      const int e = o - L.eq_ux, k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
-      v = fdj ? (eqxu[(1 + i) * ps + (nd + j) * ne + k] - eqxu[(nd + j) * ne + k]) * inv_eps : hess(1, k, nd + j, i);
-    } else if (o < L.eq_uu + ne * nu * nu) {
-      const int e = o - L.eq_uu, k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
-      v = fdj ? (eqxu[(1 + nd + i) * ps + (nd + j) * ne + k] - eqxu[(nd + j) * ne + k]) * inv_eps : hess(1, k, nd + j, nd + i);
+  const bool fdj = pl.mode == HESS_FD_JACOBIANS;
+#define FOR_BLOCK(kk, e, SIZE) _Pragma("unroll 4") for (int idx_ = tid, kk = idx_ / (SIZE), e = idx_ - kk * (SIZE); idx_ < nk * (SIZE); idx_ += nthr, kk = idx_ / (SIZE), e = idx_ - kk * (SIZE))
+#define REC(kk, off) rec0[(size_t)(kk) * L.size + (off)]
+  {
+    // cost blocks lx | lu | lxx | lux | luu (adjacent), then f
+    constexpr int CB = nd + nu + nd * nd + nu * nd + nu * nu;
+    FOR_BLOCK(kk, e, CB) {
+      double v = 0.0;
+      if (e >= nd && e < nd + nu) v = bd.c * SM(kk, pl.o_base)[2 * n + (e - nd)];              // lu = c u
+      else if (e >= CB - nu * nu) { const int q = e - (CB - nu * nu); v = (q / nu == q % nu) ? bd.c : 0.0; }  // luu = c I
+      REC(kk, L.lx + e) = v;
     }
-    rec0[idx] = v;
+    FOR_BLOCK(kk, e, nx) REC(kk, L.f + e) = SM(kk, pl.o_fval)[e];
+    FOR_BLOCK(kk, e, nd * nd) REC(kk, L.fx + e) = fx_at(kk, 0, e % nd, e / nd);
+    FOR_BLOCK(kk, e, nd * nu) REC(kk, L.fu + e) = fu_at(kk, 0, e % nd, e / nd);
+    if (L.size > L.eq_uu + ne * nu * nu) FOR_BLOCK(kk, e, 1) REC(kk, L.size - 1) = 0.0;  // padding double
   }
+  if (fdj) {
+    // problem.hpp:128-145: T(k,j,idx) = (J'(k,j) - J(k,j)) / eps ; rows k < n are exact constants (zero difference).
+    // bottom rows: fx(k,j) of point p is DQ/DV[(k-n) + j'*n] of that point's record; fu(k,j) is dt * M^-1 of its q-set.
+    FOR_BLOCK(kk, e, nd * nd * nd) {
+      const int k = e % nd, j = (e / nd) % nd, i = e / (nd * nd);
+      double v = 0.0;
+      if (k >= n) {
+        const int off = (j < n ? V::DQ + j * NJ : V::DV + (j - n) * NJ) + (k - n);
+        const double* vr = SM(kk, pl.o_vrec);
+        v = (vr[(size_t)(1 + i) * V::SIZE + off] - vr[off]) * inv_eps;
+      }
+      REC(kk, L.fxx + e) = v;
+    }
+    FOR_BLOCK(kk, e, nd * nu * nd) {
+      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
+      double v = 0.0;
+      if (k >= n && i < n) {  // only a q-perturbation changes M^-1; v-perturbed points share the base q-set (exact zero)
+        const double* qr = SM(kk, pl.o_qrec);
+        const int off = Q::MINV + j * NJ + (k - n);
+        v = (qr[(size_t)(1 + i) * Q::SIZE + off] * dt - qr[off] * dt) * inv_eps;
+      }
+      REC(kk, L.fux + e) = v;
+    }
+    FOR_BLOCK(kk, e, nd * nu * nu) REC(kk, L.fuu + e) = 0.0;  // u-perturbed points share the base q-set: same M^-1, exact zero
+    if (ne > 0) {
+      FOR_BLOCK(kk, e, ne) REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e];
+      FOR_BLOCK(kk, e, ne * N) REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e];  // eq_x | eq_u adjacent on both sides
+      FOR_BLOCK(kk, e, ne * nd * nd) {
+        const int k = e % ne, j = (e / ne) % nd, i = e / (ne * nd);
+        const double* x = SM(kk, pl.o_eqxu);
+        REC(kk, L.eq_xx + e) = (x[(1 + i) * ps + j * ne + k] - x[j * ne + k]) * inv_eps;
+      }
+      FOR_BLOCK(kk, e, ne * nu * nd) {
+        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
+        const double* x = SM(kk, pl.o_eqxu);
+        REC(kk, L.eq_ux + e) = (x[(1 + i) * ps + (nd + j) * ne + k] - x[(nd + j) * ne + k]) * inv_eps;
+      }
+      FOR_BLOCK(kk, e, ne * nu * nu) {
+        const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
+        const double* x = SM(kk, pl.o_eqxu);
+        REC(kk, L.eq_uu + e) = pl.u_points ? (x[(1 + nd + i) * ps + (nd + j) * ne + k] - x[(nd + j) * ne + k]) * inv_eps : 0.0;
+      }
+    }
+  } else {
+    // problem.hpp:192-296 (value-based FD): row k of function `which` (0 = f, 1 = eq), global tangent indices ga, gb
+    auto diag = [&](double f1, double f0, double col) -> double {
+      double df = f1 - f0;
+      df -= eps * col;
+      df *= 2.0;
+      return df * inv_eps2;
+    };
+    auto offd = [&](double f1, double f0, double col1, double col2, double d1, double d2) -> double {
+      double df = f1 - f0;
+      df -= eps * col1;
+      df -= eps * col2;
+      df *= 2.0;
+      return 0.5 * (df * inv_eps2 - d1 - d2);
+    };
+    auto hess = [&](int kk, int which, int k, int ga, int gb) -> double {
+      const double* fval = SM(kk, pl.o_fval);
+      const double* eqv = SM(kk, pl.o_eqv);
+      const double* eqxu = SM(kk, pl.o_eqxu);
+      auto jcol = [&](int g) -> double {
+        if (which == 0) return g < nd ? fx_at(kk, 0, k, g) : fu_at(kk, 0, k, g - nd);
+        return eqxu[g * ne + k];
+      };
+      auto val = [&](int p) -> double { return which == 0 ? fval[p * nx + k] : eqv[p * ne_sm + k]; };
+      const double f0 = val(0);
+      if (ga == gb) return diag(val(1 + ga), f0, jcol(ga));
+      const int i = ga < gb ? ga : gb, j = ga < gb ? gb : ga;
+      const double ci = jcol(i), cj = jcol(j);
+      const double di = diag(val(1 + i), f0, ci), dj = diag(val(1 + j), f0, cj);
+      return offd(val(1 + N + pair_rank(i, j, N)), f0, ci, cj, di, dj);
+    };
+    FOR_BLOCK(kk, e, nd * nd * nd) { const int k = e % nd, j = (e / nd) % nd, i = e / (nd * nd); REC(kk, L.fxx + e) = hess(kk, 0, k, j, i); }
+    FOR_BLOCK(kk, e, nd * nu * nd) { const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu); REC(kk, L.fux + e) = hess(kk, 0, k, nd + j, i); }
+    FOR_BLOCK(kk, e, nd * nu * nu) { const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu); REC(kk, L.fuu + e) = hess(kk, 0, k, nd + j, nd + i); }
+    if (ne > 0) {
+      FOR_BLOCK(kk, e, ne) REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e];
+      FOR_BLOCK(kk, e, ne * N) REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e];
+      FOR_BLOCK(kk, e, ne * nd * nd) { const int k = e % ne, j = (e / ne) % nd, i = e / (ne * nd); REC(kk, L.eq_xx + e) = hess(kk, 1, k, j, i); }
+      FOR_BLOCK(kk, e, ne * nu * nd) { const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu); REC(kk, L.eq_ux + e) = hess(kk, 1, k, nd + j, i); }
+      FOR_BLOCK(kk, e, ne * nu * nu) { const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu); REC(kk, L.eq_uu + e) = hess(kk, 1, k, nd + j, nd + i); }
+    }
+  }
+#undef FOR_BLOCK
+#undef REC
+  DDPB_PHASE_MARK(bd, 7, pc_);
 #undef SM
 }
 

@@ -111,7 +111,7 @@ void emu_linearize(void* hv) {
     const int kpb = 3;  // exercise the several-knots-per-CTA path, including a ragged last group
     for (int t = 0; t < bd.T; ++t) {
       LinPlan<NJ> pl;
-      pl.init(bd.hess_mode, bd.ne[t], bd.ne[t]);   // shared memory sized for this knot's row count, as the launcher does
+      pl.init(bd.hess_mode, bd.ne[t], bd.ne[t], bd.eq_kind);   // shared memory sized for this knot's row count, as the launcher does
       std::vector<double> sm((size_t)pl.total * kpb);
       for (int b0 = 0; b0 < bd.B; b0 += kpb) {
         const int nk = bd.B - b0 < kpb ? bd.B - b0 : kpb;

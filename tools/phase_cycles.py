@@ -1,0 +1,22 @@
+"""Per-phase cycle breakdown of the linearization kernel (development aid; uses the undeclared debug entry point)."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import ddpb_loader
+ddpb_loader.load()
+from ddp_pinocchio_b200 import capi, synthetic
+for name in sys.argv[1:] or ["c3"]:
+    w = synthetic.workload(name)
+    g = w.generate()
+    bt = capi.Batch.from_workload(w)
+    bt.set_targets(g["targets"]); bt.make_trajectory(g["x0"], g["us"]); bt.set_multipliers(None, g["mult_jac"])
+    bt.compute_derivatives()
+    out = (C.c_ulonglong * 16)()
+    capi.lib().ddpb_debug_phase_cycles(bt._h, 1, None)
+    bt.compute_derivatives()
+    capi.lib().ddpb_debug_phase_cycles(bt._h, 1, out)
+    v = np.array(list(out), dtype=float)
+    names = ["stage", "q_task", "v_task", "columns", "products", "eq_values", "eq_jac", "assemble"]
+    tot = v[:8].sum()
+    print(w.name, " ".join(f"{n}={100*x/tot:.1f}%" for n, x in zip(names, v[:8])), f"| cycles/CTA {tot / (w.B * w.T / max(1, int(os.environ.get('DDPB_LIN_KPB', '1')))):.0f}")
+    bt.close()
