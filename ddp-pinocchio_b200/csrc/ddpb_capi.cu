@@ -124,6 +124,7 @@ struct ddpb_batch {
   std::vector<long long> slab_off;
   std::vector<void*> allocs;
   double* costs_old = nullptr;
+  double *ls_xs = nullptr, *ls_us = nullptr;  // scratch trajectories of the concurrent line-search trials
   double* stage = nullptr;
   size_t stage_bytes = 0;
   double* h_stage = nullptr;  // pinned bounce buffer for small scalar traffic
@@ -211,7 +212,8 @@ static int launch_backward(ddpb_batch* h) {
 }
 static int launch_forward(ddpb_batch* h) {
   PhaseScope ps(h, 2);
-  DISPATCH(h->mt, L::forward(h->model, h->bd, h->costs_old, h->stream));
+  DISPATCH(h->mt, L::forward(h->model, h->bd, h->costs_old, h->ls_xs, h->ls_us, h->stream));
+  h->launches += 1;  // cost_seq_aug of the current trajectory + the concurrent line search
   return check_launch(h, "forward");
 }
 static int launch_al_update(ddpb_batch* h, double thr) {
@@ -330,6 +332,11 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   A(bd.fb_origin, T * nx * B); A(bd.fb_k, T * nu * B); A(bd.fb_K, T * nu * nd * B);
   A(bd.slab, (size_t)h->slab_off[T] * B); A(bd.scal, (size_t)NSCALARS * B); A(h->costs_old, (size_t)(T + 1) * B);
   A(d_ne, T); A(d_eo, T + 1); A(d_so, T + 1);
+  {
+    int slots = 1;
+    DISPATCH(h->mt, { slots = L::linesearch_slots(); });
+    A(h->ls_xs, (size_t)slots * (T + 1) * nx * B); A(h->ls_us, (size_t)slots * T * nu * B);
+  }
 #undef A
   if (rc) { ddpb_batch_destroy(h); return rc; }
   bd.ne = d_ne; bd.eq_off = d_eo; bd.slab_off = d_so;

@@ -121,9 +121,48 @@ template <int NJ> DDPB_HD double cost_seq_problem(const ModelDev& m, const Batch
   return plain;
 }
 
-// forward_pass with line search for one problem
-template <int NJ> DDPB_HD void forward_problem(const ModelDev& m, const BatchDev& bd, int b, double* costs_old) {
+// one trial of the line search (ddp_fwd.ipp:39-56): closed-loop rollout with step size `step` from x_0, written
+// to (xs_out, us_out) (same SoA layout as the trajectory), and sum_t (cost_new - cost_old) in the reference's order
+template <int NJ>
+DDPB_HD void rollout_candidate(const ModelDev& m, const BatchDev& bd, int b, double step, double mu, const double* costs_old, double* xs_out,
+                               double* us_out, double* sum_out, double* merit_out, double* plain_out) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n;
+  const int B = bd.B, T = bd.T;
+  double x[nx], xn[nx], u[nu];
+#pragma unroll
+  for (int k = 0; k < nx; ++k) x[k] = bd.xs_new[(size_t)k * B + b];  // x_0 of the new-trajectory storage (= x_0)
+  double sum = 0.0, merit = 0.0, plain = 0.0;
+  for (int t = 0; t < T; ++t) {
+    double dx[nd];
+#pragma unroll
+    for (int k = 0; k < nd; ++k) dx[k] = x[k] - bd.xs[((size_t)t * nx + k) * B + b];
+#pragma unroll
+    for (int i = 0; i < nu; ++i) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < nd; ++k) a += bd.fb_K[((size_t)t * nu * nd + k * nu + i) * B + b] * dx[k];
+      u[i] = bd.us[((size_t)t * nu + i) * B + b] + step * bd.fb_k[((size_t)t * nu + i) * B + b] + a;
+      us_out[((size_t)t * nu + i) * B + b] = u[i];
+    }
+    DynOps<NJ>::eval(m, bd.dt, x, u, xn);
+    const double cn = merit_term<NJ>(m, bd, b, t, x, u, xn, mu);
+    sum += cn - costs_old[(size_t)t * B + b];
+    merit += cn;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < nu; ++k) s += u[k] * u[k];
+    plain += 0.5 * bd.c * s;
+#pragma unroll
+    for (int k = 0; k < nx; ++k) { x[k] = xn[k]; xs_out[((size_t)(t + 1) * nx + k) * B + b] = xn[k]; }
+  }
+  sum += 0.0 - costs_old[(size_t)T * B + b];
+  *sum_out = sum; *merit_out = merit; *plain_out = plain;
+}
+
+// forward_pass with sequential step halving for one problem (the CPU-emulated statement of the line search; the
+// device runs the same trials concurrently, see linesearch_block in outer_warp.cuh)
+template <int NJ> DDPB_HD void forward_problem(const ModelDev& m, const BatchDev& bd, int b, double* costs_old) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
   const int B = bd.B, T = bd.T;
   if (bd.scal[(size_t)S_STATUS * B + b] != 0.0) {
     // frozen problem: keep its trajectory through the pointer swap
@@ -142,35 +181,8 @@ template <int NJ> DDPB_HD void forward_problem(const ModelDev& m, const BatchDev
   while (!success) {
     if (step < 1e-10) break;
     ++rollouts;
-    double x[nx], xn[nx], u[nu];
-#pragma unroll
-    for (int k = 0; k < nx; ++k) x[k] = bd.xs_new[(size_t)k * B + b];
-    double sum = 0.0;
-    merit = 0.0; plain = 0.0;
-    for (int t = 0; t < T; ++t) {
-      double dx[nd];
-#pragma unroll
-      for (int k = 0; k < nd; ++k) dx[k] = x[k] - bd.xs[((size_t)t * nx + k) * B + b];
-#pragma unroll
-      for (int i = 0; i < nu; ++i) {
-        double a = 0.0;
-#pragma unroll
-        for (int k = 0; k < nd; ++k) a += bd.fb_K[((size_t)t * nu * nd + k * nu + i) * B + b] * dx[k];
-        u[i] = bd.us[((size_t)t * nu + i) * B + b] + step * bd.fb_k[((size_t)t * nu + i) * B + b] + a;
-        bd.us_new[((size_t)t * nu + i) * B + b] = u[i];
-      }
-      DynOps<NJ>::eval(m, bd.dt, x, u, xn);
-      const double cn = merit_term<NJ>(m, bd, b, t, x, u, xn, mu);
-      sum += cn - costs_old[(size_t)t * B + b];
-      merit += cn;
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < nu; ++k) s += u[k] * u[k];
-      plain += 0.5 * bd.c * s;
-#pragma unroll
-      for (int k = 0; k < nx; ++k) { x[k] = xn[k]; bd.xs_new[((size_t)(t + 1) * nx + k) * B + b] = xn[k]; }
-    }
-    sum += 0.0 - costs_old[(size_t)T * B + b];
+    double sum;
+    rollout_candidate<NJ>(m, bd, b, step, mu, costs_old, bd.xs_new, bd.us_new, &sum, &merit, &plain);
     if (sum <= 0.0) success = true;
     else step *= 0.5;
   }

@@ -46,10 +46,15 @@ template <int NJ> __global__ void linearize_kernel(const __grid_constant__ Model
 }
 #endif
 
-template <int NJ> __global__ void forward_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, double* costs_old) {
+// line search: cost_seq_aug of the current trajectory (thread per problem), then LS_NC concurrent trials per problem
+template <int NJ> __global__ void cost_old_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, double* costs_old) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= bd.B) return;
-  forward_problem<NJ>(m, bd, b, costs_old);
+  if (b >= bd.B || bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
+  cost_seq_problem<NJ>(m, bd, b, costs_old, bd.scal[(size_t)S_MU * bd.B + b]);
+}
+template <int NJ> __global__ void __launch_bounds__(32 * LS_NC) forward_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
+                                                                               const double* costs_old, double* xs_c, double* us_c) {
+  linesearch_block<NJ>(m, bd, costs_old, xs_c, us_c);
 }
 template <int NJ> __global__ void rollout_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,9 +137,11 @@ template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t s
   (void)bd; (void)threads; (void)smem; (void)s;
 #endif
 }
-template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, cudaStream_t s) {
-  forward_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs_old);
+template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, cudaStream_t s) {
+  cost_old_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs_old);
+  forward_kernel<KNJ><<<(bd.B + 31) / 32, 32 * LS_NC, 0, s>>>(m, bd, costs_old, xs_c, us_c);
 }
+template <> int Launch<KNJ>::linesearch_slots() { return LS_NC; }
 template <> void Launch<KNJ>::rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s) {
   rollout_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(m, bd);
 }

@@ -188,5 +188,76 @@ template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev&
   }
 }
 
+// ---- line search with concurrent trials ---------------------------------------------------------------------
+// The reference tries step = 1, 1/2, 1/4, ... one rollout after the other and takes the first step whose merit does not
+// increase (ddp_fwd.ipp:29-60).  The trials are independent, so a block evaluates LS_NC of them at once: block =
+// LS_NC warps, warp w = trial slot w of 32 consecutive problems (lane = problem => coalesced SoA accesses).  Every trial
+// rolls out into its own scratch trajectory; the smallest accepted trial index wins exactly as in the sequential scan
+// (34 trials at most, last one kept on give-up, ddp_fwd.ipp:35-37), and the block copies the winner into the
+// new-trajectory storage.  The `rollouts` scalar keeps counting what the sequential algorithm would have run.
+constexpr int LS_NC = 8;
+constexpr int LS_MAX_TRIALS = 34;  // 2^-33 >= 1e-10 > 2^-34
+
+template <int NJ>
+__device__ __forceinline__ void linesearch_block(const ModelDev& m, const BatchDev& bd, const double* costs_old, double* xs_c, double* us_c) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
+  const int B = bd.B, T = bd.T;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + lane;
+  const bool valid = b < B;
+  const size_t xs_slot = (size_t)(T + 1) * nx * B, us_slot = (size_t)T * nu * B;
+  __shared__ double s_sum[LS_NC][32], s_merit[LS_NC][32], s_plain[LS_NC][32];
+  __shared__ int s_win[32];
+  const bool frozen = valid && bd.scal[(size_t)S_STATUS * B + b] != 0.0;
+  const double mu = valid ? bd.scal[(size_t)S_MU * B + b] : 0.0;
+  if (w == 0) s_win[lane] = (valid && !frozen) ? -1 : -2;  // -1 unresolved, -2 nothing to do
+  __syncthreads();
+  int win = -1;
+  for (int r = 0; r * LS_NC < LS_MAX_TRIALS; ++r) {
+    const int c = r * LS_NC + w;
+    const bool run = valid && !frozen && s_win[lane] == -1 && c < LS_MAX_TRIALS;
+    double sum = 1.0, merit = 0.0, plain = 0.0;
+    if (run) rollout_candidate<NJ>(m, bd, b, ldexp(1.0, -c), mu, costs_old, xs_c + w * xs_slot, us_c + w * us_slot, &sum, &merit, &plain);
+    s_sum[w][lane] = run ? sum : 1.0;
+    s_merit[w][lane] = merit; s_plain[w][lane] = plain;
+    __syncthreads();
+    if (w == 0 && valid && !frozen && s_win[lane] == -1) {
+      int found = -1;
+      for (int k = 0; k < LS_NC; ++k)
+        if (found < 0 && r * LS_NC + k < LS_MAX_TRIALS && s_sum[k][lane] <= 0.0) found = k;
+      const bool last_round = (r + 1) * LS_NC >= LS_MAX_TRIALS;
+      if (found < 0 && last_round) found = (LS_MAX_TRIALS - 1) - r * LS_NC;  // give up: keep the last trial
+      if (found >= 0) {
+        const int cstar = r * LS_NC + found;
+        const bool accepted = s_sum[found][lane] <= 0.0;
+        bd.scal[(size_t)S_STEP * B + b] = accepted ? ldexp(1.0, -cstar) : ldexp(1.0, -LS_MAX_TRIALS);
+        bd.scal[(size_t)S_ROLLOUTS * B + b] += (double)(accepted ? cstar + 1 : LS_MAX_TRIALS);
+        bd.scal[(size_t)S_MERIT * B + b] = s_merit[found][lane];
+        bd.scal[(size_t)S_COST * B + b] = s_plain[found][lane];
+        s_win[lane] = 1000 + found;  // resolved in this round: slot `found`
+      }
+    }
+    __syncthreads();
+    // problems resolved in this round: copy the winning scratch trajectory now (a later round would overwrite the slot)
+    if (valid && s_win[lane] >= 1000) {
+      const int slot = s_win[lane] - 1000;
+      const double* xw = xs_c + slot * xs_slot;
+      const double* uw = us_c + slot * us_slot;
+      for (int e = nx + w; e < (T + 1) * nx; e += LS_NC) bd.xs_new[(size_t)e * B + b] = xw[(size_t)e * B + b];
+      for (int e = w; e < T * nu; e += LS_NC) bd.us_new[(size_t)e * B + b] = uw[(size_t)e * B + b];
+    }
+    __syncthreads();
+    if (w == 0 && valid && s_win[lane] >= 1000) s_win[lane] = 0;  // done
+    win = 0;
+    for (int k = 0; k < 32; ++k) win |= (s_win[k] == -1);
+    __syncthreads();
+    if (!win) break;
+  }
+  if (frozen) {  // keep a frozen problem's trajectory through the pointer swap
+    for (int e = w; e < (T + 1) * nx; e += LS_NC) bd.xs_new[(size_t)e * B + b] = bd.xs[(size_t)e * B + b];
+    for (int e = w; e < T * nu; e += LS_NC) bd.us_new[(size_t)e * B + b] = bd.us[(size_t)e * B + b];
+  }
+}
+
 }  // namespace ddpb
 #endif

@@ -131,7 +131,8 @@ def workload(name, B=None, T=None):
         m = models.arm_6r()
         w = Workload("c4_arm6r_spatial_1024x100", m, 1024, 100, eq_kind=EQ_SPATIAL, frame=m.n_frames - 1)
     elif name == "c5":  # 7R arm, value-based finite-difference Hessians, 8192 x 200 over 8 GPUs
-        w = Workload("c5_arm7r_fd_8192x200", models.arm_7r(), 8192, 200, hess_mode=HESS_FD_VALUES)
+        # value-based FD Hessians (eps = 2^-13) are noisier: goals within 0.25 rad keep the reference algorithm convergent
+        w = Workload("c5_arm7r_fd_8192x200", models.arm_7r(), 8192, 200, hess_mode=HESS_FD_VALUES, target_offset=0.25)
     else:
         raise ValueError(name)
     if B is not None:
