@@ -52,6 +52,7 @@ struct BatchDev {
   int hess_mode, eq_kind, frame_id, jac_mode;
   int ne_max, ne_total;
   int max_restarts, pad_;             // 0 = unbounded restarts (reference behaviour)
+  int b0, nb;                         // problems [b0, b0 + nb) covered by a launch (sub-batches run on their own streams)
   double dt, c;
   double *xs, *us, *xs_new, *us_new;  // [(T+1)][nx][B], [T][nu][B]
   double* targets;                    // [ne_total][B]

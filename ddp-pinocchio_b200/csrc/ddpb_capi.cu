@@ -306,6 +306,7 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   BatchDev& bd = h->bd;
   std::memset(&bd, 0, sizeof(bd));
   bd.B = B; bd.T = T; bd.n = n; bd.nx = 2 * n; bd.nu = n;
+  bd.b0 = 0; bd.nb = B;
   bd.hess_mode = p->hess_mode; bd.eq_kind = p->eq_kind; bd.frame_id = p->frame_id; bd.jac_mode = p->frame_jac_mode;
   bd.dt = p->dt; bd.c = p->c;
   bd.max_restarts = p->max_backward_restarts < 0 ? 0 : p->max_backward_restarts;

@@ -12,6 +12,9 @@ namespace ddpb {
 
 constexpr int KNJ = DDPB_NJ;
 
+// Every kernel covers the problems [bd.b0, bd.b0 + bd.nb) of the batch: the solver splits a batch into sub-batches
+// that run the iteration sequence on their own streams, so the latency-bound sweeps of one sub-batch overlap the
+// throughput-bound linearization of another and a straggling problem delays only its own sub-batch.
 #if DDPB_NJ > 0
 // grid: (knots t0..t1-1) x (groups of `kpb` consecutive problems); all knots of a launch have the same ne
 #ifndef DDPB_LIN_LB_THREADS
@@ -21,9 +24,9 @@ constexpr int KNJ = DDPB_NJ;
 template <int NJ> __global__ void __launch_bounds__(DDPB_LIN_LB_THREADS, DDPB_LIN_LB_BLOCKS) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
                                                                           int t0, int kpb, int ne_sm) {
   extern __shared__ __align__(16) double sm[];
-  const int groups = (bd.B + kpb - 1) / kpb;
-  const int t = t0 + blockIdx.x / groups, b0 = (blockIdx.x % groups) * kpb;
-  const int nk = min(kpb, bd.B - b0);
+  const int groups = (bd.nb + kpb - 1) / kpb;
+  const int t = t0 + blockIdx.x / groups, b0 = bd.b0 + (blockIdx.x % groups) * kpb;
+  const int nk = min(kpb, bd.b0 + bd.nb - b0);
   bool any = false;
   for (int k = 0; k < nk; ++k) any = any || bd.scal[(size_t)S_STATUS * bd.B + b0 + k] == 0.0;
   if (!any) return;  // every problem of the group is frozen (converged / diverged)
@@ -32,15 +35,15 @@ template <int NJ> __global__ void __launch_bounds__(DDPB_LIN_LB_THREADS, DDPB_LI
 // one warp (= one CTA of 32 threads) per problem; enough CTAs per SM that a whole batch is resident in one wave
 template <int NJ> __global__ void __launch_bounds__(32, NJ <= 2 ? 28 : (NJ <= 4 ? 16 : 8)) backward_kernel(const __grid_constant__ BatchDev bd) {
   extern __shared__ __align__(16) double sm[];
-  const int b = blockIdx.x;
+  const int b = bd.b0 + blockIdx.x;
   if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
   backward_problem<NJ, 32>(bd, b, sm, DevExec{});
 }
 #else
 template <int NJ> __global__ void linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, int t0, int t1) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)bd.B * (t1 - t0)) return;
-  const int b = (int)(i % bd.B), t = t0 + (int)(i / bd.B);
+  if (i >= (size_t)bd.nb * (t1 - t0)) return;
+  const int b = bd.b0 + (int)(i % bd.nb), t = t0 + (int)(i / bd.nb);
   if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
   linearize_pendulum(m, bd, b, t);
 }
@@ -48,8 +51,8 @@ template <int NJ> __global__ void linearize_kernel(const __grid_constant__ Model
 
 // line search: cost_seq_aug of the current trajectory (thread per problem), then LS_NC concurrent trials per problem
 template <int NJ> __global__ void cost_old_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, double* costs_old) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= bd.B || bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = bd.b0 + i;
+  if (i >= bd.nb || bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
   cost_seq_problem<NJ>(m, bd, b, costs_old, bd.scal[(size_t)S_MU * bd.B + b]);
 }
 template <int NJ> __global__ void __launch_bounds__(32 * LS_NC) forward_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
@@ -57,35 +60,35 @@ template <int NJ> __global__ void __launch_bounds__(32 * LS_NC) forward_kernel(c
   linesearch_block<NJ>(m, bd, costs_old, xs_c, us_c);
 }
 template <int NJ> __global__ void rollout_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= bd.B) return;
-  rollout_problem<NJ>(m, bd, b);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bd.nb) return;
+  rollout_problem<NJ>(m, bd, bd.b0 + i);
 }
 template <int NJ> __global__ void cost_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, double* costs) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= bd.B) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = bd.b0 + i;
+  if (i >= bd.nb) return;
   const double plain = cost_seq_problem<NJ>(m, bd, b, costs, bd.scal[(size_t)S_MU * bd.B + b]);
   bd.scal[(size_t)S_COST * bd.B + b] = plain;
 }
 // outer-loop sweeps (outer_warp.cuh): per-(knot, problem) kernels and one-warp-per-problem adjoint recursion
 template <int NJ> __global__ void origin_update_kernel(const __grid_constant__ BatchDev bd) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)bd.B * bd.T) return;
-  origin_update_knot<NJ>(bd, (int)(i % bd.B), (int)(i / bd.B));
+  if (i >= (size_t)bd.nb * bd.T) return;
+  origin_update_knot<NJ>(bd, bd.b0 + (int)(i % bd.nb), (int)(i / bd.nb));
 }
 template <int NJ> __global__ void mult_update_kernel(const __grid_constant__ BatchDev bd) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)bd.B * bd.T) return;
-  mult_update_knot<NJ>(bd, (int)(i % bd.B), (int)(i / bd.B));
+  if (i >= (size_t)bd.nb * bd.T) return;
+  mult_update_knot<NJ>(bd, bd.b0 + (int)(i % bd.nb), (int)(i / bd.nb));
 }
 template <int NJ> __global__ void al_decide_kernel(const __grid_constant__ BatchDev bd, double thr, int phase) {
-  const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (b >= bd.B) return;
-  al_decide_warp<NJ>(bd, b, thr, phase);
+  const int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (i >= bd.nb) return;
+  al_decide_warp<NJ>(bd, bd.b0 + i, thr, phase);
 }
 template <int NJ> __global__ void optimality_kernel(const __grid_constant__ BatchDev bd) {
-  const int b = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (b >= bd.B) return;
+  const int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), b = bd.b0 + i;
+  if (i >= bd.nb) return;
   const double oo = optimality_obj_warp<NJ>(bd, b, bd.scal[(size_t)S_MU * bd.B + b]);
   if ((threadIdx.x & 31) != 0) return;
   bd.scal[(size_t)S_OPT_OBJ * bd.B + b] = oo;
@@ -122,42 +125,42 @@ template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
 template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, int threads, int kpb, int t0, int t1, int ne_sm, cudaStream_t s) {
 #if DDPB_NJ > 0
   const size_t smem = lin_smem_bytes(bd.hess_mode, ne_sm, bd.eq_kind) * kpb;
-  const int groups = (bd.B + kpb - 1) / kpb;
+  const int groups = (bd.nb + kpb - 1) / kpb;
   linearize_kernel<KNJ><<<(unsigned)((size_t)groups * (t1 - t0)), threads, smem, s>>>(m, bd, t0, kpb, ne_sm);
 #else
   (void)threads; (void)kpb; (void)ne_sm;
-  const size_t n = (size_t)bd.B * (t1 - t0);
+  const size_t n = (size_t)bd.nb * (t1 - t0);
   linearize_kernel<KNJ><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(m, bd, t0, t1);
 #endif
 }
 template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
 #if DDPB_NJ > 0
-  backward_kernel<KNJ><<<bd.B, threads, smem, s>>>(bd);
+  backward_kernel<KNJ><<<bd.nb, threads, smem, s>>>(bd);
 #else
   (void)bd; (void)threads; (void)smem; (void)s;
 #endif
 }
 template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, cudaStream_t s) {
-  cost_old_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs_old);
-  forward_kernel<KNJ><<<(bd.B + 31) / 32, 32 * LS_NC, 0, s>>>(m, bd, costs_old, xs_c, us_c);
+  cost_old_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs_old);
+  forward_kernel<KNJ><<<(bd.nb + 31) / 32, 32 * LS_NC, 0, s>>>(m, bd, costs_old, xs_c, us_c);
 }
 template <> int Launch<KNJ>::linesearch_slots() { return LS_NC; }
 template <> void Launch<KNJ>::rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s) {
-  rollout_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(m, bd);
+  rollout_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, 0, s>>>(m, bd);
 }
 template <> void Launch<KNJ>::cost(const ModelDev& m, const BatchDev& bd, double* costs, cudaStream_t s) {
-  cost_kernel<KNJ><<<(bd.B + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs);
+  cost_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs);
 }
 template <> void Launch<KNJ>::al_update(const BatchDev& bd, double thr, cudaStream_t s) {
-  const size_t nkb = (size_t)bd.B * bd.T;
-  const unsigned wblocks = (unsigned)(((size_t)bd.B * 32 + 127) / 128);
+  const size_t nkb = (size_t)bd.nb * bd.T;
+  const unsigned wblocks = (unsigned)(((size_t)bd.nb * 32 + 127) / 128);
   origin_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 0);
   mult_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 1);
 }
 template <> void Launch<KNJ>::optimality(const BatchDev& bd, cudaStream_t s) {
-  optimality_kernel<KNJ><<<(unsigned)(((size_t)bd.B * 32 + 127) / 128), 128, 0, s>>>(bd);
+  optimality_kernel<KNJ><<<(unsigned)(((size_t)bd.nb * 32 + 127) / 128), 128, 0, s>>>(bd);
 }
 
 }  // namespace ddpb

@@ -203,8 +203,8 @@ __device__ __forceinline__ void linesearch_block(const ModelDev& m, const BatchD
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
   const int B = bd.B, T = bd.T;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int b = blockIdx.x * 32 + lane;
-  const bool valid = b < B;
+  const int b = bd.b0 + blockIdx.x * 32 + lane;
+  const bool valid = b < bd.b0 + bd.nb;
   const size_t xs_slot = (size_t)(T + 1) * nx * B, us_slot = (size_t)T * nu * B;
   __shared__ double s_sum[LS_NC][32], s_merit[LS_NC][32], s_plain[LS_NC][32];
   __shared__ int s_win[32];
