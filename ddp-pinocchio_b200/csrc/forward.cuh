@@ -22,7 +22,7 @@ template <int NJ> DDPB_HD void dyn_eval(const ModelDev& m, double dt, const doub
   double qrec[QRec<NJ>::SIZE];
   double qdd[NJ];
   q_task<NJ>(m, x, qrec);
-  v_task<NJ>(m, qrec, x + NJ, u, qdd, nullptr);
+  v_task<NJ, false>(m, qrec, x + NJ, u, qdd, nullptr);
 #pragma unroll
   for (int k = 0; k < NJ; ++k) {
     const double vo = dt * x[NJ + k];

@@ -21,7 +21,7 @@ constexpr int KNJ = DDPB_NJ;
 #define DDPB_LIN_LB_THREADS 256
 #define DDPB_LIN_LB_BLOCKS 1
 #endif
-template <int NJ> __global__ void __launch_bounds__(DDPB_LIN_LB_THREADS, DDPB_LIN_LB_BLOCKS) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
+template <int NJ, int MODE> __global__ void __launch_bounds__(DDPB_LIN_LB_THREADS, DDPB_LIN_LB_BLOCKS) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
                                                                           int t0, int kpb, int ne_sm) {
   extern __shared__ __align__(16) double sm[];
   const int groups = (bd.nb + kpb - 1) / kpb;
@@ -30,7 +30,7 @@ template <int NJ> __global__ void __launch_bounds__(DDPB_LIN_LB_THREADS, DDPB_LI
   bool any = false;
   for (int k = 0; k < nk; ++k) any = any || bd.scal[(size_t)S_STATUS * bd.B + b0 + k] == 0.0;
   if (!any) return;  // every problem of the group is frozen (converged / diverged)
-  linearize_group<NJ>(m, bd, t, b0, nk, ne_sm, sm, DevExec{});
+  linearize_group<NJ, MODE>(m, bd, t, b0, nk, ne_sm, sm, DevExec{});
 }
 // one warp (= one CTA of 32 threads) per problem; enough CTAs per SM that a whole batch is resident in one wave
 template <int NJ> __global__ void __launch_bounds__(32, NJ <= 2 ? 28 : (NJ <= 4 ? 16 : 8)) backward_kernel(const __grid_constant__ BatchDev bd) {
@@ -116,7 +116,9 @@ template <> size_t Launch<KNJ>::bwd_smem_bytes() {
 }
 template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
 #if DDPB_NJ > 0
-  return cudaFuncSetAttribute(linearize_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
+  cudaError_t e = cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_JACOBIANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
 #else
   (void)lin_smem;
   return cudaSuccess;
@@ -126,7 +128,9 @@ template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, i
 #if DDPB_NJ > 0
   const size_t smem = lin_smem_bytes(bd.hess_mode, ne_sm, bd.eq_kind) * kpb;
   const int groups = (bd.nb + kpb - 1) / kpb;
-  linearize_kernel<KNJ><<<(unsigned)((size_t)groups * (t1 - t0)), threads, smem, s>>>(m, bd, t0, kpb, ne_sm);
+  const unsigned grid = (unsigned)((size_t)groups * (t1 - t0));
+  if (bd.hess_mode == HESS_FD_JACOBIANS) linearize_kernel<KNJ, HESS_FD_JACOBIANS><<<grid, threads, smem, s>>>(m, bd, t0, kpb, ne_sm);
+  else linearize_kernel<KNJ, HESS_FD_VALUES><<<grid, threads, smem, s>>>(m, bd, t0, kpb, ne_sm);
 #else
   (void)threads; (void)kpb; (void)ne_sm;
   const size_t n = (size_t)bd.nb * (t1 - t0);

@@ -80,7 +80,9 @@ template <int NJ> struct LinPlan {
 
 // One CTA linearizes `nk` consecutive problems b0 .. b0+nk-1 of knot t (same t => same number of equality
 // rows, adjacent records in HBM).  `ne_sm` is the row count the shared-memory plan was sized for (>= ne(t)).
-template <int NJ, class Ex>
+// MODE = HESS_FD_JACOBIANS / HESS_FD_VALUES at compile time: the two modes are separate kernels, so the register
+// allocation of one does not pay for the code paths of the other.
+template <int NJ, int MODE, class Ex>
 DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b0, int nk, int ne_sm, double* sm_all, const Ex& ex) {
   constexpr int n = NJ, nd = 2 * NJ, nu = NJ, nx = 2 * NJ, N = 3 * NJ;
   using Q = QRec<NJ>;
@@ -88,7 +90,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   const int B = bd.B;
   const int ne = bd.ne[t];
   LinPlan<NJ> pl;
-  pl.init(bd.hess_mode, ne_sm, ne, bd.eq_kind);
+  pl.init(MODE, ne_sm, ne, bd.eq_kind);
   const double eps = pl.eps();
   const double dt = bd.dt;
   const int tid = ex.tid(), nthr = ex.nthr();
@@ -134,7 +136,9 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       qd[k] = base[n + k] + ((n + k == i || n + k == j) ? eps : 0.0);
       tau[k] = base[2 * n + k] + ((2 * n + k == i || 2 * n + k == j) ? eps : 0.0);
     }
-    v_task<NJ>(m, SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, qd, tau, qdd, p < pl.NT ? SM(kk, pl.o_vrec) + (size_t)p * V::SIZE : nullptr);
+    const double* qr = SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE;
+    if (MODE == HESS_FD_JACOBIANS || p == 0) v_task<NJ, true>(m, qr, qd, tau, qdd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+    else v_task<NJ, false>(m, qr, qd, tau, qdd, nullptr);
     // dynamics_t::eval_to (problem.hpp:441-461): v_out = dt v ; q_out = q + v_out ; v_out = v + acc dt
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
@@ -149,17 +153,17 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   // phase 3: tangent columns of inverse dynamics and columns of M^-1
   {
     const int n_tan = pl.NT * 2 * NJ;
-    const int n_minv = (pl.mode == HESS_FD_JACOBIANS ? pl.NQ : 1) * NJ;
+    const int n_minv = (MODE == HESS_FD_JACOBIANS ? pl.NQ : 1) * NJ;
     // tangent tasks of all knots first (j-major inside a knot), then the M^-1 tasks
     for (int idx = tid; idx < nk * (n_tan + n_minv); idx += nthr) {
       double col[NJ];
       if (idx < nk * n_tan) {
-        // order: j slowest so that the threads of a warp share the loop bounds of tangent_col
+        // order: j slowest so that the threads of a warp share the loop bounds of col_task
         const int j = idx / (nk * 2 * pl.NT), rem = idx - j * nk * 2 * pl.NT;
         const int kk = rem / (2 * pl.NT), rem2 = rem - kk * 2 * pl.NT;
         const int wrt = rem2 / pl.NT, p = rem2 - wrt * pl.NT;
         double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
-        tangent_col<NJ>(m, SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, vr, j, wrt, col);
+        col_task<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, vr, j, wrt, col);
         double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
 #pragma unroll
         for (int k = 0; k < NJ; ++k) dst[k] = col[k];
@@ -168,7 +172,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const int kk = r / n_minv, r2 = r - kk * n_minv;
         const int c = r2 % NJ, s = r2 / NJ;
         double* qr = SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE;
-        minv_col<NJ>(m, qr, c, col);
+        minv_col<NJ>(qr, c, col);
 #pragma unroll
         for (int k = 0; k < NJ; ++k) qr[Q::MINV + c * NJ + k] = col[k];
       }
@@ -262,7 +266,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   double* rec0 = slab_rec(bd, t, b0, L.size);
   const double inv_eps = 1.0 / eps, inv_eps2 = 1.0 / (eps * eps);
   const size_t ps = (size_t)ne_sm * N;  // eqxu stride per point
-  const bool fdj = pl.mode == HESS_FD_JACOBIANS;
+  constexpr bool fdj = MODE == HESS_FD_JACOBIANS;
 #define FOR_BLOCK(kk, e, SIZE) _Pragma("unroll 4") for (int idx_ = tid, kk = idx_ / (SIZE), e = idx_ - kk * (SIZE); idx_ < nk * (SIZE); idx_ += nthr, kk = idx_ / (SIZE), e = idx_ - kk * (SIZE))
 #define REC(kk, off) rec0[(size_t)(kk) * L.size + (off)]
   {

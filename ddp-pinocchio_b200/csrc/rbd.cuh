@@ -6,16 +6,17 @@
 // :417-462 frame position / WORLD frame Jacobian) and pendulum_model.hpp:105-130.
 //
 // Work split (one CTA = one knot, see linearize.cuh):
-//   q_task        : everything that depends on q only -- joint rotations, articulated-body
-//                   inertias IA_i, U_i = IA_i S_i, 1/D_i.  Shared by all evaluation points with
-//                   the same q (velocity / control perturbations do not change it).
+//   q_task        : everything that depends on q only -- world-frame joint axes S_i and body
+//                   inertias Y_i, articulated-body inertias IA_i, U_i = IA_i S_i, 1/D_i.  Shared by
+//                   all evaluation points with the same q (velocity / control perturbations do
+//                   not change it).
 //   v_task        : the velocity/torque dependent sweeps of the articulated-body algorithm ->
-//                   joint accelerations (+ per-body v, X a_parent, subtree force F for tangents).
-//   tangent_col   : one column of d tau / d q or d tau / d qdot of inverse dynamics at the ABA
-//                   solution (forward-mode tangent of RNEA restricted to bodies i >= j).
-//   minv_col      : one column of M^-1(q) (unit-torque ABA sweeps on the cached U, 1/D).
-// Spatial vectors are [angular; linear] in body coordinates; X_i = (E_i, r_i) maps parent to
-// child coordinates with E_i = (Rp_i * Rodrigues(axis_i, q_i))^T and r_i = placement translation.
+//                   joint accelerations (+ per-body v, a, momentum h, subtree force F for the columns).
+//   col_task      : one column of d tau / d q or d tau / d qdot of inverse dynamics at the ABA
+//                   solution (closed form per (body, joint) in world coordinates).
+//   minv_col      : one column of M^-1(q) (unit-torque ABA sweeps on the cached S, U, 1/D).
+// Spatial vectors are [angular; linear] Pluecker coordinates in the WORLD frame (linear part taken at
+// the world origin), so quantities of different bodies add without transforms.
 #pragma once
 #include <math.h>
 
@@ -147,341 +148,323 @@ DDPB_HD void joint_E(const ModelDev& m, int i, double q, double* E) {
     for (int cc = 0; cc < 3; ++cc) E[cc * 3 + r] = Rp[r * 3 + 0] * RJ[0 * 3 + cc] + Rp[r * 3 + 1] * RJ[1 * 3 + cc] + Rp[r * 3 + 2] * RJ[2 * 3 + cc];
 }
 
+// ---- world-frame spatial algebra -----------------------------------------------------------------
+// All spatial vectors of the tasks below are Pluecker coordinates in the WORLD frame, [angular; linear at the
+// world origin].  A chain in world coordinates needs no per-joint transforms: parent/child quantities simply add,
+// the articulated-body recursion is IA_parent += IA - U U^T / D, and the derivative of inverse dynamics with respect
+// to q_j / qdot_j has a closed form per (body k, joint j) (see col_task).
+//
+// rigid-body inertia Y = [mass, h (3) = mass * com, I (6) = rotational inertia about the world origin: xx,xy,xz,yy,yz,zz]
+DDPB_HD void y_mul(const double* Y, const double* v, double* o) {  // [I w + h x vl ; m vl - h x w]
+  double a[3], l[3];
+  sym3v(Y + 4, v, a);
+  cross3_add(Y + 1, v + 3, a);
+  cross3(Y + 1, v, l);
+  o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
+  o[3] = Y[0] * v[3] - l[0]; o[4] = Y[0] * v[4] - l[1]; o[5] = Y[0] * v[5] - l[2];
+}
+// packed upper triangle of a symmetric 6x6: (r, c), r <= c  ->  r*6 - r(r-1)/2 + (c - r)
+DDPB_HD constexpr int s6(int r, int c) { return r <= c ? r * 6 - (r * (r - 1)) / 2 + (c - r) : c * 6 - (c * (c - 1)) / 2 + (r - c); }
+DDPB_HD void sym6_mul(const double* A, const double* x, double* o) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double a = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a += A[s6(r, c)] * x[c];
+    o[r] = a;
+  }
+}
+DDPB_HD double dot6(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5]; }
+
 // ---- record layouts (offsets in doubles; sizes padded to an odd count so that consecutive
 // tasks' records start in different shared-memory banks) -------------------------------------
 template <int NJ> struct QRec {
-  static constexpr int E = 0;                 // [NJ][9]
-  static constexpr int IA = E + 9 * NJ;       // [NJ][21]: A(6 sym) | B(9 row-major) | C(6 sym)
-  static constexpr int U = IA + 21 * NJ;      // [NJ][6]
-  static constexpr int DINV = U + 6 * NJ;     // [NJ]
-  static constexpr int MINV = DINV + NJ;      // [NJ][NJ] column-major
+  static constexpr int S = 0;                 // [NJ][6] joint axes (world)
+  static constexpr int Y = S + 6 * NJ;        // [NJ][10] rigid-body inertias (world)
+  static constexpr int U = Y + 10 * NJ;       // [NJ][6]  IA_i S_i
+  static constexpr int DINV = U + 6 * NJ;     // [NJ]     1 / (S_i . U_i)
+  static constexpr int IA = DINV + NJ;        // [NJ][21] articulated inertias (packed symmetric)
+  static constexpr int MINV = IA + 21 * NJ;   // [NJ][NJ] column-major
   static constexpr int RAW = MINV + NJ * NJ;
   static constexpr int SIZE = RAW | 1;
 };
 template <int NJ> struct VRec {
   static constexpr int V = 0;                 // [NJ][6] body velocities
-  static constexpr int XA = V + 6 * NJ;       // [NJ][6] X_i a_parent
-  static constexpr int F = XA + 6 * NJ;       // [NJ][6] subtree forces of RNEA at the ABA solution
-  static constexpr int QD = F + 6 * NJ;       // [NJ]
-  static constexpr int QDD = QD + NJ;         // [NJ]
-  static constexpr int DQ = QDD + NJ;         // [NJ][NJ] d tau/d q, then da/dq (column-major)
-  static constexpr int DV = DQ + NJ * NJ;     // [NJ][NJ] d tau/d qdot, then da/dqdot
+  static constexpr int A = V + 6 * NJ;        // [NJ][6] body accelerations at the ABA solution (gravity folded in)
+  static constexpr int H = A + 6 * NJ;        // [NJ][6] momenta Y_i v_i
+  static constexpr int F = H + 6 * NJ;        // [NJ][6] subtree forces of inverse dynamics at the ABA solution
+  static constexpr int DQ = F + 6 * NJ;       // [NJ][NJ] d tau/d q, then dt * da/dq (column-major)
+  static constexpr int DV = DQ + NJ * NJ;     // [NJ][NJ] d tau/d qdot, then I + dt * da/dqdot
   static constexpr int RAW = DV + NJ * NJ;
   static constexpr int SIZE = RAW | 1;
 };
 
-// ---- q_task ------------------------------------------------------------------------------------
-template <int NJ> DDPB_HD void q_task(const ModelDev& m, const double* q, double* rec) {
-  using R = QRec<NJ>;
+// world rotation / origin of joint frame i from those of its parent:  R <- R Rp_i Rot(axis_i, q_i),  p <- p + R_parent pp_i
+DDPB_HD void joint_advance(const ModelDev& m, int i, double q, double* R, double* p) {
+  double t[3];
+  m3v(R, m.pp[i], t);
+  p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
+  double s, c;
+  sincos_(q, &s, &c);
+  const double v = 1.0 - c;
+  const double* a = m.axis[i];
+  const double RJ[9] = {c + v * a[0] * a[0],        v * a[0] * a[1] - s * a[2], v * a[0] * a[2] + s * a[1],
+                        v * a[1] * a[0] + s * a[2], c + v * a[1] * a[1],        v * a[1] * a[2] - s * a[0],
+                        v * a[2] * a[0] - s * a[1], v * a[2] * a[1] + s * a[0], c + v * a[2] * a[2]};
+  const double* Rp = m.Rp[i];
+  double Rl[9], Rn[9];
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) {
-    double E[9];
-    joint_E(m, i, q[i], E);
+  for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int k = 0; k < 9; ++k) rec[R::E + 9 * i + k] = E[k];
-  }
-  // articulated inertia of the current body: A (ang-ang, sym), B (ang-lin), C (lin-lin, sym)
-  double A[6], B[9], C[6];
+    for (int cc = 0; cc < 3; ++cc) Rl[r * 3 + cc] = Rp[r * 3 + 0] * RJ[0 * 3 + cc] + Rp[r * 3 + 1] * RJ[1 * 3 + cc] + Rp[r * 3 + 2] * RJ[2 * 3 + cc];
 #pragma unroll
-  for (int i = NJ - 1; i >= 0; --i) {
-    const double* hh = m.h[i];
-    if (i == NJ - 1) {
+  for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { A[k] = m.Io[i][k]; C[k] = 0.0; }
+    for (int cc = 0; cc < 3; ++cc) Rn[r * 3 + cc] = R[r * 3 + 0] * Rl[0 * 3 + cc] + R[r * 3 + 1] * Rl[1 * 3 + cc] + R[r * 3 + 2] * Rl[2 * 3 + cc];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) B[k] = 0.0;
-    } else {
+  for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+}
+// joint axis S = [w ; p x w] and rigid-body inertia Y of body i in world coordinates about the world origin.
+// With h_p = R h_i (first moment about the joint origin), g = h_p + (m/2) p:
+//   h_O = h_p + m p ,  I_O = R Io_i R^T + 2 (g . p) Id - (g p^T + p g^T)      (parallel-axis shift, no division by m)
+DDPB_HD void body_world(const ModelDev& m, int i, const double* R, const double* p, double* S, double* Y) {
+  double w[3], mo[3];
+  m3v(R, m.axis[i], w);
+  cross3(p, w, mo);
+  S[0] = w[0]; S[1] = w[1]; S[2] = w[2]; S[3] = mo[0]; S[4] = mo[1]; S[5] = mo[2];
+  const double mass = m.mass[i];
+  double hp[3];
+  m3v(R, m.h[i], hp);
+  const double g[3] = {hp[0] + 0.5 * mass * p[0], hp[1] + 0.5 * mass * p[1], hp[2] + 0.5 * mass * p[2]};
+  const double* Io = m.Io[i];
+  const double If[9] = {Io[0], Io[1], Io[2], Io[1], Io[3], Io[4], Io[2], Io[4], Io[5]};
+  double T[9];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) A[k] += m.Io[i][k];
-    }
-    // B += skew(h), C += mass * I
-    B[1] -= hh[2]; B[2] += hh[1]; B[3] += hh[2]; B[5] -= hh[0]; B[6] -= hh[1]; B[7] += hh[0];
-    C[0] += m.mass[i]; C[3] += m.mass[i]; C[5] += m.mass[i];
-    double* ia = rec + R::IA + 21 * i;
+  for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { ia[k] = A[k]; ia[15 + k] = C[k]; }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) ia[6 + k] = B[k];
-    const double* ax = m.axis[i];
-    double Ua[3], Ul[3];
-    sym3v(A, ax, Ua);
-    m3tv(B, ax, Ul);
-    const double D = ax[0] * Ua[0] + ax[1] * Ua[1] + ax[2] * Ua[2];
-    const double Dinv = 1.0 / D;
-    rec[R::U + 6 * i + 0] = Ua[0]; rec[R::U + 6 * i + 1] = Ua[1]; rec[R::U + 6 * i + 2] = Ua[2];
-    rec[R::U + 6 * i + 3] = Ul[0]; rec[R::U + 6 * i + 4] = Ul[1]; rec[R::U + 6 * i + 5] = Ul[2];
-    rec[R::DINV + i] = Dinv;
-    if (i > 0) {
-      // Ia = IA - U D^-1 U^T
-      const double sa[3] = {Ua[0] * Dinv, Ua[1] * Dinv, Ua[2] * Dinv};
-      const double sl[3] = {Ul[0] * Dinv, Ul[1] * Dinv, Ul[2] * Dinv};
-      A[0] -= sa[0] * Ua[0]; A[1] -= sa[0] * Ua[1]; A[2] -= sa[0] * Ua[2];
-      A[3] -= sa[1] * Ua[1]; A[4] -= sa[1] * Ua[2]; A[5] -= sa[2] * Ua[2];
-      C[0] -= sl[0] * Ul[0]; C[1] -= sl[0] * Ul[1]; C[2] -= sl[0] * Ul[2];
-      C[3] -= sl[1] * Ul[1]; C[4] -= sl[1] * Ul[2]; C[5] -= sl[2] * Ul[2];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) B[r * 3 + c] -= sa[r] * Ul[c];
-      // rotate the three blocks into the parent orientation:  M' = E^T M E
-      const double* E = rec + R::E + 9 * i;
-      double Af[9] = {A[0], A[1], A[2], A[1], A[3], A[4], A[2], A[4], A[5]};
-      double Cf[9] = {C[0], C[1], C[2], C[1], C[3], C[4], C[2], C[4], C[5]};
-      double T[9], Ab[9], Bb[9], Cb[9];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) T[r * 3 + c] = Af[r * 3] * E[c] + Af[r * 3 + 1] * E[3 + c] + Af[r * 3 + 2] * E[6 + c];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) Ab[r * 3 + c] = E[r] * T[c] + E[3 + r] * T[3 + c] + E[6 + r] * T[6 + c];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) T[r * 3 + c] = B[r * 3] * E[c] + B[r * 3 + 1] * E[3 + c] + B[r * 3 + 2] * E[6 + c];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) Bb[r * 3 + c] = E[r] * T[c] + E[3 + r] * T[3 + c] + E[6 + r] * T[6 + c];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) T[r * 3 + c] = Cf[r * 3] * E[c] + Cf[r * 3 + 1] * E[3 + c] + Cf[r * 3 + 2] * E[6 + c];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) Cb[r * 3 + c] = E[r] * T[c] + E[3 + r] * T[3 + c] + E[6 + r] * T[6 + c];
-      // shift to the parent origin (r = placement translation):
-      //   C' = Cb ; B' = Bb + rx Cb ; A' = Ab - Bb rx + rx B'^T
-      const double* rr = m.pp[i];
-      double Bn[9];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        Bn[0 * 3 + c] = Bb[0 * 3 + c] + (-rr[2] * Cb[3 + c] + rr[1] * Cb[6 + c]);
-        Bn[1 * 3 + c] = Bb[1 * 3 + c] + (rr[2] * Cb[c] - rr[0] * Cb[6 + c]);
-        Bn[2 * 3 + c] = Bb[2 * 3 + c] + (-rr[1] * Cb[c] + rr[0] * Cb[3 + c]);
-      }
-      double An[9];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        // (Bb rx)[r][:]
-        const double b0 = Bb[r * 3 + 1] * rr[2] - Bb[r * 3 + 2] * rr[1];
-        const double b1 = -Bb[r * 3 + 0] * rr[2] + Bb[r * 3 + 2] * rr[0];
-        const double b2 = Bb[r * 3 + 0] * rr[1] - Bb[r * 3 + 1] * rr[0];
-        An[r * 3 + 0] = Ab[r * 3 + 0] - b0;
-        An[r * 3 + 1] = Ab[r * 3 + 1] - b1;
-        An[r * 3 + 2] = Ab[r * 3 + 2] - b2;
-      }
-      // + rx B'^T : row r of rx times column c of B'^T (= row c of B')
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        An[0 * 3 + c] += -rr[2] * Bn[c * 3 + 1] + rr[1] * Bn[c * 3 + 2];
-        An[1 * 3 + c] += rr[2] * Bn[c * 3 + 0] - rr[0] * Bn[c * 3 + 2];
-        An[2 * 3 + c] += -rr[1] * Bn[c * 3 + 0] + rr[0] * Bn[c * 3 + 1];
-      }
-      A[0] = An[0]; A[1] = An[1]; A[2] = An[2]; A[3] = An[4]; A[4] = An[5]; A[5] = An[8];
-      C[0] = Cb[0]; C[1] = Cb[1]; C[2] = Cb[2]; C[3] = Cb[4]; C[4] = Cb[5]; C[5] = Cb[8];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) B[k] = Bn[k];
-    }
-  }
+    for (int c = 0; c < 3; ++c) T[r * 3 + c] = R[r * 3 + 0] * If[0 * 3 + c] + R[r * 3 + 1] * If[1 * 3 + c] + R[r * 3 + 2] * If[2 * 3 + c];
+  const double gp2 = 2.0 * (g[0] * p[0] + g[1] * p[1] + g[2] * p[2]);
+  Y[0] = mass;
+  Y[1] = hp[0] + mass * p[0]; Y[2] = hp[1] + mass * p[1]; Y[3] = hp[2] + mass * p[2];
+  Y[4] = (T[0] * R[0] + T[1] * R[1] + T[2] * R[2]) + gp2 - 2.0 * g[0] * p[0];
+  Y[5] = (T[0] * R[3] + T[1] * R[4] + T[2] * R[5]) - (g[0] * p[1] + p[0] * g[1]);
+  Y[6] = (T[0] * R[6] + T[1] * R[7] + T[2] * R[8]) - (g[0] * p[2] + p[0] * g[2]);
+  Y[7] = (T[3] * R[3] + T[4] * R[4] + T[5] * R[5]) + gp2 - 2.0 * g[1] * p[1];
+  Y[8] = (T[3] * R[6] + T[4] * R[7] + T[5] * R[8]) - (g[1] * p[2] + p[1] * g[2]);
+  Y[9] = (T[6] * R[6] + T[7] * R[7] + T[8] * R[8]) + gp2 - 2.0 * g[2] * p[2];
+}
+// IA (packed symmetric 6x6) += rigid-body inertia Y:  [[I, skew(h)], [skew(h)^T, m Id]]
+DDPB_HD void ia_add_body(double* IA, const double* Y) {
+  IA[s6(0, 0)] += Y[4]; IA[s6(0, 1)] += Y[5]; IA[s6(0, 2)] += Y[6]; IA[s6(1, 1)] += Y[7]; IA[s6(1, 2)] += Y[8]; IA[s6(2, 2)] += Y[9];
+  IA[s6(0, 4)] -= Y[3]; IA[s6(0, 5)] += Y[2]; IA[s6(1, 3)] += Y[3]; IA[s6(1, 5)] -= Y[1]; IA[s6(2, 3)] -= Y[2]; IA[s6(2, 4)] += Y[1];
+  IA[s6(3, 3)] += Y[0]; IA[s6(4, 4)] += Y[0]; IA[s6(5, 5)] += Y[0];
 }
 
-// IA_i * c  with IA stored as A | B | C
-DDPB_HD void ia_mul(const double* ia, const double* c, double* o) {
-  double a[3], l[3], t[3];
-  sym3v(ia, c, a);
-  m3v(ia + 6, c + 3, t);
-  a[0] += t[0]; a[1] += t[1]; a[2] += t[2];
-  m3tv(ia + 6, c, l);
-  sym3v(ia + 15, c + 3, t);
-  o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
-  o[3] = l[0] + t[0]; o[4] = l[1] + t[1]; o[5] = l[2] + t[2];
+// ---- q_task ------------------------------------------------------------------------------------
+// everything that depends on q only: world-frame joint axes and body inertias, articulated inertias IA_i, U_i, 1/D_i
+template <int NJ> DDPB_HD void q_task(const ModelDev& m, const double* q, double* rec) {
+  using Q = QRec<NJ>;
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    joint_advance(m, i, q[i], R, p);
+    double S[6], Y[10];
+    body_world(m, i, R, p, S, Y);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rec[Q::S + 6 * i + k] = S[k];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) rec[Q::Y + 10 * i + k] = Y[k];
+  }
+  double IA[21];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) IA[k] = 0.0;
+#pragma unroll
+  for (int i = NJ - 1; i >= 0; --i) {
+    double Y[10], S[6], U[6];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) Y[k] = rec[Q::Y + 10 * i + k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) S[k] = rec[Q::S + 6 * i + k];
+    ia_add_body(IA, Y);
+#pragma unroll
+    for (int k = 0; k < 21; ++k) rec[Q::IA + 21 * i + k] = IA[k];
+    sym6_mul(IA, S, U);
+    const double Dinv = 1.0 / dot6(S, U);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rec[Q::U + 6 * i + k] = U[k];
+    rec[Q::DINV + i] = Dinv;
+    if (i > 0) {
+      // what the parent sees of this subtree: IA - U D^-1 U^T
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const double sr = U[r] * Dinv;
+#pragma unroll
+        for (int c = r; c < 6; ++c) IA[s6(r, c)] -= sr * U[c];
+      }
+    }
+  }
 }
 
 // ---- v_task --------------------------------------------------------------------------------------
-// qdd_out[NJ] always; when vrec != nullptr also the per-body data the tangent columns need.
-template <int NJ> DDPB_HD void v_task(const ModelDev& m, const double* qrec, const double* qd, const double* tau, double* qdd_out, double* vrec) {
+// velocity / torque dependent sweeps of the articulated-body algorithm -> joint accelerations qdd_out[NJ].
+// REC = true: the per-body intermediates live in the point's shared-memory record `vrec`, which afterwards holds
+// what the derivative columns need (V, A, H, F).  REC = false: value only, intermediates in registers.
+template <int NJ, bool REC> DDPB_HD void v_task(const ModelDev& m, const double* qrec, const double* qd, const double* tau, double* qdd_out, double* vrec) {
   using Q = QRec<NJ>;
   using V = VRec<NJ>;
-  double v[NJ][6], pA[NJ][6], u[NJ];
+  double cl[REC ? 1 : NJ][6], pl[REC ? 1 : NJ][6];  // bias accelerations / bias forces when there is no record
+  double u[NJ];
+  {
+    double v[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) {
-    const double* ax = m.axis[i];
-    if (i == 0) {
-      v[0][0] = ax[0] * qd[0]; v[0][1] = ax[1] * qd[0]; v[0][2] = ax[2] * qd[0];
-      v[0][3] = 0.0; v[0][4] = 0.0; v[0][5] = 0.0;
-    } else {
-      xf_motion(qrec + Q::E + 9 * i, m.pp[i], v[i - 1], v[i]);
-      v[i][0] += ax[0] * qd[i]; v[i][1] += ax[1] * qd[i]; v[i][2] += ax[2] * qd[i];
+    for (int i = 0; i < NJ; ++i) {
+      const double* S = qrec + Q::S + 6 * i;
+      double sq[6], c[6], h[6], pa[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { sq[k] = S[k] * qd[i]; v[k] += sq[k]; }
+      crm(v, sq, c);                      // c_i = v_i x (S_i qd_i)
+      y_mul(qrec + Q::Y + 10 * i, v, h);  // h_i = Y_i v_i
+      crf(v, h, pa);                      // p_i = v_i x* h_i
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (REC) { vrec[V::V + 6 * i + k] = v[k]; vrec[V::H + 6 * i + k] = h[k]; vrec[V::A + 6 * i + k] = c[k]; vrec[V::F + 6 * i + k] = pa[k]; }
+        else { cl[REC ? 0 : i][k] = c[k]; pl[REC ? 0 : i][k] = pa[k]; }
+      }
     }
-    double hv[6];
-    inertia_mul(m, i, v[i], hv);
-    crf(v[i], hv, pA[i]);
   }
 #pragma unroll
   for (int i = NJ - 1; i >= 0; --i) {
-    const double* ax = m.axis[i];
-    u[i] = tau[i] - (ax[0] * pA[i][0] + ax[1] * pA[i][1] + ax[2] * pA[i][2]);
-    if (i > 0) {
-      double c[6], Iac[6], pa[6];
-      crm_axis(v[i], ax, qd[i], c);
-      const double* U = qrec + Q::U + 6 * i;
-      const double Uc = U[0] * c[0] + U[1] * c[1] + U[2] * c[2] + U[3] * c[3] + U[4] * c[4] + U[5] * c[5];
-      const double t = qrec[Q::DINV + i] * (u[i] - Uc);
-      ia_mul(qrec + Q::IA + 21 * i, c, Iac);
+    const double* S = qrec + Q::S + 6 * i;
+    double pa[6], c[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) pa[k] = pA[i][k] + Iac[k] + U[k] * t;
-      xf_force_T_add(qrec + Q::E + 9 * i, m.pp[i], pa, pA[i - 1]);
+    for (int k = 0; k < 6; ++k) { pa[k] = REC ? vrec[V::F + 6 * i + k] : pl[REC ? 0 : i][k]; c[k] = REC ? vrec[V::A + 6 * i + k] : cl[REC ? 0 : i][k]; }
+    u[i] = tau[i] - dot6(S, pa);
+    if (i > 0) {
+      const double* U = qrec + Q::U + 6 * i;
+      double Iac[6];
+      const double t = qrec[Q::DINV + i] * (u[i] - dot6(U, c));
+      sym6_mul(qrec + Q::IA + 21 * i, c, Iac);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double add = pa[k] + Iac[k] + U[k] * t;
+        if (REC) vrec[V::F + 6 * (i - 1) + k] += add; else pl[REC ? 0 : i - 1][k] += add;
+      }
     }
   }
   double a[6] = {0.0, 0.0, 0.0, -m.grav[0], -m.grav[1], -m.grav[2]};
-  double F[NJ][6];
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    const double* ax = m.axis[i];
-    double Xa[6], c[6];
-    xf_motion(qrec + Q::E + 9 * i, m.pp[i], a, Xa);
-    crm_axis(v[i], ax, qd[i], c);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) a[k] = Xa[k] + c[k];
+    const double* S = qrec + Q::S + 6 * i;
     const double* U = qrec + Q::U + 6 * i;
-    const double Ua = U[0] * a[0] + U[1] * a[1] + U[2] * a[2] + U[3] * a[3] + U[4] * a[4] + U[5] * a[5];
-    const double qdd = qrec[Q::DINV + i] * (u[i] - Ua);
-    a[0] += ax[0] * qdd; a[1] += ax[1] * qdd; a[2] += ax[2] * qdd;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] += REC ? vrec[V::A + 6 * i + k] : cl[REC ? 0 : i][k];
+    const double qdd = qrec[Q::DINV + i] * (u[i] - dot6(U, a));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] += S[k] * qdd;
     qdd_out[i] = qdd;
-    if (vrec) {
+    if (REC) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { vrec[V::V + 6 * i + k] = v[i][k]; vrec[V::XA + 6 * i + k] = Xa[k]; }
-      vrec[V::QD + i] = qd[i];
-      vrec[V::QDD + i] = qdd;
-      double Ia[6], hv[6], vf[6];
-      inertia_mul(m, i, a, Ia);
-      inertia_mul(m, i, v[i], hv);
-      crf(v[i], hv, vf);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) F[i][k] = Ia[k] + vf[k];
+      for (int k = 0; k < 6; ++k) vrec[V::A + 6 * i + k] = a[k];
     }
   }
-  if (vrec) {
+  if (REC) {
+    // subtree forces of inverse dynamics at this solution: F_i = sum_{k >= i} (Y_k a_k + v_k x* h_k)
+    double F[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int i = NJ - 1; i >= 0; --i) {
-      if (i > 0) xf_force_T_add(qrec + Q::E + 9 * i, m.pp[i], F[i], F[i - 1]);
+      double ak[6], vk[6], hk[6], Ya[6], vh[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) vrec[V::F + 6 * i + k] = F[i][k];
+      for (int k = 0; k < 6; ++k) { ak[k] = vrec[V::A + 6 * i + k]; vk[k] = vrec[V::V + 6 * i + k]; hk[k] = vrec[V::H + 6 * i + k]; }
+      y_mul(qrec + Q::Y + 10 * i, ak, Ya);
+      crf(vk, hk, vh);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { F[k] += Ya[k] + vh[k]; vrec[V::F + 6 * i + k] = F[k]; }
     }
   }
 }
 
-// ---- tangent_col -----------------------------------------------------------------------------------
-// column j of d tau/d q (wrt_v = 0) or d tau/d qdot (wrt_v = 1) of RNEA(q, qdot, qddot = ABA result)
-template <int NJ> DDPB_HD void tangent_col(const ModelDev& m, const double* qrec, const double* vrec, int j, int wrt_v, double* out /*[NJ]*/) {
+// ---- col_task -----------------------------------------------------------------------------------
+// column j of d tau/d q (wrt_v = 0) or d tau/d qdot (wrt_v = 1) of inverse dynamics at (q, qdot, qddot = ABA result).
+// World-frame closed form (bodies k >= j move rigidly with joint j; S_j x is the spatial motion cross product):
+//   d = v_j x S_j ,   g_k = Y_k (alpha + beta x (v_k - v_j)) + gamma x* h_k + v_k x* (Y_k gamma)
+//     wrt q_j    : alpha = a_j x S_j, beta = gamma = d ;   d f_k = S_j x* f_k + g_k
+//     wrt qdot_j : alpha = d, beta = gamma = S_j       ;   d f_k = g_k
+//   out[i] = S_i . sum_{k >= max(i,j)} g_k   ( + S_i . (S_j x* F_j) for i < j, wrt q: for i >= j that term cancels
+//   against the derivative of S_i itself )
+template <int NJ> DDPB_HD void col_task(const double* qrec, const double* vrec, int j, int wrt_v, double* out /*[NJ]*/) {
   using Q = QRec<NJ>;
   using V = VRec<NJ>;
-  double dF[NJ][6];
-  double dv[6] = {0, 0, 0, 0, 0, 0}, da[6] = {0, 0, 0, 0, 0, 0};
+  double Sj[6], vj[6], d[6], al[6], be[6];
 #pragma unroll
-  for (int i = 0; i < NJ; ++i) {
-    if (i < j) {
+  for (int k = 0; k < 6; ++k) { Sj[k] = qrec[Q::S + 6 * j + k]; vj[k] = vrec[V::V + 6 * j + k]; }
+  crm(vj, Sj, d);
+  if (!wrt_v) {
+    double aj[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) dF[i][k] = 0.0;
-      continue;
-    }
-    const double* ax = m.axis[i];
-    const double* vi = vrec + V::V + 6 * i;
-    const double qdi = vrec[V::QD + i];
-    if (i == j) {
-      if (!wrt_v) {
-        // d(X_j m)/dq_j = (X_j m) x S_j  with  X_j v_parent = v_j - S_j qd_j,  X_j a_parent = XA_j
-        double Xv[6] = {vi[0] - ax[0] * qdi, vi[1] - ax[1] * qdi, vi[2] - ax[2] * qdi, vi[3], vi[4], vi[5]};
-        crm_axis(Xv, ax, 1.0, dv);
-        crm_axis(vrec + V::XA + 6 * i, ax, 1.0, da);
-      } else {
-        dv[0] = ax[0]; dv[1] = ax[1]; dv[2] = ax[2]; dv[3] = 0.0; dv[4] = 0.0; dv[5] = 0.0;
-        crm_axis(vi, ax, 1.0, da);
-      }
-    } else {
-      double t[6];
-      xf_motion(qrec + Q::E + 9 * i, m.pp[i], dv, t);
+    for (int k = 0; k < 6; ++k) aj[k] = vrec[V::A + 6 * j + k];
+    crm(aj, Sj, al);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) dv[k] = t[k];
-      xf_motion(qrec + Q::E + 9 * i, m.pp[i], da, t);
+    for (int k = 0; k < 6; ++k) be[k] = d[k];
+  } else {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) da[k] = t[k];
-    }
-    {
-      double t[6];
-      crm_axis(dv, ax, qdi, t);
+    for (int k = 0; k < 6; ++k) { al[k] = d[k]; be[k] = Sj[k]; }
+  }
+  double G[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int k = 0; k < 6; ++k) da[k] += t[k];
-    }
-    double Ida[6], Idv[6], hv[6], t1[6], t2[6];
-    inertia_mul(m, i, da, Ida);
-    inertia_mul(m, i, dv, Idv);
-    inertia_mul(m, i, vi, hv);
-    crf(dv, hv, t1);
-    crf(vi, Idv, t2);
+  for (int k = NJ - 1; k >= 0; --k) {
+    if (k < j) continue;
+    const double* Yk = qrec + Q::Y + 10 * k;
+    double vk[6], hk[6], dv[6], t[6], g1[6], g2[6], Yg[6], g3[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dF[i][k] = Ida[k] + t1[k] + t2[k];
+    for (int e = 0; e < 6; ++e) { vk[e] = vrec[V::V + 6 * k + e]; hk[e] = vrec[V::H + 6 * k + e]; dv[e] = vk[e] - vj[e]; }
+    crm(be, dv, t);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) t[e] += al[e];
+    y_mul(Yk, t, g1);
+    crf(be, hk, g2);
+    y_mul(Yk, be, Yg);
+    crf(vk, Yg, g3);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) G[e] += g1[e] + g2[e] + g3[e];
+    out[k] = dot6(qrec + Q::S + 6 * k, G);
+  }
+  if (!wrt_v) {
+    double Fj[6], x[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) Fj[e] = vrec[V::F + 6 * j + e];
+    crf(Sj, Fj, x);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) G[e] += x[e];
   }
 #pragma unroll
-  for (int i = NJ - 1; i >= 0; --i) {
-    const double* ax = m.axis[i];
-    out[i] = ax[0] * dF[i][0] + ax[1] * dF[i][1] + ax[2] * dF[i][2];
-    if (i > 0 && i >= j) {
-      double tot[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tot[k] = dF[i][k];
-      if (i == j && !wrt_v) {
-        // + S_j x* F_j
-        const double* Fj = vrec + V::F + 6 * i;
-        cross3_add(ax, Fj, tot);
-        cross3_add(ax, Fj + 3, tot + 3);
-      }
-      xf_force_T_add(qrec + Q::E + 9 * i, m.pp[i], tot, dF[i - 1]);
-    } else if (i > 0) {
-      // bodies above j only pass the accumulated force on
-      xf_force_T_add(qrec + Q::E + 9 * i, m.pp[i], dF[i], dF[i - 1]);
-    }
-  }
+  for (int i = 0; i < NJ; ++i)
+    if (i < j) out[i] = dot6(qrec + Q::S + 6 * i, G);
 }
 
 // ---- minv_col ---------------------------------------------------------------------------------------
-template <int NJ> DDPB_HD void minv_col(const ModelDev& m, const double* qrec, int col, double* out /*[NJ]*/) {
+// column `col` of M^-1(q): unit-torque articulated-body sweeps on the cached S, U, 1/D
+template <int NJ> DDPB_HD void minv_col(const double* qrec, int col, double* out /*[NJ]*/) {
   using Q = QRec<NJ>;
   double pA[6] = {0, 0, 0, 0, 0, 0};
   double u[NJ];
 #pragma unroll
   for (int i = NJ - 1; i >= 0; --i) {
-    const double* ax = m.axis[i];
     if (i > col) { u[i] = 0.0; continue; }
-    u[i] = (i == col ? 1.0 : 0.0) - (ax[0] * pA[0] + ax[1] * pA[1] + ax[2] * pA[2]);
+    u[i] = (i == col ? 1.0 : 0.0) - dot6(qrec + Q::S + 6 * i, pA);
     if (i > 0) {
       const double* U = qrec + Q::U + 6 * i;
       const double t = qrec[Q::DINV + i] * u[i];
-      double pa[6], np[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int k = 0; k < 6; ++k) pa[k] = pA[k] + U[k] * t;
-      xf_force_T_add(qrec + Q::E + 9 * i, m.pp[i], pa, np);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) pA[k] = np[k];
+      for (int k = 0; k < 6; ++k) pA[k] += U[k] * t;
     }
   }
   double a[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    const double* ax = m.axis[i];
-    if (i > 0) {
-      double t[6];
-      xf_motion(qrec + Q::E + 9 * i, m.pp[i], a, t);
+    const double* S = qrec + Q::S + 6 * i;
+    const double qdd = qrec[Q::DINV + i] * (u[i] - dot6(qrec + Q::U + 6 * i, a));
 #pragma unroll
-      for (int k = 0; k < 6; ++k) a[k] = t[k];
-    }
-    const double* U = qrec + Q::U + 6 * i;
-    const double Ua = U[0] * a[0] + U[1] * a[1] + U[2] * a[2] + U[3] * a[3] + U[4] * a[4] + U[5] * a[5];
-    const double qdd = qrec[Q::DINV + i] * (u[i] - Ua);
-    a[0] += ax[0] * qdd; a[1] += ax[1] * qdd; a[2] += ax[2] * qdd;
+    for (int k = 0; k < 6; ++k) a[k] += S[k] * qdd;
     out[i] = qdd;
   }
 }

@@ -30,6 +30,8 @@ def main():
             mv = np.zeros(o.ne_total)
             k, K, mu1, reg1, rs = o.backward_pass(d, xs0, mv, g["mult_jac"][b], 0.0, w.mu)
             r = o.solve(xs0, g["us"][b], g["mult_jac"][b], kw["iters"], w.mu)
+            rq = o.solve(xs0, g["us"][b], g["mult_jac"][b], kw["iters"], w.mu, prec=1)   # __float128 oracle (accuracy reference)
+            out[f"xsq_{b}"] = rq["xs"]
             out.update({f"xs0_{b}": xs0, f"k_{b}": k, f"K_{b}": K, f"mu1_{b}": mu1, f"reg1_{b}": reg1, f"xs_{b}": r["xs"], f"us_{b}": r["us"],
                         f"log_{b}": r["log"]})
             for f in ("f_val", "fx", "fu", "eq_val", "eq_x", "eq_u", "fxx", "fux", "eq_xx"):

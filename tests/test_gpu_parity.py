@@ -79,7 +79,9 @@ def test_against_committed_golden_vectors(name):
     bt.solve(int(z["iters"]), float(z["mu"]))
     xs, us = bt.get_trajectory()
     for b in range(2):
-        assert pc.relerr(xs[b], z[f"xs_{b}"]) < 1e-5
+        # end-to-end: as close to the __float128 oracle as the double oracle is (DESIGN.md "Tolerances")
+        e_ref = pc.relerr(z[f"xs_{b}"], z[f"xsq_{b}"])
+        assert pc.relerr(xs[b], z[f"xsq_{b}"]) <= 50 * e_ref + 1e-8, (pc.relerr(xs[b], z[f"xsq_{b}"]), e_ref)
     bt.close()
 
 
