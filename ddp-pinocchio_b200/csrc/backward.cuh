@@ -1,4 +1,4 @@
-// backward.cuh -- Riccati-like backward recursion, ONE WARP per problem, sequential over knots.
+// backward.cuh -- Riccati-like backward recursion, one group of BT threads (1..4 warps) per problem, sequential over knots.
 //
 // Restates ddp_solver_t::backward_pass (/root/reference/include/ddp/ddp_bwd.ipp:9-155):
 //   tmp = p + mu eq ; tmp2 = P + mu eq_x                                   (:46-47)
@@ -7,12 +7,16 @@
 //   k = -(LL^T)^-1 Q_u ; K = -(LL^T)^-1 Q_ux ; origin = x_t                (:134-136)
 //   V_x = Q_x + Q_ux^T k ; V_xx = Q_xx + Q_ux^T K                          (:142-146)
 //
-// The recursion is a latency chain (T dependent knots), so the design minimises the dependent path of one knot
-// instead of occupancy: a single warp owns a problem (phase boundaries are __syncwarp, not CTA barriers), every
-// element loop has a compile-time trip count and is fully unrolled so each lane runs several independent FMA
-// chains, all global loads of a knot are issued back to back at its start (one memory latency per knot), and the
-// Cholesky factorisation is spread over lanes.  Small matrices live in shared memory; the third-order tensors are
-// used once and go HBM -> registers -> V_x-contraction, each lane reading the contiguous k-run of its output element.
+// The recursion is a latency chain (T dependent knots) fed by 8 * rec_size bytes per knot, so the design keeps the
+// dependent path of one knot short and the memory system busy ahead of it:
+//   * the record of knot t-1 is pulled into L2 with one bulk prefetch (cp.async.bulk.prefetch.L2) while knot t is
+//     being processed, so the loads at the start of a knot are L2 hits;
+//   * the third-order tensors are used once: every warp streams its share with fully coalesced 16-byte loads through
+//     a small warp-private staging buffer and contracts the k-run of one output element per lane with V_x;
+//   * every matrix product is a list of inner products over CONTIGUOUS shared-memory runs (V_xx is kept row-major,
+//     everything else column-major as in the record), read with 16-byte loads;
+//   * the Cholesky factorisation runs in one warp with the rows of Q_uu in registers and shuffles instead of barriers
+//     (Eigen::LLT semantics: left-looking, fails on a pivot <= 0); k and K are one right-hand side per lane.
 // Every sum keeps the reference's term order, so results do not depend on the thread count.
 #pragma once
 #include "batch.cuh"
@@ -22,22 +26,133 @@ namespace ddpb {
 template <int NJ> struct BwdSmem {
   static constexpr int nd = 2 * NJ, nu = NJ;
   static constexpr int NTEN = nd * nd + nu * nd + nu * nu;  // Q_xx | Q_ux | Q_uu task list
-  static constexpr int Vxx = 0, Vx = Vxx + nd * nd, Qx = Vx + nd, Qu = Qx + nd, Qxx = Qu + nu, Qux = Qxx + nd * nd,
-                       Quu = Qux + nu * nd, VF = Quu + nu * nu, VU = VF + nd * nd, fx = VU + nd * nu, fu = fx + nd * nd,
-                       L = fu + nd * nu, kk = L + nu * nu, KK = kk + nu, small = KK + nu * nd,  // lx | lu
-                       eqv = small + nd + nu, eqx = eqv + MAXE, equ = eqx + MAXE * nd, pe = equ + MAXE * nu,
+  // head of the slab record, copied verbatim: lx | lu | lxx | lux | luu | f | fx | fu  (batch.cuh rec_layout)
+  static constexpr int h_lx = 0, h_lu = h_lx + nd, h_lxx = h_lu + nu, h_lux = h_lxx + nd * nd, h_luu = h_lux + nu * nd,
+                       h_f = h_luu + nu * nu, h_fx = h_f + nd, h_fu = h_fx + nd * nd, NHEAD = h_fu + nd * nu;
+  static constexpr int even(int x) { return (x + 1) & ~1; }
+  static constexpr int head = 0, VxxR = even(head + NHEAD), Vx = VxxR + nd * nd, VF = even(Vx + nd), VU = VF + nd * nd,
+                       Qx = even(VU + nd * nu), Qu = Qx + nd, Qxx = even(Qu + nu), Qux = Qxx + nd * nd, Quu = Qux + nu * nd,
+                       Wf = even(Quu + nu * nu),  // V_x-contraction of fxx | fux | fuu, task-list order
+                       L = even(Wf + NTEN), dinv = L + nu * nu, kk = even(dinv + nu), KK = even(kk + nu),
+                       eqv = even(KK + nu * nd), eqx = eqv + MAXE, equ = eqx + MAXE * nd, pe = equ + MAXE * nu,
                        pex = pe + MAXE, tmp = pex + MAXE * nd, tmp2 = tmp + MAXE, flags = tmp2 + MAXE * nd,
-                       Wf = flags + 4,  // V_x-contraction of fxx | fux | fuu, task-list order
-                       SIZE = Wf + NTEN;
-  static constexpr int BT = 32;  // threads per problem on the device
+                       zero = flags + 2,  // one double that stays 0.0 (tasks without a tensor term add it)
+                       stage = even(zero + 2),  // device: NW warp-private staging buffers of 32 * nd doubles
+                       SIZE = stage;
+  static constexpr int size_for(int threads) { return SIZE + (threads >= 32 ? (threads / 32) * 32 * nd : 0); }
+  // head offset of fx must be even for the 16-byte inner products: nd + nu + nd*nd + nu*nd + nu*nu + nd = nu (mod 2)
+  static constexpr bool head_aligned = (h_fx % 2) == 0 && (h_fu % 2) == 0;
 };
 
-// BT = compile-time thread count of the executor (32 on the device, 1 in the CPU emulation)
+// threads per problem on the device
+template <int NJ> struct BwdGeom { static constexpr int BT = NJ <= 3 ? 32 : (NJ <= 5 ? 64 : 128); };
+
+// inner product over N contiguous doubles with four interleaved partial sums (the dependent chain is N/4 FMAs instead
+// of N); 16-byte loads on the device when both runs are 16-byte aligned (ALIGNED) and N is even.  Host and device use
+// the same association, so the CPU emulation of this kernel rounds identically.
+template <int N, bool ALIGNED> DDPB_HD double dot_run(const double* a, const double* b) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#if defined(__CUDA_ARCH__)
+  if (ALIGNED && (N % 2) == 0) {
+    const double2* a2 = reinterpret_cast<const double2*>(a);
+    const double2* b2 = reinterpret_cast<const double2*>(b);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      const double2 x = a2[k], y = b2[k];
+      acc[(2 * k) & 3] += x.x * y.x;
+      acc[(2 * k + 1) & 3] += x.y * y.y;
+    }
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+#endif
+#pragma unroll
+  for (int k = 0; k < N; ++k) acc[k & 3] += a[k] * b[k];
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+// 16-byte asynchronous copy global -> shared (LDGSTS) and its completion fence
+DDPB_HD void cp_async16(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#else
+  (void)smem_dst; (void)gmem_src;
+#endif
+}
+DDPB_HD void cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// one bulk request that pulls `bytes` (multiple of 16) starting at the 16-byte aligned `p` into L2
+DDPB_HD void l2_prefetch_bulk(const void* p, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+  (void)p; (void)bytes;
+#endif
+}
+
+// Cholesky of the lower triangle of A (nu x nu, column-major in shared memory) in place + 1/diag; returns false on a
+// non-positive pivot.  Device: executed by the first warp, lane i owns row i; host: the same arithmetic serially.
+template <int NU> DDPB_HD bool chol_warp(double* A, double* dinv, int lane) {
+#if defined(__CUDA_ARCH__)
+  const unsigned FULL = 0xffffffffu;
+  double a[NU];
+  const int row = lane < NU ? lane : NU - 1;
+#pragma unroll
+  for (int j = 0; j < NU; ++j) a[j] = A[j * NU + row];
+  bool ok = true;
+  double di = 0.0;
+#pragma unroll
+  for (int k = 0; k < NU; ++k) {
+    double x = a[k];
+#pragma unroll
+    for (int j = 0; j < NU; ++j)
+      if (j < k) x -= a[j] * a[j];
+    const double piv = __shfl_sync(FULL, x, k);
+    if (piv <= 0.0) { ok = false; break; }
+    const double linv = rsqrt(piv);  // column scaling by 1/sqrt(pivot): one special-function latency per column
+    double s = a[k];
+#pragma unroll
+    for (int j = 0; j < NU; ++j)
+      if (j < k) s -= a[j] * __shfl_sync(FULL, a[j], k);
+    a[k] = lane == k ? piv * linv : s * linv;
+    if (lane == k) di = linv;
+  }
+  if (ok && lane < NU) {
+#pragma unroll
+    for (int j = 0; j < NU; ++j)
+      if (j <= lane) A[j * NU + lane] = a[j];
+    dinv[lane] = di;
+  }
+  return ok;
+#else
+  (void)lane;
+  for (int k = 0; k < NU; ++k) {
+    double x = A[k * NU + k];
+    for (int j = 0; j < k; ++j) x -= A[j * NU + k] * A[j * NU + k];
+    if (x <= 0.0) return false;
+    const double linv = 1.0 / sqrt(x);
+    A[k * NU + k] = x * linv;
+    dinv[k] = linv;
+    for (int i = k + 1; i < NU; ++i) {
+      double s = A[k * NU + i];
+      for (int j = 0; j < k; ++j) s -= A[j * NU + i] * A[j * NU + k];
+      A[k * NU + i] = s * linv;
+    }
+  }
+  return true;
+#endif
+}
+
+// BT = compile-time thread count of the executor (BwdGeom<NJ>::BT on the device, 1 in the CPU emulation)
 template <int NJ, int BT, class Ex>
 DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& ex) {
   constexpr int nd = 2 * NJ, nu = NJ, nx = 2 * NJ;
   using S = BwdSmem<NJ>;
   constexpr int nQxx = nd * nd, nQux = nu * nd, nQuu = nu * nu, NTEN = S::NTEN;
+  constexpr bool AL = S::head_aligned;  // fx / fu columns of the head copy start on 16-byte boundaries
   const int B = bd.B, T = bd.T;
   const int tid = ex.tid();
   double mu = bd.scal[(size_t)S_MU * B + b];
@@ -45,95 +160,198 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
   int restarts = 0;
   bool success = false;
 #define FOR_ELEMS(e, N) _Pragma("unroll") for (int u_ = 0; u_ < ((N) + BT - 1) / BT; ++u_) if (const int e = tid + u_ * BT; e < (N))
+  const double* fx = sm + S::head + S::h_fx;
+  const double* fu = sm + S::head + S::h_fu;
+  // Per-thread task descriptors (shared-memory offsets of the operands of every inner product this thread owns),
+  // computed once: the knot loop then runs one branch-free code path per phase instead of re-deriving row / column /
+  // block from the task index at every knot.
+  constexpr int NB = nd * nd + nd * nu;    // phase B: VF | VU
+  constexpr int NC = NTEN + nd + nu;       // phase C: Q_xx | Q_ux | Q_uu | Q_x | Q_u
+  constexpr int NF = nd * nd + nd;         // phase F: V_xx | V_x
+  // PRE: descriptors live in registers for the whole kernel (small models, where the register budget of a resident
+  // wave allows it); otherwise they are re-derived at every use.
+  constexpr bool PRE = NJ <= 5 || BT == 1;
+  auto mkB = [&](int e) -> unsigned {  // a | b << 16
+    const int r = e % nd, c = e / nd;  // c runs over the columns of f_x, then of f_u (adjacent in the head)
+    return (unsigned)(S::VxxR + r * nd) | ((unsigned)(S::head + S::h_fx + c * nd) << 16);
+  };
+  auto mkC = [&](int e, unsigned& d0, unsigned& d1, unsigned& d2) {  // a|b , l|w , dst|ldst (bit 15 of ldst: diagonal)
+    int a, bo, l, w = S::zero, dst, ldst = 0x7fff, diag = 0;
+    if (e < nQxx) {
+      const int r = e % nd, c = e / nd;
+      a = S::h_fx + r * nd; bo = S::VF + c * nd; l = S::h_lxx + e; w = S::Wf + e; dst = S::Qxx + e;
+    } else if (e < nQxx + nQux) {
+      const int ee = e - nQxx, r = ee % nu, c = ee / nu;
+      a = S::h_fu + r * nd; bo = S::VF + c * nd; l = S::h_lux + ee; w = S::Wf + e; dst = S::Qux + ee;
+    } else if (e < NTEN) {
+      const int ee = e - nQxx - nQux, r = ee % nu, c = ee / nu;
+      a = S::h_fu + r * nd; bo = S::VU + c * nd; l = S::h_luu + ee; w = S::Wf + e; dst = S::Quu + ee;
+      ldst = S::L + ee; diag = r == c;
+    } else if (e < NTEN + nd) {
+      const int i = e - NTEN;
+      a = S::h_fx + i * nd; bo = S::Vx; l = S::h_lx + i; dst = S::Qx + i;
+    } else {
+      const int i = e - NTEN - nd;
+      a = S::h_fu + i * nd; bo = S::Vx; l = S::h_lu + i; dst = S::Qu + i;
+    }
+    d0 = (unsigned)(S::head + a) | ((unsigned)bo << 16);
+    d1 = (unsigned)(S::head + l) | ((unsigned)w << 16);
+    d2 = (unsigned)dst | ((unsigned)(ldst | (diag << 15)) << 16);
+  };
+  auto mkF = [&](int e, unsigned& d0, unsigned& d1) {  // a|b , q|dst
+    if (e < nd * nd) {
+      const int c = e % nd, r = e / nd;  // row-major destination: consecutive threads -> consecutive c
+      d0 = (unsigned)(S::Qux + r * nu) | ((unsigned)(S::KK + c * nu) << 16);
+      d1 = (unsigned)(S::Qxx + r + c * nd) | ((unsigned)(S::VxxR + e) << 16);
+    } else {
+      const int i = e - nd * nd;
+      d0 = (unsigned)(S::Qux + i * nu) | ((unsigned)S::kk << 16);
+      d1 = (unsigned)(S::Qx + i) | ((unsigned)(S::VxxR + e) << 16);
+    }
+  };
+  constexpr int PB = PRE ? (NB + BT - 1) / BT : 1, PC = PRE ? (NC + BT - 1) / BT : 1, PF = PRE ? (NF + BT - 1) / BT : 1;
+  unsigned dB[PB], dC0[PC], dC1[PC], dC2[PC], dF0[PF], dF1[PF];
+  if (PRE) {
+    FOR_ELEMS(e, NB) dB[PRE ? u_ : 0] = mkB(e);
+    FOR_ELEMS(e, NC) mkC(e, dC0[PRE ? u_ : 0], dC1[PRE ? u_ : 0], dC2[PRE ? u_ : 0]);
+    FOR_ELEMS(e, NF) mkF(e, dF0[PRE ? u_ : 0], dF1[PRE ? u_ : 0]);
+  }
+  if (tid == 0) { sm[S::zero] = 0.0; sm[S::zero + 1] = 0.0; }
   while (!success) {
     // V_xx = lfxx = 0, V_x = lfx = 0  (problem.hpp:958-959)
-    FOR_ELEMS(e, nd * nd + nd) sm[S::Vxx + e] = 0.0;
+    FOR_ELEMS(e, nd * nd + nd) sm[S::VxxR + e] = 0.0;
     ex.sync();
     bool failed = false;
+    // software pipeline: what knot t needs first -- the head of its record (registers) and round 0 of every warp's
+    // tensor share (warp-private staging buffer, cp.async) -- is fetched while knot t+1 is being processed
+    double hv[(S::NHEAD + BT - 1) / BT];
+#if defined(__CUDA_ARCH__)
+    constexpr int NW = BT / 32, EW = (NTEN + NW - 1) / NW, CPE = nd / 2;  // CPE: 16-byte chunks per tensor element
+    const int warp = tid >> 5, lane = tid & 31;
+    double* stg = sm + S::stage + warp * 32 * nd;
+    const int e_beg = warp * EW, e_end = (warp + 1) * EW < NTEN ? (warp + 1) * EW : NTEN;
+#endif
+    auto prefetch = [&](int tp) {
+      const RecLayout Lp = rec_layout(nd, nu, nx, bd.ne[tp]);
+      const double* recp = slab_rec(bd, tp, b, Lp.size);
+      FOR_ELEMS(e, S::NHEAD) hv[u_] = recp[e];
+#if defined(__CUDA_ARCH__)
+      const int ne_round = e_end - e_beg < 32 ? e_end - e_beg : 32;
+      const double2* src = reinterpret_cast<const double2*>(recp + Lp.fxx + (size_t)e_beg * nd);
+#pragma unroll
+      for (int i = 0; i < CPE; ++i) {
+        const int c = lane + 32 * i;
+        if (c < ne_round * CPE) cp_async16(reinterpret_cast<double2*>(stg) + c, src + c);
+      }
+#endif
+    };
+    cp_async_wait_all();  // a restarted pass may still have the aborted knot's prefetch in flight
+    ex.sync_warp();
+    prefetch(T - 1);
     for (int t = T - 1; t >= 0; --t) {
+      DDPB_PHASE_START(bd, pc_);
       const int ne = bd.ne[t], eo = bd.eq_off[t];
       const RecLayout L = rec_layout(nd, nu, nx, ne);
       const double* rec = slab_rec(bd, t, b, L.size);
-      // ---- phase A: every global load of the knot, back to back -------------------------------------------
+      if (tid == 0 && t > 1) {
+        // the record after next -> L2 (one bulk request), so that the prefetch issued at the next knot hits L2
+        const int sz = rec_layout(nd, nu, nx, bd.ne[t - 2]).size;
+        l2_prefetch_bulk(slab_rec(bd, t - 2, b, sz), (unsigned)(sz * sizeof(double)));
+      }
+      // ---- phase A: head of the record -> shared memory; tensors -> V_x contraction ------------------------------
       double xorg = 0.0;
       if (tid < nx) xorg = bd.xs[((size_t)t * nx + tid) * B + b];
       {
-        constexpr int EPT = (NTEN + BT - 1) / BT;
-        constexpr int CH = EPT < 4 ? EPT : 4;  // tensor elements in flight per lane (CH * nd doubles of registers)
+        FOR_ELEMS(e, S::NHEAD) sm[S::head + e] = hv[u_];
+#if defined(__CUDA_ARCH__)
+        // Each warp owns a contiguous range of the Q_xx | Q_ux | Q_uu task list (= a contiguous piece of the adjacent
+        // fxx | fux | fuu blocks) and streams it in rounds of 32 elements: fully coalesced 16-byte loads (consecutive
+        // lanes -> consecutive chunks) into the warp's staging buffer, then every lane contracts the k-run of its own
+        // element with V_x.  Only __syncwarp is needed: the buffer is private to the warp.  Round 0 was fetched
+        // asynchronously during the previous knot; the loads of round r+1 are in flight while round r is contracted.
+        {
+          double2 buf[CPE];
+          auto load_round = [&](int e0) {
+            const int ne_round = e_end - e0 < 32 ? e_end - e0 : 32;
+            const double2* src = reinterpret_cast<const double2*>(rec + L.fxx + (size_t)e0 * nd);
 #pragma unroll
-        for (int u0 = 0; u0 < EPT; u0 += CH) {
-          double ten[CH][nd];
-#pragma unroll
-          for (int u = 0; u < CH; ++u) {
-            const int e = tid + (u0 + u) * BT;
-            if (u0 + u < EPT && e < NTEN) {
-              // element e of Q_xx | Q_ux | Q_uu  <->  k-run of fxx | fux | fuu
-              const double* f3 = e < nQxx ? rec + L.fxx + (size_t)e * nd
-                                          : (e < nQxx + nQux ? rec + L.fux + (size_t)(e - nQxx) * nd : rec + L.fuu + (size_t)(e - nQxx - nQux) * nd);
-#pragma unroll
-              for (int k = 0; k < nd; ++k) ten[u][k] = f3[k];
+            for (int i = 0; i < CPE; ++i) {
+              const int c = lane + 32 * i;
+              if (c < ne_round * CPE) buf[i] = src[c];
             }
-          }
-          if (u0 == 0) {
-            FOR_ELEMS(e, nd * nd) sm[S::fx + e] = rec[L.fx + e];
-            FOR_ELEMS(e, nd * nu) sm[S::fu + e] = rec[L.fu + e];
-            FOR_ELEMS(e, nd + nu) sm[S::small + e] = rec[L.lx + e];  // lx | lu are adjacent
-            FOR_ELEMS(e, nQxx) sm[S::Qxx + e] = rec[L.lxx + e];      // Q_* start from l_*
-            FOR_ELEMS(e, nQux) sm[S::Qux + e] = rec[L.lux + e];
-            FOR_ELEMS(e, nQuu) sm[S::Quu + e] = rec[L.luu + e];
-            if (ne > 0) {
-              for (int e = tid; e < ne; e += BT) {
-                sm[S::eqv + e] = rec[L.eq + e];
-                sm[S::pe + e] = bd.m_val[((size_t)eo + e) * B + b];
+          };
+          if (e_beg + 32 < e_end) load_round(e_beg + 32);
+          DDPB_PHASE_MARK(bd, 13, pc_);
+          cp_async_wait_all();
+          __syncwarp();
+          DDPB_PHASE_MARK(bd, 14, pc_);
+          for (int e0 = e_beg; e0 < e_end; e0 += 32) {
+            const int ne_round = e_end - e0 < 32 ? e_end - e0 : 32;
+            if (lane < ne_round) {
+              const double2* mine = reinterpret_cast<const double2*>(stg + lane * nd);
+              const double2* vx2 = reinterpret_cast<const double2*>(sm + S::Vx);  // broadcast reads
+              double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+              for (int k = 0; k < CPE; ++k) {
+                const double2 v = mine[k], x = vx2[k];
+                a0 += x.x * v.x;
+                a1 += x.y * v.y;
               }
-              for (int e = tid; e < ne * nd; e += BT) {
-                sm[S::eqx + e] = rec[L.eq_x + e];
-                sm[S::pex + e] = bd.m_jac[((size_t)eo * nd + e) * B + b];
-              }
-              for (int e = tid; e < ne * nu; e += BT) sm[S::equ + e] = rec[L.eq_u + e];
+              sm[S::Wf + e0 + lane] = a0 + a1;
             }
-          }
-          double vx[nd], wacc[CH];
+            __syncwarp();
+            if (e0 + 32 < e_end) {
+              const int nn = e_end - (e0 + 32) < 32 ? e_end - (e0 + 32) : 32;
 #pragma unroll
-          for (int k = 0; k < nd; ++k) vx[k] = sm[S::Vx + k];
-#pragma unroll
-          for (int u = 0; u < CH; ++u) {
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < nd; ++k) a += vx[k] * ten[u][k];
-            wacc[u] = a;
-          }
-#pragma unroll
-          for (int u = 0; u < CH; ++u) {
-            const int e = tid + (u0 + u) * BT;
-            if (u0 + u < EPT && e < NTEN) sm[S::Wf + e] = wacc[u];
+              for (int i = 0; i < CPE; ++i) {
+                const int c = lane + 32 * i;
+                if (c < nn * CPE) reinterpret_cast<double2*>(stg)[c] = buf[i];
+              }
+              if (e0 + 64 < e_end) load_round(e0 + 64);
+              __syncwarp();
+            }
           }
         }
+#else
+        for (int e = 0; e < NTEN; ++e) {
+          const double* f3 = rec + L.fxx + (size_t)e * nd;
+          const double* vx = sm + S::Vx;
+          double a0 = 0.0, a1 = 0.0;
+          for (int k = 0; k < nd; k += 2) { a0 += vx[k] * f3[k]; a1 += vx[k + 1] * f3[k + 1]; }
+          sm[S::Wf + e] = a0 + a1;
+        }
+#endif
+        if (ne > 0) {
+          for (int e = tid; e < ne; e += BT) {
+            sm[S::eqv + e] = rec[L.eq + e];
+            sm[S::pe + e] = bd.m_val[((size_t)eo + e) * B + b];
+          }
+          for (int e = tid; e < ne * nd; e += BT) {
+            sm[S::eqx + e] = rec[L.eq_x + e];
+            sm[S::pex + e] = bd.m_jac[((size_t)eo * nd + e) * B + b];
+          }
+          for (int e = tid; e < ne * nu; e += BT) sm[S::equ + e] = rec[L.eq_u + e];
+        }
+        DDPB_PHASE_MARK(bd, 15, pc_);
+        if (t > 0) prefetch(t - 1);  // the staging buffer and hv are free again
       }
       ex.sync();
+      DDPB_PHASE_MARK(bd, 8, pc_);
       // ---- phase B: tmp, tmp2, VF = V_xx f_x, VU = V_xx f_u ----------------------------------------------------
       for (int e = tid; e < ne; e += BT) sm[S::tmp + e] = sm[S::pe + e] + mu * sm[S::eqv + e];
       for (int e = tid; e < ne * nd; e += BT) sm[S::tmp2 + e] = sm[S::pex + e] + mu * sm[S::eqx + e];
       {
-        // results are kept in registers until every chain of the lane is done: a shared-memory store between two
+        // results are kept in registers until every chain of the thread is done: a shared-memory store between two
         // chains would order them (possible aliasing) and serialise the FMA latencies
-        constexpr int NB = nd * nd + nd * nu;
         double acc[(NB + BT - 1) / BT];
         FOR_ELEMS(e, NB) {
-          const bool isF = e < nd * nd;
-          const int ee = isF ? e : e - nd * nd;
-          const int r = ee % nd, c = ee / nd;
-          const double* M = isF ? sm + S::fx : sm + S::fu;
-          double a = 0.0;
-#pragma unroll
-          for (int k = 0; k < nd; ++k) a += sm[S::Vxx + k * nd + r] * M[c * nd + k];
-          acc[u_] = a;
+          const unsigned d = PRE ? dB[PRE ? u_ : 0] : mkB(e);
+          acc[u_] = dot_run<nd, AL>(sm + (d & 0xffffu), sm + (d >> 16));
         }
         FOR_ELEMS(e, NB) sm[S::VF + e] = acc[u_];  // VF | VU are adjacent
       }
       ex.sync();
-      const double* fx = sm + S::fx;
-      const double* fu = sm + S::fu;
+      DDPB_PHASE_MARK(bd, 9, pc_);
       const double* Vx = sm + S::Vx;
       const double* eqv = sm + S::eqv;
       const double* eqx = sm + S::eqx;
@@ -142,126 +360,118 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       const double* tmp = sm + S::tmp;
       const double* tmp2 = sm + S::tmp2;
       // ---- phase C: all Q elements as one task list: Q_xx | Q_ux | Q_uu | Q_x | Q_u ------------------------------
-      double qacc[(NTEN + nd + nu + BT - 1) / BT];
-      FOR_ELEMS(e, NTEN + nd + nu) {
-        if (e < nQxx) {
-          const int r = e % nd, c = e / nd;
-          double q = sm[S::Qxx + e], a = 0.0;
-#pragma unroll
-          for (int k = 0; k < nd; ++k) a += fx[r * nd + k] * sm[S::VF + c * nd + k];
-          q += a;
-          if (ne > 0) {
-            a = 0.0;
-            for (int k = 0; k < ne; ++k) a += eqx[r * ne + k] * tmp2[c * ne + k];
-            q += a;
-            a = 0.0;
-            for (int k = 0; k < ne; ++k) a += pex[r * ne + k] * eqx[c * ne + k];
-            q += a;
-            a = 0.0;
-            const double* t3 = rec + L.eq_xx + r * ne + (size_t)c * ne * nd;
-            for (int k = 0; k < ne; ++k) a += tmp[k] * t3[k];
-            q += a;
-          }
-          q += sm[S::Wf + e];
-          qacc[u_] = q;
-        } else if (e < nQxx + nQux) {
-          const int ee = e - nQxx;
-          const int r = ee % nu, c = ee / nu;
-          double q = sm[S::Qux + ee], a = 0.0;
-#pragma unroll
-          for (int k = 0; k < nd; ++k) a += fu[r * nd + k] * sm[S::VF + c * nd + k];
-          q += a;
-          if (ne > 0) {
-            a = 0.0;
-            for (int k = 0; k < ne; ++k) a += equ[r * ne + k] * tmp2[c * ne + k];
-            q += a;
-            a = 0.0;
-            const double* t3 = rec + L.eq_ux + r * ne + (size_t)c * ne * nu;
-            for (int k = 0; k < ne; ++k) a += tmp[k] * t3[k];
-            q += a;
-          }
-          q += sm[S::Wf + e];
-          qacc[u_] = q;
-        } else if (e < NTEN) {
-          const int ee = e - nQxx - nQux;
-          const int r = ee % nu, c = ee / nu;
-          double q = sm[S::Quu + ee], a = 0.0;
-#pragma unroll
-          for (int k = 0; k < nd; ++k) a += fu[r * nd + k] * sm[S::VU + c * nd + k];
-          q += a;
-          if (ne > 0) {
-            a = 0.0;
-            for (int k = 0; k < ne; ++k) a += equ[r * ne + k] * equ[c * ne + k];
-            q += a * mu;
-            a = 0.0;
-            const double* t3 = rec + L.eq_uu + r * ne + (size_t)c * ne * nu;
-            for (int k = 0; k < ne; ++k) a += tmp[k] * t3[k];
-            q += a;
-          }
-          q += sm[S::Wf + e];
-          qacc[u_] = q;
-        } else if (e < NTEN + nd) {
-          const int i = e - NTEN;
-          double q = sm[S::small + i], a = 0.0;
-#pragma unroll
-          for (int k = 0; k < nd; ++k) a += fx[i * nd + k] * Vx[k];
-          q += a;
-          if (ne > 0) {
-            a = 0.0;
-            for (int k = 0; k < ne; ++k) a += eqx[i * ne + k] * tmp[k];
-            q += a;
-            a = 0.0;
-            for (int k = 0; k < ne; ++k) a += pex[i * ne + k] * eqv[k];
-            q += a;
-          }
-          qacc[u_] = q;
-        } else {
-          const int i = e - NTEN - nd;
-          double q = sm[S::small + nd + i], a = 0.0;
-#pragma unroll
-          for (int k = 0; k < nd; ++k) a += fu[i * nd + k] * Vx[k];
-          q += a;
-          if (ne > 0) {
-            a = 0.0;
-            for (int k = 0; k < ne; ++k) a += equ[i * ne + k] * tmp[k];
-            q += a;
-          }
-          qacc[u_] = q;
-        }
-      }
-      // Q_xx | Q_ux | Q_uu are adjacent in shared memory and in task-list order; Q_x | Q_u sit before them
-      FOR_ELEMS(e, NTEN + nd + nu) sm[e < NTEN ? S::Qxx + e : S::Qx + (e - NTEN)] = qacc[u_];
-      ex.sync();
-      // ---- phase D: Cholesky of the lower triangle of Q_uu + reg I (Eigen::LLT semantics: fail when a pivot <= 0).
-      // Left-looking, column by column; the rows below the pivot are spread over lanes and every sum keeps the
-      // serial order, so the factor equals the one-thread result bit for bit.
+      // Q = l + f^T (V f) [+ equality terms] + tensor term, in the reference's order of additions
       {
-        double* A = sm + S::L;
-        FOR_ELEMS(e, nu * nu) A[e] = sm[S::Quu + e] + ((e / nu == e % nu) ? reg : 0.0);
-        if (tid == 0) sm[S::flags] = 1.0;
-        ex.sync();
-#pragma unroll
-        for (int k = 0; k < nu; ++k) {
-          if (tid == 0) {
-            double x = A[k * nu + k];
-#pragma unroll
-            for (int j = 0; j < nu; ++j)
-              if (j < k) x -= A[j * nu + k] * A[j * nu + k];
-            if (x <= 0.0) sm[S::flags] = 0.0;
-            A[k * nu + k] = sqrt(x);
+        double qacc[(NC + BT - 1) / BT];
+        unsigned qdst[(NC + BT - 1) / BT];
+        FOR_ELEMS(e, NC) {
+          unsigned c0, c1, c2;
+          if (PRE) { c0 = dC0[PRE ? u_ : 0]; c1 = dC1[PRE ? u_ : 0]; c2 = dC2[PRE ? u_ : 0]; } else mkC(e, c0, c1, c2);
+          qdst[u_] = c2;
+          double q = sm[c1 & 0xffffu];
+          q += dot_run<nd, AL>(sm + (c0 & 0xffffu), sm + (c0 >> 16));
+          if (ne > 0) {
+            // knots with equality rows (rare): terms by block
+            double a = 0.0;
+            if (e < nQxx) {
+              const int r = e % nd, c = e / nd;
+              for (int k = 0; k < ne; ++k) a += eqx[r * ne + k] * tmp2[c * ne + k];
+              q += a;
+              a = 0.0;
+              for (int k = 0; k < ne; ++k) a += pex[r * ne + k] * eqx[c * ne + k];
+              q += a;
+              a = 0.0;
+              const double* t3 = rec + L.eq_xx + r * ne + (size_t)c * ne * nd;
+              for (int k = 0; k < ne; ++k) a += tmp[k] * t3[k];
+              q += a;
+            } else if (e < nQxx + nQux) {
+              const int ee = e - nQxx, r = ee % nu, c = ee / nu;
+              for (int k = 0; k < ne; ++k) a += equ[r * ne + k] * tmp2[c * ne + k];
+              q += a;
+              a = 0.0;
+              const double* t3 = rec + L.eq_ux + r * ne + (size_t)c * ne * nu;
+              for (int k = 0; k < ne; ++k) a += tmp[k] * t3[k];
+              q += a;
+            } else if (e < NTEN) {
+              const int ee = e - nQxx - nQux, r = ee % nu, c = ee / nu;
+              for (int k = 0; k < ne; ++k) a += equ[r * ne + k] * equ[c * ne + k];
+              q += a * mu;
+              a = 0.0;
+              const double* t3 = rec + L.eq_uu + r * ne + (size_t)c * ne * nu;
+              for (int k = 0; k < ne; ++k) a += tmp[k] * t3[k];
+              q += a;
+            } else if (e < NTEN + nd) {
+              const int i = e - NTEN;
+              for (int k = 0; k < ne; ++k) a += eqx[i * ne + k] * tmp[k];
+              q += a;
+              a = 0.0;
+              for (int k = 0; k < ne; ++k) a += pex[i * ne + k] * eqv[k];
+              q += a;
+            } else {
+              const int i = e - NTEN - nd;
+              for (int k = 0; k < ne; ++k) a += equ[i * ne + k] * tmp[k];
+              q += a;
+            }
           }
-          ex.sync();
-          if (sm[S::flags] == 0.0) break;
-          for (int i = k + 1 + tid; i < nu; i += BT) {
-            double s = A[k * nu + i];
-#pragma unroll
-            for (int j = 0; j < nu; ++j)
-              if (j < k) s -= A[j * nu + i] * A[j * nu + k];
-            A[k * nu + i] = s / A[k * nu + k];
-          }
-          ex.sync();
+          q += sm[c1 >> 16];
+          qacc[u_] = q;
+        }
+        // the matrix the factorisation works on, Q_uu + reg I, is written by the owners of the Q_uu elements
+        FOR_ELEMS(e, NC) {
+          sm[qdst[u_] & 0xffffu] = qacc[u_];
+          const unsigned ld = qdst[u_] >> 16;
+          if ((ld & 0x7fffu) != 0x7fffu) sm[ld & 0x7fffu] = qacc[u_] + ((ld & 0x8000u) ? reg : 0.0);
         }
       }
+      ex.sync();
+      DDPB_PHASE_MARK(bd, 10, pc_);
+      // ---- phase D (first warp): Cholesky of Q_uu + reg I, then k = -(LL^T)^-1 Q_u, K = -(LL^T)^-1 Q_ux, one
+      // right-hand side per lane ------------------------------------------------------------------------------------
+      if (tid < 32) {
+        const bool ok = chol_warp<nu>(sm + S::L, sm + S::dinv, tid);
+        if (tid == 0) sm[S::flags] = ok ? 1.0 : 0.0;
+        if (ok) {
+          ex.sync_warp();
+          FOR_ELEMS(c, nd + 1) {
+            if (c < 32 || BT == 1) {
+              const double* A = sm + S::L;
+              const double* di = sm + S::dinv;
+              double rhs[nu];
+#pragma unroll
+              for (int i = 0; i < nu; ++i) rhs[i] = -(c == nd ? sm[S::Qu + i] : sm[S::Qux + c * nu + i]);
+#pragma unroll
+              for (int i = 0; i < nu; ++i) {
+                double s = rhs[i];
+#pragma unroll
+                for (int j = 0; j < nu; ++j)
+                  if (j < i) s -= A[j * nu + i] * rhs[j];
+                rhs[i] = s * di[i];
+              }
+#pragma unroll
+              for (int i = nu - 1; i >= 0; --i) {
+                double s = rhs[i];
+#pragma unroll
+                for (int j = 0; j < nu; ++j)
+                  if (j > i) s -= A[i * nu + j] * rhs[j];
+                rhs[i] = s * di[i];
+              }
+#pragma unroll
+              for (int i = 0; i < nu; ++i) {
+                if (c == nd) {
+                  sm[S::kk + i] = rhs[i];
+                  bd.fb_k[((size_t)t * nu + i) * B + b] = rhs[i];
+                } else {
+                  sm[S::KK + c * nu + i] = rhs[i];
+                  bd.fb_K[((size_t)t * nu * nd + c * nu + i) * B + b] = rhs[i];
+                }
+              }
+            }
+          }
+        }
+      }
+      if (tid < nx) bd.fb_origin[((size_t)t * nx + tid) * B + b] = xorg;
+      ex.sync();
+      DDPB_PHASE_MARK(bd, 11, pc_);
       if (sm[S::flags] == 0.0) {
         if (reg < mu) reg = mu;
         mu *= 2.0;
@@ -271,62 +481,25 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         ex.sync();
         break;
       }
-      // ---- phase E: k = -(LL^T)^-1 Q_u, K = -(LL^T)^-1 Q_ux: one right-hand side per lane ----------------------
-      FOR_ELEMS(c, nd + 1) {
-        const double* A = sm + S::L;
-        double rhs[nu];
-#pragma unroll
-        for (int i = 0; i < nu; ++i) rhs[i] = -(c == nd ? sm[S::Qu + i] : sm[S::Qux + c * nu + i]);
-#pragma unroll
-        for (int i = 0; i < nu; ++i) {
-          double s = rhs[i];
-#pragma unroll
-          for (int j = 0; j < nu; ++j)
-            if (j < i) s -= A[j * nu + i] * rhs[j];
-          rhs[i] = s / A[i * nu + i];
-        }
-#pragma unroll
-        for (int i = nu - 1; i >= 0; --i) {
-          double s = rhs[i];
-#pragma unroll
-          for (int j = 0; j < nu; ++j)
-            if (j > i) s -= A[i * nu + j] * rhs[j];
-          rhs[i] = s / A[i * nu + i];
-        }
-#pragma unroll
-        for (int i = 0; i < nu; ++i) {
-          if (c == nd) {
-            sm[S::kk + i] = rhs[i];
-            bd.fb_k[((size_t)t * nu + i) * B + b] = rhs[i];
-          } else {
-            sm[S::KK + c * nu + i] = rhs[i];
-            bd.fb_K[((size_t)t * nu * nd + c * nu + i) * B + b] = rhs[i];
-          }
-        }
-      }
-      if (tid < nx) bd.fb_origin[((size_t)t * nx + tid) * B + b] = xorg;
-      ex.sync();
-      // ---- phase F: V_x = Q_x + Q_ux^T k ; V_xx = Q_xx + Q_ux^T K ---------------------------------------------------
+      // ---- phase F: V_x = Q_x + Q_ux^T k ; V_xx = Q_xx + Q_ux^T K  (V_xx stored row-major) ----------------------------
       {
-        double vacc[(nd * nd + nd + BT - 1) / BT];
-        FOR_ELEMS(e, nd * nd + nd) {
-          if (e < nd * nd) {
-            const int r = e % nd, c = e / nd;
-            double a = 0.0;
+        double vacc[(NF + BT - 1) / BT];
+        unsigned vdst[(NF + BT - 1) / BT];
+        FOR_ELEMS(e, NF) {
+          unsigned f0, f1;
+          if (PRE) { f0 = dF0[PRE ? u_ : 0]; f1 = dF1[PRE ? u_ : 0]; } else mkF(e, f0, f1);
+          vdst[u_] = f1 >> 16;
+          const double* qa = sm + (f0 & 0xffffu);
+          const double* kb = sm + (f0 >> 16);
+          double a = 0.0;
 #pragma unroll
-            for (int k = 0; k < nu; ++k) a += sm[S::Qux + r * nu + k] * sm[S::KK + c * nu + k];
-            vacc[u_] = sm[S::Qxx + e] + a;
-          } else {
-            const int i = e - nd * nd;
-            double a = 0.0;
-#pragma unroll
-            for (int k = 0; k < nu; ++k) a += sm[S::Qux + i * nu + k] * sm[S::kk + k];
-            vacc[u_] = sm[S::Qx + i] + a;
-          }
+          for (int k = 0; k < nu; ++k) a += qa[k] * kb[k];
+          vacc[u_] = sm[f1 & 0xffffu] + a;
         }
-        FOR_ELEMS(e, nd * nd + nd) sm[S::Vxx + e] = vacc[u_];  // V_xx | V_x are adjacent
+        FOR_ELEMS(e, NF) sm[vdst[u_]] = vacc[u_];  // V_xx (row-major) | V_x are adjacent
       }
       ex.sync();
+      DDPB_PHASE_MARK(bd, 12, pc_);
     }
     if (!failed) success = true;
     else if (bd.max_restarts > 0 && (restarts > bd.max_restarts || !(mu < 1.79e308))) {

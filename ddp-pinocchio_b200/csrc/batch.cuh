@@ -108,6 +108,11 @@ struct DevExec {
     __syncthreads();
 #endif
   }
+  DDPB_HD void sync_warp() const {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+  }
 };
 
 }  // namespace ddpb

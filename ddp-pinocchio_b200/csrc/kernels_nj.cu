@@ -32,12 +32,12 @@ template <int NJ, int MODE> __global__ void __launch_bounds__(DDPB_LIN_LB_THREAD
   if (!any) return;  // every problem of the group is frozen (converged / diverged)
   linearize_group<NJ, MODE>(m, bd, t, b0, nk, ne_sm, sm, DevExec{});
 }
-// one warp (= one CTA of 32 threads) per problem; enough CTAs per SM that a whole batch is resident in one wave
-template <int NJ> __global__ void __launch_bounds__(32, NJ <= 2 ? 28 : (NJ <= 4 ? 16 : 8)) backward_kernel(const __grid_constant__ BatchDev bd) {
+// one CTA of BwdGeom<NJ>::BT threads per problem; enough CTAs per SM that a whole batch is resident in one wave
+template <int NJ> __global__ void __launch_bounds__(BwdGeom<NJ>::BT, NJ <= 2 ? 28 : (NJ <= 3 ? 16 : (NJ <= 5 ? 8 : 7))) backward_kernel(const __grid_constant__ BatchDev bd) {
   extern __shared__ __align__(16) double sm[];
   const int b = bd.b0 + blockIdx.x;
   if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
-  backward_problem<NJ, 32>(bd, b, sm, DevExec{});
+  backward_problem<NJ, BwdGeom<NJ>::BT>(bd, b, sm, DevExec{});
 }
 #else
 template <int NJ> __global__ void linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, int t0, int t1) {
@@ -109,7 +109,7 @@ template <> size_t Launch<KNJ>::lin_smem_bytes(int hess_mode, int ne_max, int eq
 }
 template <> size_t Launch<KNJ>::bwd_smem_bytes() {
 #if DDPB_NJ > 0
-  return (size_t)BwdSmem<KNJ>::SIZE * sizeof(double);
+  return (size_t)BwdSmem<KNJ>::size_for(BwdGeom<KNJ>::BT) * sizeof(double);
 #else
   return 0;
 #endif
@@ -139,7 +139,8 @@ template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, i
 }
 template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
 #if DDPB_NJ > 0
-  backward_kernel<KNJ><<<bd.nb, threads, smem, s>>>(bd);
+  (void)threads;
+  backward_kernel<KNJ><<<bd.nb, BwdGeom<KNJ>::BT, smem, s>>>(bd);
 #else
   (void)bd; (void)threads; (void)smem; (void)s;
 #endif
