@@ -24,9 +24,9 @@ static_assert(sizeof(ModelDev) < 3500, "model must fit the kernel parameter spac
 // kernels
 // -------------------------------------------------------------------------------------------------
 __global__ void post_forward_kernel(const __grid_constant__ BatchDev bd) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= bd.B) return;
-  post_forward_problem(bd, b);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bd.nb) return;
+  post_forward_problem(bd, bd.b0 + i);
 }
 // 16 independent FMA chains per thread: saturates the FP64 pipe
 __global__ void fp64_peak_kernel(double* out, int iters) {
@@ -43,9 +43,9 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
   for (int k = 0; k < 16; ++k) s += a[k];
   if (s == 12345.678) out[0] = s;  // keep the chains alive
 }
-__global__ void scalar_copy_kernel(double* scal, int B, int dst, int src) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) scal[(size_t)dst * B + b] = scal[(size_t)src * B + b];
+__global__ void scalar_copy_kernel(double* scal, int B, int b0, int nb, int dst, int src) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) scal[(size_t)dst * B + b0 + i] = scal[(size_t)src * B + b0 + i];
 }
 __global__ void fill_kernel(double* p, size_t n, double v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -135,6 +135,14 @@ struct ddpb_batch {
   float phase_ms[4] = {0, 0, 0, 0};
   size_t lin_smem = 0;
   int lin_threads = 128, bwd_threads = 128, lin_kpb = 1;
+  // ddpb_solve runs the batch as `nsub` sub-batches, each on its own stream: the latency-bound sweeps (backward pass,
+  // rollouts) of one sub-batch overlap the throughput-bound linearization of another, and a problem that needs
+  // several backward restarts only delays its own sub-batch
+  int nsub = 1;
+  std::vector<cudaStream_t> sub_streams;     // high priority: backward pass, rollouts, outer-loop sweeps (latency-bound)
+  std::vector<cudaStream_t> sub_streams_lo;  // low priority: linearization (throughput-bound, fills whatever is free)
+  std::vector<cudaEvent_t> sub_done, sub_lin, sub_hi;
+  cudaEvent_t fork_ev = nullptr;
   size_t bwd_smem = 0;
 };
 
@@ -157,15 +165,21 @@ static int ensure_stage(ddpb_batch* h, size_t bytes) {
 }
 
 struct PhaseScope {
-  ddpb_batch* h; int idx = -1;
-  PhaseScope(ddpb_batch* hh, int phase) : h(hh) {
+  ddpb_batch* h; int idx = -1; cudaStream_t s;
+  PhaseScope(ddpb_batch* hh, int phase, cudaStream_t ss) : h(hh), s(ss) {
     if (!h->timing) return;
     PhaseEv ev; ev.phase = phase;
     cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
-    cudaEventRecord(ev.a, h->stream);
+    cudaEventRecord(ev.a, s);
     h->events.push_back(ev); idx = (int)h->events.size() - 1;
   }
-  ~PhaseScope() { if (idx >= 0) cudaEventRecord(h->events[idx].b, h->stream); }
+  ~PhaseScope() { if (idx >= 0) cudaEventRecord(h->events[idx].b, s); }
+};
+// the launch helpers take the (sub-)batch descriptor and the stream explicitly; LaunchCtx{h} = whole batch on h->stream
+struct LaunchCtx {
+  ddpb_batch* h; BatchDev bd; cudaStream_t s;
+  explicit LaunchCtx(ddpb_batch* hh) : h(hh), bd(hh->bd), s(hh->stream) {}
+  LaunchCtx(ddpb_batch* hh, int b0, int nb, cudaStream_t ss) : h(hh), bd(hh->bd), s(ss) { bd.b0 = b0; bd.nb = nb; }
 };
 
 // run STMT with L = Launch<k> for the model tag k (0 = pendulum, 1..7 = joints)
@@ -189,8 +203,9 @@ static int check_launch(ddpb_batch* h, const char* what) {
   return DDPB_OK;
 }
 
-static int launch_linearize(ddpb_batch* h) {
-  PhaseScope ps(h, 0);
+static int launch_linearize(const LaunchCtx& c) {
+  ddpb_batch* h = c.h;
+  PhaseScope ps(h, 0, c.s);
   // one launch per maximal run of knots with the same number of equality rows: shared memory (and with it the
   // number of resident CTAs) is sized for the run, not for the most constrained knot of the horizon
   const int T = h->bd.T;
@@ -198,39 +213,43 @@ static int launch_linearize(ddpb_batch* h) {
   while (t0 < T) {
     int t1 = t0 + 1;
     while (t1 < T && h->ne[t1] == h->ne[t0]) ++t1;
-    DISPATCH(h->mt, L::linearize(h->model, h->bd, h->lin_threads, h->lin_kpb, t0, t1, h->ne[t0], h->stream));
+    DISPATCH(h->mt, L::linearize(h->model, c.bd, h->lin_threads, h->lin_kpb, t0, t1, h->ne[t0], c.s));
     int rc = check_launch(h, "linearize");
     if (rc) return rc;
     t0 = t1;
   }
   return DDPB_OK;
 }
-static int launch_backward(ddpb_batch* h) {
-  PhaseScope ps(h, 1);
-  DISPATCH(h->nj, L::backward(h->bd, h->bwd_threads, h->bwd_smem, h->stream));
+static int launch_backward(const LaunchCtx& c) {
+  ddpb_batch* h = c.h;
+  PhaseScope ps(h, 1, c.s);
+  DISPATCH(h->nj, L::backward(c.bd, h->bwd_threads, h->bwd_smem, c.s));
   return check_launch(h, "backward");
 }
-static int launch_forward(ddpb_batch* h) {
-  PhaseScope ps(h, 2);
-  DISPATCH(h->mt, L::forward(h->model, h->bd, h->costs_old, h->ls_xs, h->ls_us, h->stream));
+static int launch_forward(const LaunchCtx& c) {
+  ddpb_batch* h = c.h;
+  PhaseScope ps(h, 2, c.s);
+  DISPATCH(h->mt, L::forward(h->model, c.bd, h->costs_old, h->ls_xs, h->ls_us, c.s));
   h->launches += 1;  // cost_seq_aug of the current trajectory + the concurrent line search
   return check_launch(h, "forward");
 }
-static int launch_al_update(ddpb_batch* h, double thr) {
-  PhaseScope ps(h, 3);
-  DISPATCH(h->mt, L::al_update(h->bd, thr, h->stream));
+static int launch_al_update(const LaunchCtx& c, double thr) {
+  ddpb_batch* h = c.h;
+  PhaseScope ps(h, 3, c.s);
+  DISPATCH(h->mt, L::al_update(c.bd, thr, c.s));
   h->launches += 3;  // origin update, decision sweep, multiplier update, second sweep
   return check_launch(h, "al_update");
 }
-static int launch_simple(ddpb_batch* h, int which) {  // 0 post_forward
-  PhaseScope ps(h, 3);
+static int launch_post_forward(const LaunchCtx& c) {
+  ddpb_batch* h = c.h;
+  PhaseScope ps(h, 3, c.s);
   const int th = 128;
-  if (which == 0) post_forward_kernel<<<(h->bd.B + th - 1) / th, th, 0, h->stream>>>(h->bd);
+  post_forward_kernel<<<(c.bd.nb + th - 1) / th, th, 0, c.s>>>(c.bd);
   return check_launch(h, "post_forward");
 }
-static int scalar_copy(ddpb_batch* h, int dst, int src) {
-  scalar_copy_kernel<<<(h->bd.B + 127) / 128, 128, 0, h->stream>>>(h->bd.scal, h->bd.B, dst, src);
-  return check_launch(h, "scalar_copy");
+static int scalar_copy(const LaunchCtx& c, int dst, int src) {
+  scalar_copy_kernel<<<(c.bd.nb + 127) / 128, 128, 0, c.s>>>(c.bd.scal, c.bd.B, c.bd.b0, c.bd.nb, dst, src);
+  return check_launch(c.h, "scalar_copy");
 }
 static int fill(ddpb_batch* h, double* p, size_t n, double v) {
   if (n == 0) return DDPB_OK;
@@ -358,7 +377,7 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   h->lin_threads = fdv ? (n <= 2 ? 32 : (n <= 4 ? 128 : 256)) : 64;
   h->bwd_threads = 32;  // one warp per problem (backward.cuh)
   // development knobs (launch geometry sweeps); not part of the interface
-  if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->lin_threads = v; }
+  if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= (fdv ? 256 : 128) && v % 32 == 0) h->lin_threads = v; }
 
   // problems per CTA of the linearization: small models leave most lanes of a one-knot CTA idle
   h->lin_kpb = fdv ? 1 : (n <= 1 ? 16 : (n == 2 ? 8 : (n <= 4 ? 2 : 1)));
@@ -367,6 +386,23 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) { ddpb_batch_destroy(h); return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory"); }
   DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });
   DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(); });
+  // sub-batches of ddpb_solve: enough problems per sub-batch to keep whole warps / CTAs busy
+  h->nsub = B >= 512 ? 4 : (B >= 128 ? 2 : 1);
+  if (const char* e = getenv("DDPB_SUBBATCHES")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->nsub = v; }
+  if (h->nsub > 1) {
+    h->sub_streams.resize(h->nsub); h->sub_streams_lo.resize(h->nsub);
+    h->sub_done.resize(h->nsub); h->sub_lin.resize(h->nsub); h->sub_hi.resize(h->nsub);
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int i = 0; i < h->nsub; ++i) {
+      CU(cudaStreamCreateWithPriority(&h->sub_streams[i], cudaStreamNonBlocking, prio_hi));
+      CU(cudaStreamCreateWithPriority(&h->sub_streams_lo[i], cudaStreamNonBlocking, prio_lo));
+      CU(cudaEventCreateWithFlags(&h->sub_done[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->sub_lin[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->sub_hi[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+  }
   CU(cudaStreamSynchronize(h->stream));
   *out = h;
   return DDPB_OK;
@@ -380,6 +416,12 @@ void ddpb_batch_destroy(ddpb_batch* h) {
   if (h->stage) cudaFree(h->stage);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (auto& e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto st : h->sub_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (auto st : h->sub_streams_lo) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (auto ev : h->sub_done) cudaEventDestroy(ev);
+  for (auto ev : h->sub_lin) cudaEventDestroy(ev);
+  for (auto ev : h->sub_hi) cudaEventDestroy(ev);
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -593,7 +635,7 @@ int ddpb_scalars_device_ptr(ddpb_batch* h, void** ptr) {
 
 int ddpb_compute_derivatives(ddpb_batch* h) {
   ENTER(h);
-  int rc = launch_linearize(h);
+  int rc = launch_linearize(LaunchCtx(h));
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));
   return DDPB_OK;
@@ -604,7 +646,7 @@ int ddpb_backward_pass(ddpb_batch* h, double* mu, double* reg) {
   const int B = h->bd.B;
   CU(cudaMemcpyAsync(h->bd.scal + (size_t)S_MU * B, mu, B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->bd.scal + (size_t)S_REG * B, reg, B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  int rc = launch_backward(h);
+  int rc = launch_backward(LaunchCtx(h));
   if (rc) return rc;
   CU(cudaMemcpyAsync(mu, h->bd.scal + (size_t)S_MU * B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(reg, h->bd.scal + (size_t)S_REG * B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -613,7 +655,7 @@ int ddpb_backward_pass(ddpb_batch* h, double* mu, double* reg) {
 }
 int ddpb_forward_pass(ddpb_batch* h, double* step_out) {
   ENTER(h);
-  int rc = launch_forward(h);
+  int rc = launch_forward(LaunchCtx(h));
   if (rc) return rc;
   if (step_out) CU(cudaMemcpyAsync(step_out, h->bd.scal + (size_t)S_STEP * h->bd.B, h->bd.B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -724,23 +766,59 @@ int ddpb_solve_async(ddpb_batch* h, const ddpb_solver_params* p) {
   R(fill(h, bd.scal + S_REG * B, B, p->reg));
   R(fill(h, bd.scal + S_W * B, B, p->w));
   R(fill(h, bd.scal + S_N * B, B, p->n));
+  // sub-batches: contiguous ranges of problems, multiples of 32 (one warp of the thread-per-problem kernels)
+  const int nsub = h->nsub;
+  std::vector<LaunchCtx> sub;
+  if (nsub <= 1) {
+    sub.emplace_back(h);
+  } else {
+    const int per = (((int)B + nsub - 1) / nsub + 31) / 32 * 32;
+    for (int i = 0, b0 = 0; i < nsub && b0 < (int)B; ++i, b0 += per) sub.emplace_back(h, b0, std::min(per, (int)B - b0), h->sub_streams[i]);
+    CU(cudaEventRecord(h->fork_ev, h->stream));
+    for (auto& c : sub) CU(cudaStreamWaitEvent(c.s, h->fork_ev, 0));
+  }
   // warm-up derivative / backward / forward (ddp.hpp:768-773): mu is taken from it, reg is not,
   // and the trial trajectory is not swapped in
-  R(scalar_copy(h, S_SPARE, S_REG));
-  R(launch_linearize(h));
-  R(launch_backward(h));
-  R(scalar_copy(h, S_REG, S_SPARE));
-  R(launch_forward(h));
-  CU(cudaMemsetAsync(bd.scal + S_ROLLOUTS * B, 0, B * sizeof(double), h->stream));
-  CU(cudaMemsetAsync(bd.scal + S_RESTARTS * B, 0, B * sizeof(double), h->stream));
+  // linearization of sub-batch i runs on its low-priority stream, everything else on the high-priority one
+  auto linearize_sub = [&](size_t i) -> int {
+    LaunchCtx& c = sub[i];
+    if (nsub <= 1) return launch_linearize(c);
+    LaunchCtx lo = c;
+    lo.s = h->sub_streams_lo[i];
+    if (cudaEventRecord(h->sub_hi[i], c.s) != cudaSuccess || cudaStreamWaitEvent(lo.s, h->sub_hi[i], 0) != cudaSuccess) return fail(DDPB_ERR_CUDA, "stream fork");
+    int rc_ = launch_linearize(lo);
+    if (rc_) return rc_;
+    if (cudaEventRecord(h->sub_lin[i], lo.s) != cudaSuccess || cudaStreamWaitEvent(c.s, h->sub_lin[i], 0) != cudaSuccess) return fail(DDPB_ERR_CUDA, "stream join");
+    return DDPB_OK;
+  };
+  for (size_t i = 0; i < sub.size(); ++i) {
+    LaunchCtx& c = sub[i];
+    R(scalar_copy(c, S_SPARE, S_REG));
+    R(linearize_sub(i));
+    R(launch_backward(c));
+    R(scalar_copy(c, S_REG, S_SPARE));
+    R(launch_forward(c));
+    CU(cudaMemsetAsync(bd.scal + S_ROLLOUTS * B + c.bd.b0, 0, c.bd.nb * sizeof(double), c.s));
+    CU(cudaMemsetAsync(bd.scal + S_RESTARTS * B + c.bd.b0, 0, c.bd.nb * sizeof(double), c.s));
+  }
   for (int iter = 0; iter < p->max_iterations; ++iter) {
-    R(launch_linearize(h));
-    R(launch_al_update(h, p->optimality_stopping_threshold));
-    R(launch_backward(h));
-    R(launch_forward(h));
-    R(launch_simple(h, 0));
+    for (size_t i = 0; i < sub.size(); ++i) {
+      LaunchCtx& c = sub[i];
+      c.bd.xs = bd.xs; c.bd.us = bd.us; c.bd.xs_new = bd.xs_new; c.bd.us_new = bd.us_new;
+      R(linearize_sub(i));
+      R(launch_al_update(c, p->optimality_stopping_threshold));
+      R(launch_backward(c));
+      R(launch_forward(c));
+      R(launch_post_forward(c));
+    }
     std::swap(bd.xs, bd.xs_new);   // swap(traj, new_traj)  (ddp.hpp:826)
     std::swap(bd.us, bd.us_new);
+  }
+  if (nsub > 1) {
+    for (size_t i = 0; i < sub.size(); ++i) {
+      CU(cudaEventRecord(h->sub_done[i], sub[i].s));
+      CU(cudaStreamWaitEvent(h->stream, h->sub_done[i], 0));
+    }
   }
 #undef R
   return DDPB_OK;

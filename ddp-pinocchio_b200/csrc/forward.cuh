@@ -18,11 +18,21 @@
 namespace ddpb {
 
 // x_{t+1} = f(x_t, u_t): explicit Euler on forward dynamics (problem.hpp:441-461)
-template <int NJ> DDPB_HD void dyn_eval(const ModelDev& m, double dt, const double* x, const double* u, double* xn) {
-  double qrec[QRec<NJ>::SIZE];
+// per-thread scratch of the fused forward dynamics: element e at p[e * stride] (rbd.cuh aba_fused)
+struct Scratch {
+  double* p;
+  int stride;
+};
+template <int NJ> DDPB_HD void dyn_eval(const ModelDev& m, double dt, const double* x, const double* u, double* xn, const Scratch& sc) {
   double qdd[NJ];
-  q_task<NJ>(m, x, qrec);
-  v_task<NJ, false>(m, qrec, x + NJ, u, qdd, nullptr);
+  if (NJ <= 3) {
+    // small models: the whole q-record fits the register file (same arithmetic as aba_fused)
+    double qrec[QRec<NJ>::SIZE];
+    q_task<NJ>(m, x, qrec);
+    v_task<NJ, false>(m, qrec, x + NJ, u, qdd, nullptr);
+  } else {
+    aba_fused<NJ>(m, x, x + NJ, u, qdd, sc.p, sc.stride);
+  }
 #pragma unroll
   for (int k = 0; k < NJ; ++k) {
     const double vo = dt * x[NJ + k];
@@ -31,12 +41,14 @@ template <int NJ> DDPB_HD void dyn_eval(const ModelDev& m, double dt, const doub
   }
 }
 template <int NJ> struct DynOps {
-  DDPB_HD static void eval(const ModelDev& m, double dt, const double* x, const double* u, double* xn) { dyn_eval<NJ>(m, dt, x, u, xn); }
+  static constexpr int SCR = NJ <= 3 ? 1 : ABA_SCR_PER_BODY * NJ;  // scratch doubles per thread
+  DDPB_HD static void eval(const ModelDev& m, double dt, const double* x, const double* u, double* xn, const Scratch& sc) { dyn_eval<NJ>(m, dt, x, u, xn, sc); }
   DDPB_HD static void frame(const ModelDev& m, const double* q, int frame, double* p3) { frame_task<NJ>(m, q, frame, 0, p3, nullptr); }
 };
 // pendulum: NJ = 0 selects the analytic model
 template <> struct DynOps<0> {
-  DDPB_HD static void eval(const ModelDev& m, double dt, const double* x, const double* u, double* xn) { pend_eval(m, dt, x, u[0], xn); }
+  static constexpr int SCR = 1;
+  DDPB_HD static void eval(const ModelDev& m, double dt, const double* x, const double* u, double* xn, const Scratch&) { pend_eval(m, dt, x, u[0], xn); }
   DDPB_HD static void frame(const ModelDev&, const double*, int, double* p3) { p3[0] = p3[1] = p3[2] = 0.0; }
 };
 template <int NJ> struct Dim { static constexpr int n = NJ == 0 ? 1 : NJ; };
@@ -83,7 +95,7 @@ DDPB_HD double merit_term(const ModelDev& m, const BatchDev& bd, int b, int t, c
 }
 
 // make_trajectory: roll the stored controls out from x_0 (xs[0] must be set)
-template <int NJ> DDPB_HD void rollout_problem(const ModelDev& m, const BatchDev& bd, int b) {
+template <int NJ> DDPB_HD void rollout_problem(const ModelDev& m, const BatchDev& bd, int b, const Scratch& sc) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
   const int B = bd.B;
   double x[nx], u[nu], xn[nx];
@@ -92,14 +104,14 @@ template <int NJ> DDPB_HD void rollout_problem(const ModelDev& m, const BatchDev
   for (int t = 0; t < bd.T; ++t) {
 #pragma unroll
     for (int k = 0; k < nu; ++k) u[k] = bd.us[((size_t)t * nu + k) * B + b];
-    DynOps<NJ>::eval(m, bd.dt, x, u, xn);
+    DynOps<NJ>::eval(m, bd.dt, x, u, xn, sc);
 #pragma unroll
     for (int k = 0; k < nx; ++k) { x[k] = xn[k]; bd.xs[((size_t)(t + 1) * nx + k) * B + b] = xn[k]; }
   }
 }
 
 // cost_seq_aug of the current trajectory into costs[(T+1)][B]; returns the plain cost sum_t l
-template <int NJ> DDPB_HD double cost_seq_problem(const ModelDev& m, const BatchDev& bd, int b, double* costs, double mu) {
+template <int NJ> DDPB_HD double cost_seq_problem(const ModelDev& m, const BatchDev& bd, int b, double* costs, double mu, const Scratch& sc) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
   const int B = bd.B;
   double plain = 0.0;
@@ -110,7 +122,7 @@ template <int NJ> DDPB_HD double cost_seq_problem(const ModelDev& m, const Batch
 #pragma unroll
     for (int k = 0; k < nu; ++k) u[k] = bd.us[((size_t)t * nu + k) * B + b];
     // the reference re-evaluates f(x_t,u_t) inside eval_eq_to; only needed where the knot has rows
-    if (bd.ne[t] > 0) DynOps<NJ>::eval(m, bd.dt, x, u, xn);
+    if (bd.ne[t] > 0) DynOps<NJ>::eval(m, bd.dt, x, u, xn, sc);
     costs[(size_t)t * B + b] = merit_term<NJ>(m, bd, b, t, x, u, xn, mu);
     double s = 0.0;
 #pragma unroll
@@ -121,18 +133,42 @@ template <int NJ> DDPB_HD double cost_seq_problem(const ModelDev& m, const Batch
   return plain;
 }
 
+DDPB_HD void l2_prefetch(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// rows of knot t that a rollout step reads (x_t, u_t, k_t, K_t, old cost) -> L2, one request per row and warp
+template <int NJ> DDPB_HD void prefetch_knot(const BatchDev& bd, int b, int t, const double* costs_old) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n;
+  const int B = bd.B;
+  if (t >= bd.T) return;
+#pragma unroll
+  for (int k = 0; k < nx; ++k) l2_prefetch(bd.xs + ((size_t)t * nx + k) * B + b);
+#pragma unroll
+  for (int k = 0; k < nu; ++k) { l2_prefetch(bd.us + ((size_t)t * nu + k) * B + b); l2_prefetch(bd.fb_k + ((size_t)t * nu + k) * B + b); }
+#pragma unroll
+  for (int k = 0; k < nu * nd; ++k) l2_prefetch(bd.fb_K + ((size_t)t * nu * nd + k) * B + b);
+  l2_prefetch(costs_old + (size_t)t * B + b);
+}
+
 // one trial of the line search (ddp_fwd.ipp:39-56): closed-loop rollout with step size `step` from x_0, written
 // to (xs_out, us_out) (same SoA layout as the trajectory), and sum_t (cost_new - cost_old) in the reference's order
 template <int NJ>
 DDPB_HD void rollout_candidate(const ModelDev& m, const BatchDev& bd, int b, double step, double mu, const double* costs_old, double* xs_out,
-                               double* us_out, double* sum_out, double* merit_out, double* plain_out) {
+                               double* us_out, double* sum_out, double* merit_out, double* plain_out, const Scratch& sc, bool do_prefetch = false) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n;
   const int B = bd.B, T = bd.T;
   double x[nx], xn[nx], u[nu];
 #pragma unroll
   for (int k = 0; k < nx; ++k) x[k] = bd.xs_new[(size_t)k * B + b];  // x_0 of the new-trajectory storage (= x_0)
   double sum = 0.0, merit = 0.0, plain = 0.0;
+  if (do_prefetch) prefetch_knot<NJ>(bd, b, 1, costs_old);
   for (int t = 0; t < T; ++t) {
+    // the rows of knot t+2 start their way to L2 while the dynamics of knot t is evaluated
+    if (do_prefetch) prefetch_knot<NJ>(bd, b, t + 2, costs_old);
     double dx[nd];
 #pragma unroll
     for (int k = 0; k < nd; ++k) dx[k] = x[k] - bd.xs[((size_t)t * nx + k) * B + b];
@@ -144,7 +180,7 @@ DDPB_HD void rollout_candidate(const ModelDev& m, const BatchDev& bd, int b, dou
       u[i] = bd.us[((size_t)t * nu + i) * B + b] + step * bd.fb_k[((size_t)t * nu + i) * B + b] + a;
       us_out[((size_t)t * nu + i) * B + b] = u[i];
     }
-    DynOps<NJ>::eval(m, bd.dt, x, u, xn);
+    DynOps<NJ>::eval(m, bd.dt, x, u, xn, sc);
     const double cn = merit_term<NJ>(m, bd, b, t, x, u, xn, mu);
     sum += cn - costs_old[(size_t)t * B + b];
     merit += cn;
@@ -173,7 +209,9 @@ template <int NJ> DDPB_HD void forward_problem(const ModelDev& m, const BatchDev
     return;
   }
   const double mu = bd.scal[(size_t)S_MU * B + b];
-  cost_seq_problem<NJ>(m, bd, b, costs_old, mu);
+  double scr_[DynOps<NJ>::SCR];
+  const Scratch sc{scr_, 1};
+  cost_seq_problem<NJ>(m, bd, b, costs_old, mu, sc);
   double step = 1.0;
   bool success = false;
   int rollouts = 0;
@@ -182,7 +220,7 @@ template <int NJ> DDPB_HD void forward_problem(const ModelDev& m, const BatchDev
     if (step < 1e-10) break;
     ++rollouts;
     double sum;
-    rollout_candidate<NJ>(m, bd, b, step, mu, costs_old, bd.xs_new, bd.us_new, &sum, &merit, &plain);
+    rollout_candidate<NJ>(m, bd, b, step, mu, costs_old, bd.xs_new, bd.us_new, &sum, &merit, &plain, sc);
     if (sum <= 0.0) success = true;
     else step *= 0.5;
   }

@@ -17,11 +17,13 @@ constexpr int KNJ = DDPB_NJ;
 // throughput-bound linearization of another and a straggling problem delays only its own sub-batch.
 #if DDPB_NJ > 0
 // grid: (knots t0..t1-1) x (groups of `kpb` consecutive problems); all knots of a launch have the same ne
+// FD-of-Jacobians kernels run with <= 128 threads and are compiled for 4 resident CTAs per SM (128 registers);
+// the value-based mode has 1 + n + n(n-1)/2 evaluation points per knot and runs one 256-thread CTA per SM.
 #ifndef DDPB_LIN_LB_THREADS
-#define DDPB_LIN_LB_THREADS 256
-#define DDPB_LIN_LB_BLOCKS 1
+#define DDPB_LIN_LB_THREADS 128
+#define DDPB_LIN_LB_BLOCKS 4
 #endif
-template <int NJ, int MODE> __global__ void __launch_bounds__(DDPB_LIN_LB_THREADS, DDPB_LIN_LB_BLOCKS) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
+template <int NJ, int MODE> __global__ void __launch_bounds__(MODE == HESS_FD_JACOBIANS ? DDPB_LIN_LB_THREADS : 256, MODE == HESS_FD_JACOBIANS ? DDPB_LIN_LB_BLOCKS : 1) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
                                                                           int t0, int kpb, int ne_sm) {
   extern __shared__ __align__(16) double sm[];
   const int groups = (bd.nb + kpb - 1) / kpb;
@@ -50,24 +52,27 @@ template <int NJ> __global__ void linearize_kernel(const __grid_constant__ Model
 #endif
 
 // line search: cost_seq_aug of the current trajectory (thread per problem), then LS_NC concurrent trials per problem
+// per-thread scratch of the fused forward dynamics in dynamic shared memory: element e of thread i at dyn_scr[e * blockDim.x + i]
+extern __shared__ __align__(16) double dyn_scr[];
+__device__ __forceinline__ Scratch thread_scratch() { return Scratch{dyn_scr + threadIdx.x, (int)blockDim.x}; }
 template <int NJ> __global__ void cost_old_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, double* costs_old) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, b = bd.b0 + i;
   if (i >= bd.nb || bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
-  cost_seq_problem<NJ>(m, bd, b, costs_old, bd.scal[(size_t)S_MU * bd.B + b]);
+  cost_seq_problem<NJ>(m, bd, b, costs_old, bd.scal[(size_t)S_MU * bd.B + b], thread_scratch());
 }
 template <int NJ> __global__ void __launch_bounds__(32 * LS_NC) forward_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
                                                                                const double* costs_old, double* xs_c, double* us_c) {
-  linesearch_block<NJ>(m, bd, costs_old, xs_c, us_c);
+  linesearch_block<NJ>(m, bd, costs_old, xs_c, us_c, thread_scratch());
 }
 template <int NJ> __global__ void rollout_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= bd.nb) return;
-  rollout_problem<NJ>(m, bd, bd.b0 + i);
+  rollout_problem<NJ>(m, bd, bd.b0 + i, thread_scratch());
 }
 template <int NJ> __global__ void cost_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, double* costs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, b = bd.b0 + i;
   if (i >= bd.nb) return;
-  const double plain = cost_seq_problem<NJ>(m, bd, b, costs, bd.scal[(size_t)S_MU * bd.B + b]);
+  const double plain = cost_seq_problem<NJ>(m, bd, b, costs, bd.scal[(size_t)S_MU * bd.B + b], thread_scratch());
   bd.scal[(size_t)S_COST * bd.B + b] = plain;
 }
 // outer-loop sweeps (outer_warp.cuh): per-(knot, problem) kernels and one-warp-per-problem adjoint recursion
@@ -96,6 +101,7 @@ template <int NJ> __global__ void optimality_kernel(const __grid_constant__ Batc
 }
 
 constexpr int TPP = 32;  // threads per block of the thread-per-problem kernels
+static size_t scr_bytes(int threads) { return (size_t)DynOps<KNJ>::SCR * threads * sizeof(double); }
 
 template <> size_t Launch<KNJ>::lin_smem_bytes(int hess_mode, int ne_max, int eq_kind) {
 #if DDPB_NJ > 0
@@ -115,6 +121,13 @@ template <> size_t Launch<KNJ>::bwd_smem_bytes() {
 #endif
 }
 template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
+  {
+    cudaError_t e = cudaFuncSetAttribute(forward_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(32 * LS_NC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cost_old_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cost_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rollout_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
+    if (e != cudaSuccess) return e;
+  }
 #if DDPB_NJ > 0
   cudaError_t e = cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_JACOBIANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
   if (e != cudaSuccess) return e;
@@ -146,15 +159,15 @@ template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t s
 #endif
 }
 template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, cudaStream_t s) {
-  cost_old_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs_old);
-  forward_kernel<KNJ><<<(bd.nb + 31) / 32, 32 * LS_NC, 0, s>>>(m, bd, costs_old, xs_c, us_c);
+  cost_old_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd, costs_old);
+  forward_kernel<KNJ><<<(bd.nb + 31) / 32, 32 * LS_NC, scr_bytes(32 * LS_NC), s>>>(m, bd, costs_old, xs_c, us_c);
 }
 template <> int Launch<KNJ>::linesearch_slots() { return LS_NC; }
 template <> void Launch<KNJ>::rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s) {
-  rollout_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, 0, s>>>(m, bd);
+  rollout_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd);
 }
 template <> void Launch<KNJ>::cost(const ModelDev& m, const BatchDev& bd, double* costs, cudaStream_t s) {
-  cost_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, 0, s>>>(m, bd, costs);
+  cost_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd, costs);
 }
 template <> void Launch<KNJ>::al_update(const BatchDev& bd, double thr, cudaStream_t s) {
   const size_t nkb = (size_t)bd.nb * bd.T;

@@ -286,25 +286,40 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   if (fdj) {
     // problem.hpp:128-145: T(k,j,idx) = (J'(k,j) - J(k,j)) / eps ; rows k < n are exact constants (zero difference).
     // bottom rows: fx(k,j) of point p is DQ/DV[(k-n) + j'*n] of that point's record; fu(k,j) is dt * M^-1 of its q-set.
-    FOR_BLOCK(kk, e, nd * nd * nd) {
-      const int k = e % nd, j = (e / nd) % nd, i = e / (nd * nd);
-      double v = 0.0;
+    // Two-level loops: a thread owns a (row k, column j) pair of the Jacobian and walks the perturbation index i, so
+    // the row / column / offset arithmetic is done once per pair and the inner loop is load - subtract - scale - store
+    // with constant strides (consecutive threads still write consecutive doubles for every i).
+    for (int idx = tid; idx < nk * nd * nd; idx += nthr) {
+      const int kk = idx / (nd * nd), r = idx - kk * (nd * nd);
+      const int k = r % nd, j = r / nd;
+      double* dst = &REC(kk, L.fxx + r);
       if (k >= n) {
         const int off = (j < n ? V::DQ + j * NJ : V::DV + (j - n) * NJ) + (k - n);
-        const double* vr = SM(kk, pl.o_vrec);
-        v = (vr[(size_t)(1 + i) * V::SIZE + off] - vr[off]) * inv_eps;
+        const double* vr = SM(kk, pl.o_vrec) + off;
+        const double base = vr[0];
+#pragma unroll
+        for (int i = 0; i < nd; ++i) dst[(size_t)i * nd * nd] = (vr[(size_t)(1 + i) * V::SIZE] - base) * inv_eps;
+      } else {
+#pragma unroll
+        for (int i = 0; i < nd; ++i) dst[(size_t)i * nd * nd] = 0.0;
       }
-      REC(kk, L.fxx + e) = v;
     }
-    FOR_BLOCK(kk, e, nd * nu * nd) {
-      const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu);
-      double v = 0.0;
-      if (k >= n && i < n) {  // only a q-perturbation changes M^-1; v-perturbed points share the base q-set (exact zero)
-        const double* qr = SM(kk, pl.o_qrec);
-        const int off = Q::MINV + j * NJ + (k - n);
-        v = (qr[(size_t)(1 + i) * Q::SIZE + off] * dt - qr[off] * dt) * inv_eps;
+    for (int idx = tid; idx < nk * nd * nu; idx += nthr) {
+      const int kk = idx / (nd * nu), r = idx - kk * (nd * nu);
+      const int k = r % nd, j = r / nd;
+      double* dst = &REC(kk, L.fux + r);
+      if (k >= n) {
+        // only a q-perturbation changes M^-1; v-perturbed points share the base q-set (exact zero)
+        const double* qr = SM(kk, pl.o_qrec) + Q::MINV + j * NJ + (k - n);
+        const double base = qr[0] * dt;
+#pragma unroll
+        for (int i = 0; i < n; ++i) dst[(size_t)i * nd * nu] = (qr[(size_t)(1 + i) * Q::SIZE] * dt - base) * inv_eps;
+#pragma unroll
+        for (int i = n; i < nd; ++i) dst[(size_t)i * nd * nu] = 0.0;
+      } else {
+#pragma unroll
+        for (int i = 0; i < nd; ++i) dst[(size_t)i * nd * nu] = 0.0;
       }
-      REC(kk, L.fux + e) = v;
     }
     FOR_BLOCK(kk, e, nd * nu * nu) REC(kk, L.fuu + e) = 0.0;  // u-perturbed points share the base q-set: same M^-1, exact zero
     if (ne > 0) {

@@ -195,11 +195,11 @@ template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev&
 // rolls out into its own scratch trajectory; the smallest accepted trial index wins exactly as in the sequential scan
 // (34 trials at most, last one kept on give-up, ddp_fwd.ipp:35-37), and the block copies the winner into the
 // new-trajectory storage.  The `rollouts` scalar keeps counting what the sequential algorithm would have run.
-constexpr int LS_NC = 8;
+constexpr int LS_NC = 4;
 constexpr int LS_MAX_TRIALS = 34;  // 2^-33 >= 1e-10 > 2^-34
 
 template <int NJ>
-__device__ __forceinline__ void linesearch_block(const ModelDev& m, const BatchDev& bd, const double* costs_old, double* xs_c, double* us_c) {
+__device__ __forceinline__ void linesearch_block(const ModelDev& m, const BatchDev& bd, const double* costs_old, double* xs_c, double* us_c, const Scratch& sc) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
   const int B = bd.B, T = bd.T;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -217,7 +217,11 @@ __device__ __forceinline__ void linesearch_block(const ModelDev& m, const BatchD
     const int c = r * LS_NC + w;
     const bool run = valid && !frozen && s_win[lane] == -1 && c < LS_MAX_TRIALS;
     double sum = 1.0, merit = 0.0, plain = 0.0;
-    if (run) rollout_candidate<NJ>(m, bd, b, ldexp(1.0, -c), mu, costs_old, xs_c + w * xs_slot, us_c + w * us_slot, &sum, &merit, &plain);
+    // trial slot 0 rolls out straight into the new-trajectory storage: when the first trial of a round wins (the
+    // usual case: the full step) nothing has to be copied
+    double* xo = w == 0 ? bd.xs_new : xs_c + w * xs_slot;
+    double* uo = w == 0 ? bd.us_new : us_c + w * us_slot;
+    if (run) rollout_candidate<NJ>(m, bd, b, ldexp(1.0, -c), mu, costs_old, xo, uo, &sum, &merit, &plain, sc, w == 0);
     s_sum[w][lane] = run ? sum : 1.0;
     s_merit[w][lane] = merit; s_plain[w][lane] = plain;
     __syncthreads();
@@ -239,11 +243,13 @@ __device__ __forceinline__ void linesearch_block(const ModelDev& m, const BatchD
     }
     __syncthreads();
     // problems resolved in this round: copy the winning scratch trajectory now (a later round would overwrite the slot)
-    if (valid && s_win[lane] >= 1000) {
+    if (valid && s_win[lane] > 1000) {
       const int slot = s_win[lane] - 1000;
       const double* xw = xs_c + slot * xs_slot;
       const double* uw = us_c + slot * us_slot;
+#pragma unroll 8
       for (int e = nx + w; e < (T + 1) * nx; e += LS_NC) bd.xs_new[(size_t)e * B + b] = xw[(size_t)e * B + b];
+#pragma unroll 8
       for (int e = w; e < T * nu; e += LS_NC) bd.us_new[(size_t)e * B + b] = uw[(size_t)e * B + b];
     }
     __syncthreads();

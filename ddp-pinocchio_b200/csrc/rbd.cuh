@@ -383,6 +383,85 @@ template <int NJ, bool REC> DDPB_HD void v_task(const ModelDev& m, const double*
   }
 }
 
+// ---- aba_fused ------------------------------------------------------------------------------------
+// Forward dynamics qdd = ABA(q, qd, tau) for ONE evaluation (the rollouts): the same arithmetic as q_task followed by
+// v_task<NJ, false> -- bit for bit, the derivative records' f(x, u) must equal the rollout -- but with the three
+// sweeps fused so that only 28 doubles per body survive between them.  They live in `scr`, a per-thread strided
+// scratch (element e at scr[e * stride]): shared memory with stride = threads per block on the device (conflict-free,
+// no local-memory traffic), a plain array on the host.
+constexpr int ABA_SCR_PER_BODY = 28;  // S(6) | c(6) | pA(6) | Y(10, reused as U(6), 1/D, u after the inertia is consumed)
+template <int NJ> DDPB_HD void aba_fused(const ModelDev& m, const double* q, const double* qd, const double* tau, double* qdd_out, double* scr, int stride) {
+#define SCR(i, e) scr[((i) * ABA_SCR_PER_BODY + (e)) * stride]
+  {
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+    double v[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      joint_advance(m, i, q[i], R, p);
+      double S[6], Y[10], sq[6], c[6], h[6], pa[6];
+      body_world(m, i, R, p, S, Y);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { sq[k] = S[k] * qd[i]; v[k] += sq[k]; }
+      crm(v, sq, c);
+      y_mul(Y, v, h);
+      crf(v, h, pa);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { SCR(i, k) = S[k]; SCR(i, 6 + k) = c[k]; SCR(i, 12 + k) = pa[k]; }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) SCR(i, 18 + k) = Y[k];
+    }
+  }
+  {
+    double IA[21];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) IA[k] = 0.0;
+#pragma unroll
+    for (int i = NJ - 1; i >= 0; --i) {
+      double Y[10], S[6], U[6], pa[6], c[6];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) Y[k] = SCR(i, 18 + k);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { S[k] = SCR(i, k); c[k] = SCR(i, 6 + k); pa[k] = SCR(i, 12 + k); }
+      ia_add_body(IA, Y);
+      sym6_mul(IA, S, U);
+      const double Dinv = 1.0 / dot6(S, U);
+      const double u = tau[i] - dot6(S, pa);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) SCR(i, 18 + k) = U[k];
+      SCR(i, 24) = Dinv;
+      SCR(i, 25) = u;
+      if (i > 0) {
+        double Iac[6];
+        const double t = Dinv * (u - dot6(U, c));
+        sym6_mul(IA, c, Iac);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const double add = pa[k] + Iac[k] + U[k] * t;
+          SCR(i - 1, 12 + k) += add;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double sr = U[r] * Dinv;
+#pragma unroll
+          for (int cc = r; cc < 6; ++cc) IA[s6(r, cc)] -= sr * U[cc];
+        }
+      }
+    }
+  }
+  double a[6] = {0.0, 0.0, 0.0, -m.grav[0], -m.grav[1], -m.grav[2]};
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    double S[6], U[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { S[k] = SCR(i, k); U[k] = SCR(i, 18 + k); a[k] += SCR(i, 6 + k); }
+    const double qdd = SCR(i, 24) * (SCR(i, 25) - dot6(U, a));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] += S[k] * qdd;
+    qdd_out[i] = qdd;
+  }
+#undef SCR
+}
+
 // ---- col_task -----------------------------------------------------------------------------------
 // column j of d tau/d q (wrt_v = 0) or d tau/d qdot (wrt_v = 1) of inverse dynamics at (q, qdot, qddot = ABA result).
 // World-frame closed form (bodies k >= j move rigidly with joint j; S_j x is the spatial motion cross product):

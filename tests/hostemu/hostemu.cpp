@@ -141,13 +141,13 @@ void emu_forward(void* hv) {
 }
 void emu_rollout(void* hv) {
   Emu* h = (Emu*)hv;
-  EMU_MT(h->mt, { for (int b = 0; b < h->bd.B; ++b) rollout_problem<MT>(h->model, h->bd, b); });
+  EMU_MT(h->mt, { for (int b = 0; b < h->bd.B; ++b) { double scr_[DynOps<MT>::SCR]; rollout_problem<MT>(h->model, h->bd, b, Scratch{scr_, 1}); } });
 }
 void emu_cost(void* hv) {
   Emu* h = (Emu*)hv;
   EMU_MT(h->mt, {
     for (int b = 0; b < h->bd.B; ++b)
-      h->bd.scal[(size_t)S_COST * h->bd.B + b] = cost_seq_problem<MT>(h->model, h->bd, b, h->costs_old.data(), h->bd.scal[(size_t)S_MU * h->bd.B + b]);
+      h->bd.scal[(size_t)S_COST * h->bd.B + b] = [&] { double scr_[DynOps<MT>::SCR]; return cost_seq_problem<MT>(h->model, h->bd, b, h->costs_old.data(), h->bd.scal[(size_t)S_MU * h->bd.B + b], Scratch{scr_, 1}); }();
   });
 }
 void emu_al_update(void* hv, double thr) {
