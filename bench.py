@@ -53,7 +53,8 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons; samples are time-stamped on arrival so that only those that fall inside
+    the timed region are reported."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -63,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -71,11 +72,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count(self, t0, t1=None):
+        return sum(1 for t, _ in self.rows if t >= t0 and (t1 is None or t <= t1))
+
+    def stop(self, windows):
+        """windows: list of (t0, t1) wall-clock intervals during which the timed kernels were running"""
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -83,7 +88,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if not any(a <= t <= b for a, b in windows):
+                continue
             try:
                 sm.append(float(r[0])); mx = float(r[1])
                 for nme, v in zip(names, r[3:7]):
@@ -92,6 +99,16 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def kernel_counts(workload_name):
+    """Per-kernel figures taken from ncu captures of this workload (profiles/r01_kernel_counts.json): executed FP64
+    flops per knot and DRAM bytes per knot (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its knots)."""
+    p = os.path.join(ROOT, "profiles", "r01_kernel_counts.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        return json.load(f).get(workload_name, {})
 
 
 def calibrate_cpu_sample(ol, w, nthreads, target_s):
@@ -133,7 +150,7 @@ def run_reference(args, w, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", help="c1..c5 (BASELINE.json configs); default configs[1]")
@@ -210,26 +227,55 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        resident_step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    bt.enable_phase_timing(True)
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    barrier()
+    # ---- timed region: K steps, CUDA events on the launching stream (the solver forks its sub-batch streams from it
+    # and joins them back into it), barrier + synchronize on both sides
     l0 = bt.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    windows = []
+    tw0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         resident_step()
     ev1.record(stream)
     barrier()
+    windows.append((tw0, time.time()))
     launches = bt.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
+    sc = bt.get_scalars()
+    if rank == 0:
+        # a short timed region can end before nvidia-smi delivered enough samples: keep the same steps running (untimed)
+        # until a handful of samples under this load exist
+        t_ext = time.time()
+        while sampler.proc and sum(sampler.count(a, b) for a, b in windows) + sampler.count(t_ext) < 5 and time.time() - t_ext < 4.0:
+            bt.snapshot_restore(); bt.solve(its, w.mu, read_back=False); bt.sync()   # no collective: rank 0 only
+        if time.time() - t_ext > 0.05:
+            windows.append((t_ext, time.time()))
+    barrier()
+    clocks = sampler.stop(windows) if rank == 0 else None
+    if rank == 0 and len(windows) > 1:
+        clocks["note"] = "timed region shorter than the sampling period: sampling continued over identical untimed steps"
+    # ---- per-kernel launch durations: same steps with the solver on ONE stream (kernels back to back, no overlap), one
+    # CUDA-event pair around every launch
+    ksteps = min(args.steps, 3)
+    bt.set_subbatches(1)
+    resident_step(); barrier()
+    bt.enable_phase_timing(True)
+    evk0, evk1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evk0.record(stream)
+    for _ in range(ksteps):
+        resident_step()
+    evk1.record(stream)
+    barrier()
+    ms_one_stream = evk0.elapsed_time(evk1) / ksteps
     phases = bt.phase_times()
     bt.enable_phase_timing(False)
-    sc = bt.get_scalars()
-    clocks = sampler.stop() if rank == 0 else None
+    bt.set_subbatches(int(os.environ.get("DDPB_SUBBATCHES", "0")) or bt.default_subbatches())
     # e2e leg (host buffers in, results out), wall clock bracketed by synchronisation
     e2e_step()
     barrier()
@@ -248,7 +294,8 @@ def main():
         e2e_val = knots_per_step * args.steps / (e2e_ms * 1e-3)
         hbm_peak, peak_src = read_peaks()
         lin_b, bwd_b = algorithmic_bytes_per_knot(w)
-        n_lin = n_bwd = (its + 1) * args.steps  # launches in the timed region (incl. the warm-up pass of every solve)
+        n_lin = n_bwd = (its + 1) * ksteps  # launches in the kernel-timing leg (incl. the warm-up pass of every solve)
+        kc = kernel_counts(w.name)
         kern = {
             "linearize": {"ms_avg": phases["linearize"] / n_lin, "alg_bytes": lin_b * B * T},
             "backward": {"ms_avg": phases["backward"] / n_bwd, "alg_bytes": bwd_b * B * T},
@@ -256,12 +303,21 @@ def main():
         }
         dom = max(("linearize", "backward", "forward"), key=lambda k: phases[k])
         share = {k: phases[k] / max(sum(phases.values()), 1e-9) for k in phases}
-        rk = kern[dom if kern[dom]["alg_bytes"] else "backward"]
-        rname = dom if kern[dom]["alg_bytes"] else "backward"
+        rname = dom if kern[dom]["alg_bytes"] else "linearize"
+        rk = kern[rname]
         achieved = rk["alg_bytes"] / (rk["ms_avg"] * 1e-3) / 1e9
         fp64_peak = capi.measure_fp64_peak(local)
+        traffic = kc.get(rname, {}).get("dram_bytes_per_knot")
+        kout = {}
+        for k, v in kern.items():
+            kout[k] = {"ms_avg": v["ms_avg"], "share_of_step": share[k],
+                       "hbm_gbs": (v["alg_bytes"] / (v["ms_avg"] * 1e-3) / 1e9) if v["alg_bytes"] else None}
+            fl = kc.get(k, {}).get("fp64_flops_per_knot")
+            if fl:
+                kout[k]["fp64_tflops"] = fl * B * T / (v["ms_avg"] * 1e-3) / 1e12
+                kout[k]["fp64_frac_of_measured_peak"] = kout[k]["fp64_tflops"] / fp64_peak
         line = {
-            "metric": METRIC, "value": value, "unit": "knots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": "knots/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "ddp_iterations_per_sec": world * B * its * args.steps / (ms * 1e-3),
             "config": {"workload": w.name, "problems_per_gpu": B, "horizon": T, "iterations_per_step": its, "nx": w.nx, "nu": w.nu,
@@ -273,10 +329,13 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": rname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "algorithmic bytes per launch (BASELINE.md s3) / mean CUDA-event launch duration in the timed region"},
-            "kernels": {k: {"ms_avg": v["ms_avg"], "share_of_step": share[k],
-                            "hbm_gbs": (v["alg_bytes"] / (v["ms_avg"] * 1e-3) / 1e9) if v["alg_bytes"] else None} for k, v in kern.items()},
+                         "traffic": (traffic * B * T) if traffic else None, "peak_source": peak_src,
+                         "note": "algorithmic bytes per launch (BASELINE.md s3: 8*(slab+nx+nu) per knot written by the linearization, "
+                                 "8*(slab+2nx+nu+nu*ndx+eq) read by the backward pass) / mean CUDA-event launch duration; traffic = ncu "
+                                 "dram bytes per knot (profiles/r01_kernel_counts.json) x knots per launch"},
+            "kernels": kout,
+            "kernel_timing": {"steps": ksteps, "ms_per_step_one_stream": ms_one_stream,
+                              "note": "launch durations measured with the solver on one stream (no overlap between sub-batches)"},
             "fp64_peak_tflops_measured": fp64_peak,
             "rollouts_per_iteration": float(sc["rollouts"].mean() / its), "backward_restarts_per_problem": float(sc["restarts"].mean()),
             "opt_constr_median": float(np.median(sc["opt_constr"])),

@@ -22,7 +22,7 @@ EXPORTS = ["ddpb_model_create", "ddpb_model_destroy", "ddpb_batch_create", "ddpb
            "ddpb_get_scalars", "ddpb_scalars_device_ptr", "ddpb_compute_derivatives", "ddpb_backward_pass", "ddpb_forward_pass",
            "ddpb_cost_seq_aug", "ddpb_optimality", "ddpb_solve", "ddpb_solve_async", "ddpb_batch_dims", "ddpb_launch_count",
            "ddpb_phase_times", "ddpb_enable_phase_timing", "ddpb_snapshot_save", "ddpb_snapshot_restore",
-           "ddpb_measure_fp64_peak"]
+           "ddpb_measure_fp64_peak", "ddpb_set_subbatches"]
 
 
 class DdpbError(RuntimeError):
@@ -291,6 +291,13 @@ class Batch(BatchBase):
     # ---- introspection ----
     def launch_count(self):
         return int(lib().ddpb_launch_count(self._h))
+
+    def set_subbatches(self, n):
+        _check(lib().ddpb_set_subbatches(self._h, int(n)))
+
+    def default_subbatches(self):
+        """what ddpb_batch_create chooses: enough problems per sub-batch to keep whole CTAs busy"""
+        return 4 if self.B >= 512 else (2 if self.B >= 128 else 1)
 
     def enable_phase_timing(self, on=True):
         _check(lib().ddpb_enable_phase_timing(self._h, 1 if on else 0))

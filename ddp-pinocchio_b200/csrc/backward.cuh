@@ -62,11 +62,12 @@ template <int N, bool ALIGNED> DDPB_HD double dot_run(const double* a, const dou
       acc[(2 * k) & 3] += x.x * y.x;
       acc[(2 * k + 1) & 3] += x.y * y.y;
     }
-    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
-  }
+  } else
 #endif
+  {
 #pragma unroll
-  for (int k = 0; k < N; ++k) acc[k & 3] += a[k] * b[k];
+    for (int k = 0; k < N; ++k) acc[k & 3] += a[k] * b[k];
+  }
   return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
@@ -151,7 +152,7 @@ template <int NJ, int BT, class Ex>
 DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& ex) {
   constexpr int nd = 2 * NJ, nu = NJ, nx = 2 * NJ;
   using S = BwdSmem<NJ>;
-  constexpr int nQxx = nd * nd, nQux = nu * nd, nQuu = nu * nu, NTEN = S::NTEN;
+  constexpr int nQxx = nd * nd, nQux = nu * nd, NTEN = S::NTEN;
   constexpr bool AL = S::head_aligned;  // fx / fu columns of the head copy start on 16-byte boundaries
   const int B = bd.B, T = bd.T;
   const int tid = ex.tid();

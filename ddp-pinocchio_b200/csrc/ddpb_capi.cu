@@ -374,34 +374,24 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   // launch geometry
   const bool fdv = p->hess_mode == DDPB_HESS_FD_VALUES;
   // measured on B200 (tools/sweep_geometry.sh, profiles/): small CTAs keep more knots / problems resident per SM
-  h->lin_threads = fdv ? (n <= 2 ? 32 : (n <= 4 ? 128 : 256)) : 64;
+  h->lin_threads = fdv ? (n <= 2 ? 32 : (n <= 4 ? 128 : 256)) : (n >= 5 ? 256 : 64);
   h->bwd_threads = 32;  // one warp per problem (backward.cuh)
   // development knobs (launch geometry sweeps); not part of the interface
-  if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= (fdv ? 256 : 128) && v % 32 == 0) h->lin_threads = v; }
+  if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->lin_threads = v; }
 
   // problems per CTA of the linearization: small models leave most lanes of a one-knot CTA idle
-  h->lin_kpb = fdv ? 1 : (n <= 1 ? 16 : (n == 2 ? 8 : (n <= 4 ? 2 : 1)));
+  h->lin_kpb = fdv ? 1 : (n <= 1 ? 16 : (n == 2 ? 8 : 2));
   if (const char* e = getenv("DDPB_LIN_KPB")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->lin_kpb = v; }
   DISPATCH(h->mt, { h->lin_smem = L::lin_smem_bytes(p->hess_mode, bd.ne_max, p->eq_kind) * h->lin_kpb; });
   if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) { ddpb_batch_destroy(h); return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory"); }
   DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });
   DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(); });
   // sub-batches of ddpb_solve: enough problems per sub-batch to keep whole warps / CTAs busy
-  h->nsub = B >= 512 ? 4 : (B >= 128 ? 2 : 1);
-  if (const char* e = getenv("DDPB_SUBBATCHES")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->nsub = v; }
-  if (h->nsub > 1) {
-    h->sub_streams.resize(h->nsub); h->sub_streams_lo.resize(h->nsub);
-    h->sub_done.resize(h->nsub); h->sub_lin.resize(h->nsub); h->sub_hi.resize(h->nsub);
-    int prio_lo = 0, prio_hi = 0;
-    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    for (int i = 0; i < h->nsub; ++i) {
-      CU(cudaStreamCreateWithPriority(&h->sub_streams[i], cudaStreamNonBlocking, prio_hi));
-      CU(cudaStreamCreateWithPriority(&h->sub_streams_lo[i], cudaStreamNonBlocking, prio_lo));
-      CU(cudaEventCreateWithFlags(&h->sub_done[i], cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&h->sub_lin[i], cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&h->sub_hi[i], cudaEventDisableTiming));
-    }
-    CU(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+  {
+    int nsub = B >= 512 ? 4 : (B >= 128 ? 2 : 1);
+    if (const char* e = getenv("DDPB_SUBBATCHES")) { const int v = atoi(e); if (v >= 1 && v <= 32) nsub = v; }
+    const int rc2 = ddpb_set_subbatches(h, nsub);
+    if (rc2) { ddpb_batch_destroy(h); return rc2; }
   }
   CU(cudaStreamSynchronize(h->stream));
   *out = h;
@@ -431,6 +421,28 @@ int ddpb_batch_set_stream(ddpb_batch* h, void* s) {
   if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   h->stream = (cudaStream_t)s;
   h->own_stream = false;
+  return DDPB_OK;
+}
+int ddpb_set_subbatches(ddpb_batch* h, int n) {
+  if (!h || n < 1 || n > 32) return fail(DDPB_ERR_INVALID, "sub-batch count must be in 1..32");
+  CU(cudaSetDevice(h->device));
+  if ((int)h->sub_streams.size() < n && n > 1) {
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int i = (int)h->sub_streams.size(); i < n; ++i) {
+      cudaStream_t hi = nullptr, lo = nullptr;
+      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+      CU(cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, prio_hi));
+      CU(cudaStreamCreateWithPriority(&lo, cudaStreamNonBlocking, prio_lo));
+      CU(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+      h->sub_streams.push_back(hi); h->sub_streams_lo.push_back(lo);
+      h->sub_done.push_back(e0); h->sub_lin.push_back(e1); h->sub_hi.push_back(e2);
+    }
+    if (!h->fork_ev) CU(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+  }
+  h->nsub = n;
   return DDPB_OK;
 }
 int ddpb_batch_sync(ddpb_batch* h) {

@@ -171,6 +171,11 @@ unsigned long long ddpb_launch_count(const ddpb_batch* b);
 /* device time of the last ddpb_solve / hot-path call per phase, ms: linearize, backward, forward, other */
 int ddpb_phase_times(ddpb_batch* b, float* ms4);
 int ddpb_enable_phase_timing(ddpb_batch* b, int on);
+/* ddpb_solve runs the batch as `n` contiguous sub-batches (1..32), each on its own pair of CUDA streams, so that the
+ * latency-bound sweeps of one sub-batch overlap the linearization of another; results do not depend on `n` (problems
+ * are independent -- the reference, ddp.hpp:744-842, solves one problem at a time).  n = 1: one stream, kernels of a
+ * solve run back to back (what the per-kernel timers of ddpb_phase_times assume). */
+int ddpb_set_subbatches(ddpb_batch* b, int n);
 
 #ifdef __cplusplus
 }
