@@ -165,24 +165,42 @@ DDPB_HD void rollout_candidate(const ModelDev& m, const BatchDev& bd, int b, dou
 #pragma unroll
   for (int k = 0; k < nx; ++k) x[k] = bd.xs_new[(size_t)k * B + b];  // x_0 of the new-trajectory storage (= x_0)
   double sum = 0.0, merit = 0.0, plain = 0.0;
-  if (do_prefetch) prefetch_knot<NJ>(bd, b, 1, costs_old);
-  for (int t = 0; t < T; ++t) {
-    // the rows of knot t+2 start their way to L2 while the dynamics of knot t is evaluated
-    if (do_prefetch) prefetch_knot<NJ>(bd, b, t + 2, costs_old);
-    double dx[nd];
+  // The rows a step reads (x_t, u_t, k_t, K_t, old cost) do not depend on the rollout itself.  Small models keep the
+  // NEXT knot's rows in registers (loaded one knot ahead); larger ones send the rows of knot t+2 to L2 while knot t
+  // is evaluated.
+  constexpr bool REGPRE = Dim<NJ>::n <= 3;
+  double r_x[nd], r_K[nu * nd], r_k[nu], r_u[nu], r_c = 0.0;
+  auto load_rows = [&](int t) {
 #pragma unroll
-    for (int k = 0; k < nd; ++k) dx[k] = x[k] - bd.xs[((size_t)t * nx + k) * B + b];
+    for (int k = 0; k < nd; ++k) r_x[k] = bd.xs[((size_t)t * nx + k) * B + b];
+#pragma unroll
+    for (int k = 0; k < nu * nd; ++k) r_K[k] = bd.fb_K[((size_t)t * nu * nd + k) * B + b];
+#pragma unroll
+    for (int k = 0; k < nu; ++k) { r_k[k] = bd.fb_k[((size_t)t * nu + k) * B + b]; r_u[k] = bd.us[((size_t)t * nu + k) * B + b]; }
+    r_c = costs_old[(size_t)t * B + b];
+  };
+  if (REGPRE) load_rows(0);
+  else if (do_prefetch) prefetch_knot<NJ>(bd, b, 1, costs_old);
+  for (int t = 0; t < T; ++t) {
+    if (!REGPRE) {
+      if (do_prefetch) prefetch_knot<NJ>(bd, b, t + 2, costs_old);
+      load_rows(t);
+    }
+    double dx[nd], c_old = r_c;
+#pragma unroll
+    for (int k = 0; k < nd; ++k) dx[k] = x[k] - r_x[k];
 #pragma unroll
     for (int i = 0; i < nu; ++i) {
       double a = 0.0;
 #pragma unroll
-      for (int k = 0; k < nd; ++k) a += bd.fb_K[((size_t)t * nu * nd + k * nu + i) * B + b] * dx[k];
-      u[i] = bd.us[((size_t)t * nu + i) * B + b] + step * bd.fb_k[((size_t)t * nu + i) * B + b] + a;
+      for (int k = 0; k < nd; ++k) a += r_K[k * nu + i] * dx[k];
+      u[i] = r_u[i] + step * r_k[i] + a;
       us_out[((size_t)t * nu + i) * B + b] = u[i];
     }
+    if (REGPRE && t + 1 < T) load_rows(t + 1);  // in flight during the dynamics of knot t
     DynOps<NJ>::eval(m, bd.dt, x, u, xn, sc);
     const double cn = merit_term<NJ>(m, bd, b, t, x, u, xn, mu);
-    sum += cn - costs_old[(size_t)t * B + b];
+    sum += cn - c_old;
     merit += cn;
     double s = 0.0;
 #pragma unroll
