@@ -30,16 +30,17 @@ template <int NJ> struct BwdSmem {
   static constexpr int h_lx = 0, h_lu = h_lx + nd, h_lxx = h_lu + nu, h_lux = h_lxx + nd * nd, h_luu = h_lux + nu * nd,
                        h_f = h_luu + nu * nu, h_fx = h_f + nd, h_fu = h_fx + nd * nd, NHEAD = h_fu + nd * nu;
   static constexpr int even(int x) { return (x + 1) & ~1; }
-  static constexpr int head = 0, VxxR = even(head + NHEAD), Vx = VxxR + nd * nd, VF = even(Vx + nd), VU = VF + nd * nd,
+  static constexpr int RS = NJ <= 6 ? 32 : 16;  // tensor elements per staging round and warp
+  static constexpr int head = 0, head2 = even(head + NHEAD), VxxR = even(head2 + NHEAD), Vx = VxxR + nd * nd, VF = even(Vx + nd), VU = VF + nd * nd,
                        Qx = even(VU + nd * nu), Qu = Qx + nd, Qxx = even(Qu + nu), Qux = Qxx + nd * nd, Quu = Qux + nu * nd,
                        Wf = even(Quu + nu * nu),  // V_x-contraction of fxx | fux | fuu, task-list order
                        L = even(Wf + NTEN), dinv = L + nu * nu, kk = even(dinv + nu), KK = even(kk + nu),
                        eqv = even(KK + nu * nd), eqx = eqv + MAXE, equ = eqx + MAXE * nd, pe = equ + MAXE * nu,
                        pex = pe + MAXE, tmp = pex + MAXE * nd, tmp2 = tmp + MAXE, flags = tmp2 + MAXE * nd,
                        zero = flags + 2,  // one double that stays 0.0 (tasks without a tensor term add it)
-                       stage = even(zero + 2),  // device: NW warp-private staging buffers of 32 * nd doubles
+                       stage = even(zero + 2),  // device: NW warp-private staging buffers of RS * nd doubles
                        SIZE = stage;
-  static constexpr int size_for(int threads) { return SIZE + (threads >= 32 ? (threads / 32) * 32 * nd : 0); }
+  static constexpr int size_for(int threads) { return SIZE + (threads >= 32 ? (threads / 32) * RS * nd : 0); }
   // head offset of fx must be even for the 16-byte inner products: nd + nu + nd*nd + nu*nd + nu*nu + nd = nu (mod 2)
   static constexpr bool head_aligned = (h_fx % 2) == 0 && (h_fu % 2) == 0;
 };
@@ -161,8 +162,6 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
   int restarts = 0;
   bool success = false;
 #define FOR_ELEMS(e, N) _Pragma("unroll") for (int u_ = 0; u_ < ((N) + BT - 1) / BT; ++u_) if (const int e = tid + u_ * BT; e < (N))
-  const double* fx = sm + S::head + S::h_fx;
-  const double* fu = sm + S::head + S::h_fu;
   // Per-thread task descriptors (shared-memory offsets of the operands of every inner product this thread owns),
   // computed once: the knot loop then runs one branch-free code path per phase instead of re-deriving row / column /
   // block from the task index at every knot.
@@ -174,7 +173,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
   constexpr bool PRE = NJ <= 5 || BT == 1;
   auto mkB = [&](int e) -> unsigned {  // a | b << 16
     const int r = e % nd, c = e / nd;  // c runs over the columns of f_x, then of f_u (adjacent in the head)
-    return (unsigned)(S::VxxR + r * nd) | ((unsigned)(S::head + S::h_fx + c * nd) << 16);
+    return (unsigned)(S::VxxR + r * nd) | ((unsigned)(S::h_fx + c * nd) << 16);  // b relative to the current head buffer
   };
   auto mkC = [&](int e, unsigned& d0, unsigned& d1, unsigned& d2) {  // a|b , l|w , dst|ldst (bit 15 of ldst: diagonal)
     int a, bo, l, w = S::zero, dst, ldst = 0x7fff, diag = 0;
@@ -195,8 +194,8 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       const int i = e - NTEN - nd;
       a = S::h_fu + i * nd; bo = S::Vx; l = S::h_lu + i; dst = S::Qu + i;
     }
-    d0 = (unsigned)(S::head + a) | ((unsigned)bo << 16);
-    d1 = (unsigned)(S::head + l) | ((unsigned)w << 16);
+    d0 = (unsigned)a | ((unsigned)bo << 16);  // a and l relative to the current head buffer
+    d1 = (unsigned)l | ((unsigned)w << 16);
     d2 = (unsigned)dst | ((unsigned)(ldst | (diag << 15)) << 16);
   };
   auto mkF = [&](int e, unsigned& d0, unsigned& d1) {  // a|b , q|dst
@@ -225,30 +224,35 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
     bool failed = false;
     // software pipeline: what knot t needs first -- the head of its record (registers) and round 0 of every warp's
     // tensor share (warp-private staging buffer, cp.async) -- is fetched while knot t+1 is being processed
-    double hv[(S::NHEAD + BT - 1) / BT];
+    int hcur = 0;  // which head buffer holds the knot being processed
 #if defined(__CUDA_ARCH__)
-    constexpr int NW = BT / 32, EW = (NTEN + NW - 1) / NW, CPE = nd / 2;  // CPE: 16-byte chunks per tensor element
+    constexpr int RS = S::RS, NW = BT / 32, EW = (NTEN + NW - 1) / NW, CPE = nd / 2;  // CPE: 16-byte chunks per tensor element
     const int warp = tid >> 5, lane = tid & 31;
-    double* stg = sm + S::stage + warp * 32 * nd;
+    double* stg = sm + S::stage + warp * RS * nd;
     const int e_beg = warp * EW, e_end = (warp + 1) * EW < NTEN ? (warp + 1) * EW : NTEN;
 #endif
-    auto prefetch = [&](int tp) {
+    // fetch what knot tp needs first into the buffers that are idle while the current knot is processed: the head of
+    // its record -> the other head buffer, round 0 of every warp's tensor share -> the warp's staging buffer
+    auto prefetch = [&](int tp, int hnext) {
       const RecLayout Lp = rec_layout(nd, nu, nx, bd.ne[tp]);
       const double* recp = slab_rec(bd, tp, b, Lp.size);
-      FOR_ELEMS(e, S::NHEAD) hv[u_] = recp[e];
+      double* hdst = sm + (hnext ? S::head2 : S::head);
 #if defined(__CUDA_ARCH__)
-      const int ne_round = e_end - e_beg < 32 ? e_end - e_beg : 32;
+      FOR_ELEMS(c, S::NHEAD / 2) cp_async16(hdst + 2 * c, recp + 2 * c);
+      const int ne_round = e_end - e_beg < RS ? e_end - e_beg : RS;
       const double2* src = reinterpret_cast<const double2*>(recp + Lp.fxx + (size_t)e_beg * nd);
 #pragma unroll
-      for (int i = 0; i < CPE; ++i) {
+      for (int i = 0; i < (RS * CPE + 31) / 32; ++i) {
         const int c = lane + 32 * i;
         if (c < ne_round * CPE) cp_async16(reinterpret_cast<double2*>(stg) + c, src + c);
       }
+#else
+      for (int e = 0; e < S::NHEAD; ++e) hdst[e] = recp[e];
 #endif
     };
     cp_async_wait_all();  // a restarted pass may still have the aborted knot's prefetch in flight
     ex.sync_warp();
-    prefetch(T - 1);
+    prefetch(T - 1, hcur);
     for (int t = T - 1; t >= 0; --t) {
       DDPB_PHASE_START(bd, pc_);
       const int ne = bd.ne[t], eo = bd.eq_off[t];
@@ -259,35 +263,36 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         const int sz = rec_layout(nd, nu, nx, bd.ne[t - 2]).size;
         l2_prefetch_bulk(slab_rec(bd, t - 2, b, sz), (unsigned)(sz * sizeof(double)));
       }
-      // ---- phase A: head of the record -> shared memory; tensors -> V_x contraction ------------------------------
+      // ---- phase A: head of the record (prefetched) ; tensors -> V_x contraction ----------------------------------------
+      const double* hd = sm + (hcur ? S::head2 : S::head);
       double xorg = 0.0;
       if (tid < nx) xorg = bd.xs[((size_t)t * nx + tid) * B + b];
       {
-        FOR_ELEMS(e, S::NHEAD) sm[S::head + e] = hv[u_];
 #if defined(__CUDA_ARCH__)
         // Each warp owns a contiguous range of the Q_xx | Q_ux | Q_uu task list (= a contiguous piece of the adjacent
-        // fxx | fux | fuu blocks) and streams it in rounds of 32 elements: fully coalesced 16-byte loads (consecutive
+        // fxx | fux | fuu blocks) and streams it in rounds of RS elements: fully coalesced 16-byte loads (consecutive
         // lanes -> consecutive chunks) into the warp's staging buffer, then every lane contracts the k-run of its own
         // element with V_x.  Only __syncwarp is needed: the buffer is private to the warp.  Round 0 was fetched
         // asynchronously during the previous knot; the loads of round r+1 are in flight while round r is contracted.
         {
-          double2 buf[CPE];
+          constexpr int LPR = (RS * CPE + 31) / 32;  // 16-byte loads per lane and round
+          double2 buf[LPR];
           auto load_round = [&](int e0) {
-            const int ne_round = e_end - e0 < 32 ? e_end - e0 : 32;
+            const int ne_round = e_end - e0 < RS ? e_end - e0 : RS;
             const double2* src = reinterpret_cast<const double2*>(rec + L.fxx + (size_t)e0 * nd);
 #pragma unroll
-            for (int i = 0; i < CPE; ++i) {
+            for (int i = 0; i < LPR; ++i) {
               const int c = lane + 32 * i;
               if (c < ne_round * CPE) buf[i] = src[c];
             }
           };
-          if (e_beg + 32 < e_end) load_round(e_beg + 32);
+          if (e_beg + RS < e_end) load_round(e_beg + RS);
           DDPB_PHASE_MARK(bd, 13, pc_);
           cp_async_wait_all();
           __syncwarp();
           DDPB_PHASE_MARK(bd, 14, pc_);
-          for (int e0 = e_beg; e0 < e_end; e0 += 32) {
-            const int ne_round = e_end - e0 < 32 ? e_end - e0 : 32;
+          for (int e0 = e_beg; e0 < e_end; e0 += RS) {
+            const int ne_round = e_end - e0 < RS ? e_end - e0 : RS;
             if (lane < ne_round) {
               const double2* mine = reinterpret_cast<const double2*>(stg + lane * nd);
               const double2* vx2 = reinterpret_cast<const double2*>(sm + S::Vx);  // broadcast reads
@@ -301,14 +306,14 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
               sm[S::Wf + e0 + lane] = a0 + a1;
             }
             __syncwarp();
-            if (e0 + 32 < e_end) {
-              const int nn = e_end - (e0 + 32) < 32 ? e_end - (e0 + 32) : 32;
+            if (e0 + RS < e_end) {
+              const int nn = e_end - (e0 + RS) < RS ? e_end - (e0 + RS) : RS;
 #pragma unroll
-              for (int i = 0; i < CPE; ++i) {
+              for (int i = 0; i < LPR; ++i) {
                 const int c = lane + 32 * i;
                 if (c < nn * CPE) reinterpret_cast<double2*>(stg)[c] = buf[i];
               }
-              if (e0 + 64 < e_end) load_round(e0 + 64);
+              if (e0 + 2 * RS < e_end) load_round(e0 + 2 * RS);
               __syncwarp();
             }
           }
@@ -334,7 +339,8 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
           for (int e = tid; e < ne * nu; e += BT) sm[S::equ + e] = rec[L.eq_u + e];
         }
         DDPB_PHASE_MARK(bd, 15, pc_);
-        if (t > 0) prefetch(t - 1);  // the staging buffer and hv are free again
+        if (t > 0) prefetch(t - 1, hcur ^ 1);  // the staging buffer and the other head buffer are free
+        hcur ^= 1;
       }
       ex.sync();
       DDPB_PHASE_MARK(bd, 8, pc_);
@@ -347,7 +353,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         double acc[(NB + BT - 1) / BT];
         FOR_ELEMS(e, NB) {
           const unsigned d = PRE ? dB[PRE ? u_ : 0] : mkB(e);
-          acc[u_] = dot_run<nd, AL>(sm + (d & 0xffffu), sm + (d >> 16));
+          acc[u_] = dot_run<nd, AL>(sm + (d & 0xffffu), hd + (d >> 16));
         }
         FOR_ELEMS(e, NB) sm[S::VF + e] = acc[u_];  // VF | VU are adjacent
       }
@@ -369,8 +375,8 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
           unsigned c0, c1, c2;
           if (PRE) { c0 = dC0[PRE ? u_ : 0]; c1 = dC1[PRE ? u_ : 0]; c2 = dC2[PRE ? u_ : 0]; } else mkC(e, c0, c1, c2);
           qdst[u_] = c2;
-          double q = sm[c1 & 0xffffu];
-          q += dot_run<nd, AL>(sm + (c0 & 0xffffu), sm + (c0 >> 16));
+          double q = hd[c1 & 0xffffu];
+          q += dot_run<nd, AL>(hd + (c0 & 0xffffu), sm + (c0 >> 16));
           if (ne > 0) {
             // knots with equality rows (rare): terms by block
             double a = 0.0;
