@@ -108,43 +108,115 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   ex.sync();
   DDPB_PHASE_MARK(bd, 0, pc_);
 
-  // phase 1: q-only data for every distinct configuration
-  for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
-    const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
-    const double* base = SM(kk, pl.o_base);
-    int i, j;
-    pl.qset_pert(s, &i, &j);
-    double q[NJ];
+  // Short tasks (<= 3 joints) run each narrow phase as one task per configuration / point; longer chains split them
+  // into parallel and serial sub-phases (more barriers, much shorter serial parts).
+  constexpr bool SPLIT = NJ >= 4;
+  if (!SPLIT) {
+    for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
+      const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
+      const double* base = SM(kk, pl.o_base);
+      int i, j;
+      pl.qset_pert(s, &i, &j);
+      double q[NJ];
 #pragma unroll
-    for (int k = 0; k < NJ; ++k) q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
-    q_task<NJ>(m, q, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+      for (int k = 0; k < NJ; ++k) q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
+      q_task<NJ>(m, q, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+    }
+  } else {
+    // phase 1: q-only data for every distinct configuration, as four sub-phases (rbd.cuh "q_task"): the local joint
+    // rotations and the per-body world inertias are parallel over (configuration, joint / body); only the kinematic chain
+    // and the articulated-inertia recursion are serial per configuration
+    for (int idx = tid; idx < nk * pl.NQ * NJ; idx += nthr) {
+      const int kk = idx / (pl.NQ * NJ), r = idx - kk * (pl.NQ * NJ), s = r / NJ, jn = r - s * NJ;
+      int i, j;
+      pl.qset_pert(s, &i, &j);
+      const double qj = SM(kk, pl.o_base)[jn] + ((jn == i || jn == j) ? eps : 0.0);
+      double Rl[9];
+      joint_local_rot(m, jn, qj, Rl);
+      double* dst = SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE + Q::IA + QScratch<NJ>::RL + 9 * jn;
+  #pragma unroll
+      for (int k = 0; k < 9; ++k) dst[k] = Rl[k];
+    }
+    ex.sync();
+    for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
+      const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
+      q_chain<NJ>(m, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+    }
+    ex.sync();
+    for (int idx = tid; idx < nk * pl.NQ * NJ; idx += nthr) {
+      const int kk = idx / (pl.NQ * NJ), r = idx - kk * (pl.NQ * NJ), s = r / NJ, jn = r - s * NJ;
+      q_body<NJ>(m, jn, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+    }
+    ex.sync();
+    for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
+      const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
+      q_articulate<NJ>(SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+    }
   }
   ex.sync();
   DDPB_PHASE_MARK(bd, 1, pc_);
 
-  // phase 2: accelerations (and body data where tangents are needed) at every evaluation point
-  for (int idx = tid; idx < nk * pl.P; idx += nthr) {
-    const int kk = idx / pl.P, p = idx - kk * pl.P;
+  // phase 2: accelerations (and body data where derivative columns are needed) at every evaluation point.  Points with
+  // a record (all of them in FD-of-Jacobians mode, the base point otherwise) run as sub-phases (rbd.cuh "v_task as
+  // sub-phases"); value-only points run the whole of v_task<false> in the serial sub-phase.
+  auto point_state = [&](int kk, int p, double* q, double* qd, double* tau) {
     const double* base = SM(kk, pl.o_base);
-    double* fval = SM(kk, pl.o_fval);
     int i, j;
     pl.point_pert(p, &i, &j);
-    double q[NJ], qd[NJ], tau[NJ], qdd[NJ];
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
       q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
       qd[k] = base[n + k] + ((n + k == i || n + k == j) ? eps : 0.0);
       tau[k] = base[2 * n + k] + ((2 * n + k == i || 2 * n + k == j) ? eps : 0.0);
     }
+  };
+  if (SPLIT) {
+    for (int idx = tid; idx < nk * pl.NT; idx += nthr) {
+      const int kk = idx / pl.NT, p = idx - kk * pl.NT;
+      double q[NJ], qd[NJ], tau[NJ];
+      point_state(kk, p, q, qd, tau);
+      v_prefix<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, qd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+    }
+    ex.sync();
+    for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
+      const int kk = idx / (pl.NT * NJ), r = idx - kk * (pl.NT * NJ), p = r / NJ, jn = r - p * NJ;
+      int i, j;
+      pl.point_pert(p, &i, &j);
+      const double qdj = SM(kk, pl.o_base)[n + jn] + ((n + jn == i || n + jn == j) ? eps : 0.0);
+      v_bias<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, jn, qdj, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+    }
+    ex.sync();
+  }
+  for (int idx = tid; idx < nk * pl.P; idx += nthr) {
+    const int kk = idx / pl.P, p = idx - kk * pl.P;
+    double* fval = SM(kk, pl.o_fval);
+    double q[NJ], qd[NJ], tau[NJ], qdd[NJ];
+    point_state(kk, p, q, qd, tau);
     const double* qr = SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE;
-    if (MODE == HESS_FD_JACOBIANS || p == 0) v_task<NJ, true>(m, qr, qd, tau, qdd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
-    else v_task<NJ, false>(m, qr, qd, tau, qdd, nullptr);
+    if (p < pl.NT) {
+      if (SPLIT) v_sweeps<NJ>(m, qr, tau, qdd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      else v_task<NJ, true>(m, qr, qd, tau, qdd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+    } else {
+      v_task<NJ, false>(m, qr, qd, tau, qdd, nullptr);
+    }
     // dynamics_t::eval_to (problem.hpp:441-461): v_out = dt v ; q_out = q + v_out ; v_out = v + acc dt
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
       const double vo = dt * qd[k];
       fval[p * nx + k] = q[k] + vo;
       fval[p * nx + n + k] = qd[k] + qdd[k] * dt;
+    }
+  }
+  if (SPLIT) {
+    ex.sync();
+    for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
+      const int kk = idx / (pl.NT * NJ), r = idx - kk * (pl.NT * NJ), p = r / NJ, jn = r - p * NJ;
+      v_force<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, jn, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+    }
+    ex.sync();
+    for (int idx = tid; idx < nk * pl.NT; idx += nthr) {
+      const int kk = idx / pl.NT, p = idx - kk * pl.NT;
+      v_suffix<NJ>(SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
     }
   }
   ex.sync();

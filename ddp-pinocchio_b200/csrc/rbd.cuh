@@ -193,17 +193,14 @@ template <int NJ> struct VRec {
   static constexpr int A = V + 6 * NJ;        // [NJ][6] body accelerations at the ABA solution (gravity folded in)
   static constexpr int H = A + 6 * NJ;        // [NJ][6] momenta Y_i v_i
   static constexpr int F = H + 6 * NJ;        // [NJ][6] subtree forces of inverse dynamics at the ABA solution
-  static constexpr int DQ = F + 6 * NJ;       // [NJ][NJ] d tau/d q, then dt * da/dq (column-major)
+  static constexpr int DQ = F + 6 * NJ;       // [NJ][NJ] d tau/d q, then dt * da/dq (column-major); v_bias scratch before that
   static constexpr int DV = DQ + NJ * NJ;     // [NJ][NJ] d tau/d qdot, then I + dt * da/dqdot
   static constexpr int RAW = DV + NJ * NJ;
   static constexpr int SIZE = RAW | 1;
 };
 
-// world rotation / origin of joint frame i from those of its parent:  R <- R Rp_i Rot(axis_i, q_i),  p <- p + R_parent pp_i
-DDPB_HD void joint_advance(const ModelDev& m, int i, double q, double* R, double* p) {
-  double t[3];
-  m3v(R, m.pp[i], t);
-  p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
+// local rotation of joint i:  Rl = Rp_i Rot(axis_i, q_i)   (row-major 3x3)
+DDPB_HD void joint_local_rot(const ModelDev& m, int i, double q, double* Rl) {
   double s, c;
   sincos_(q, &s, &c);
   const double v = 1.0 - c;
@@ -212,17 +209,28 @@ DDPB_HD void joint_advance(const ModelDev& m, int i, double q, double* R, double
                         v * a[1] * a[0] + s * a[2], c + v * a[1] * a[1],        v * a[1] * a[2] - s * a[0],
                         v * a[2] * a[0] - s * a[1], v * a[2] * a[1] + s * a[0], c + v * a[2] * a[2]};
   const double* Rp = m.Rp[i];
-  double Rl[9], Rn[9];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) Rl[r * 3 + cc] = Rp[r * 3 + 0] * RJ[0 * 3 + cc] + Rp[r * 3 + 1] * RJ[1 * 3 + cc] + Rp[r * 3 + 2] * RJ[2 * 3 + cc];
+}
+// world rotation / origin of joint frame i from those of its parent:  p <- p + R_parent pp_i ,  R <- R Rl_i
+DDPB_HD void joint_compose(const ModelDev& m, int i, const double* Rl, double* R, double* p) {
+  double t[3];
+  m3v(R, m.pp[i], t);
+  p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
+  double Rn[9];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) Rn[r * 3 + cc] = R[r * 3 + 0] * Rl[0 * 3 + cc] + R[r * 3 + 1] * Rl[1 * 3 + cc] + R[r * 3 + 2] * Rl[2 * 3 + cc];
 #pragma unroll
   for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+}
+DDPB_HD void joint_advance(const ModelDev& m, int i, double q, double* R, double* p) {
+  double Rl[9];
+  joint_local_rot(m, i, q, Rl);
+  joint_compose(m, i, Rl, R, p);
 }
 // joint axis S = [w ; p x w] and rigid-body inertia Y of body i in world coordinates about the world origin.
 // With h_p = R h_i (first moment about the joint origin), g = h_p + (m/2) p:
@@ -261,20 +269,50 @@ DDPB_HD void ia_add_body(double* IA, const double* Y) {
 }
 
 // ---- q_task ------------------------------------------------------------------------------------
-// everything that depends on q only: world-frame joint axes and body inertias, articulated inertias IA_i, U_i, 1/D_i
-template <int NJ> DDPB_HD void q_task(const ModelDev& m, const double* q, double* rec) {
+// everything that depends on q only: world-frame joint axes and body inertias, articulated inertias IA_i, U_i, 1/D_i.
+// The linearization kernel runs it as four sub-phases so that only the inherently serial parts are narrow:
+//   joint_local_rot  per (configuration, joint)   -> Rl_i            (parallel; scratch in the IA block of the record)
+//   q_chain          per configuration            -> R_i, p_i        (serial over joints, 2 small products per joint)
+//   body_world       per (configuration, body)    -> S_i, Y_i        (parallel)
+//   q_articulate     per configuration            -> IA_i, U_i, 1/D_i (serial, leaf to root)
+// q_task is the same arithmetic in one call (rollouts of small models, tests).
+template <int NJ> struct QScratch {  // scratch inside the IA block (21 * NJ doubles) until q_articulate overwrites it
+  static constexpr int RL = 0;            // [NJ][9]
+  static constexpr int RP = 9 * NJ;       // [NJ][12]: R_i (9) | p_i (3)
+  static_assert(9 * NJ + 12 * NJ <= 21 * NJ, "scratch must fit the IA block");
+};
+template <int NJ> DDPB_HD void q_chain(const ModelDev& m, double* rec) {
   using Q = QRec<NJ>;
+  using X = QScratch<NJ>;
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    joint_advance(m, i, q[i], R, p);
-    double S[6], Y[10];
-    body_world(m, i, R, p, S, Y);
+    double Rl[9];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) rec[Q::S + 6 * i + k] = S[k];
+    for (int k = 0; k < 9; ++k) Rl[k] = rec[Q::IA + X::RL + 9 * i + k];
+    joint_compose(m, i, Rl, R, p);
 #pragma unroll
-    for (int k = 0; k < 10; ++k) rec[Q::Y + 10 * i + k] = Y[k];
+    for (int k = 0; k < 9; ++k) rec[Q::IA + X::RP + 12 * i + k] = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rec[Q::IA + X::RP + 12 * i + 9 + k] = p[k];
   }
+}
+template <int NJ> DDPB_HD void q_body(const ModelDev& m, int i, double* rec) {
+  using Q = QRec<NJ>;
+  using X = QScratch<NJ>;
+  double R[9], p[3], S[6], Y[10];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = rec[Q::IA + X::RP + 12 * i + k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = rec[Q::IA + X::RP + 12 * i + 9 + k];
+  body_world(m, i, R, p, S, Y);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) rec[Q::S + 6 * i + k] = S[k];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) rec[Q::Y + 10 * i + k] = Y[k];
+}
+template <int NJ> DDPB_HD void q_articulate(double* rec) {
+  using Q = QRec<NJ>;
   double IA[21];
 #pragma unroll
   for (int k = 0; k < 21; ++k) IA[k] = 0.0;
@@ -303,6 +341,21 @@ template <int NJ> DDPB_HD void q_task(const ModelDev& m, const double* q, double
       }
     }
   }
+}
+template <int NJ> DDPB_HD void q_task(const ModelDev& m, const double* q, double* rec) {
+  using Q = QRec<NJ>;
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    joint_advance(m, i, q[i], R, p);
+    double S[6], Y[10];
+    body_world(m, i, R, p, S, Y);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rec[Q::S + 6 * i + k] = S[k];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) rec[Q::Y + 10 * i + k] = Y[k];
+  }
+  q_articulate<NJ>(rec);
 }
 
 // ---- v_task --------------------------------------------------------------------------------------
@@ -380,6 +433,100 @@ template <int NJ, bool REC> DDPB_HD void v_task(const ModelDev& m, const double*
 #pragma unroll
       for (int k = 0; k < 6; ++k) { F[k] += Ya[k] + vh[k]; vrec[V::F + 6 * i + k] = F[k]; }
     }
+  }
+}
+
+// ---- v_task<NJ, true> as sub-phases (same arithmetic; only the sweeps that couple bodies are serial) ------------------
+//   v_prefix  per point         : body velocities v_i = sum_{l <= i} S_l qd_l
+//   v_bias    per (point, body) : c_i = v_i x (S_i qd_i), h_i = Y_i v_i, p_i = v_i x* h_i   (into the A, H, F slots)
+//   v_sweeps  per point         : leaf-to-root bias-force sweep and root-to-leaf acceleration sweep -> qdd, a_i
+//   v_force   per (point, body) : f_i = Y_i a_i + v_i x* h_i                                 (into the F slot)
+//   v_suffix  per point         : F_i = sum_{k >= i} f_k
+template <int NJ> DDPB_HD void v_prefix(const double* qrec, const double* qd, double* vrec) {
+  using Q = QRec<NJ>;
+  using V = VRec<NJ>;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const double* S = qrec + Q::S + 6 * i;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double sq = S[k] * qd[i]; v[k] += sq; vrec[V::V + 6 * i + k] = v[k]; }
+  }
+}
+template <int NJ> DDPB_HD void v_bias(const double* qrec, int i, double qdi, double* vrec) {
+  using Q = QRec<NJ>;
+  using V = VRec<NJ>;
+  const double* S = qrec + Q::S + 6 * i;
+  double v[6], sq[6], c[6], h[6], pa[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { v[k] = vrec[V::V + 6 * i + k]; sq[k] = S[k] * qdi; }
+  crm(v, sq, c);
+  y_mul(qrec + Q::Y + 10 * i, v, h);
+  crf(v, h, pa);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { vrec[V::H + 6 * i + k] = h[k]; vrec[V::A + 6 * i + k] = c[k]; vrec[V::F + 6 * i + k] = pa[k]; }
+  if (i > 0) {
+    // the part of the leaf-to-root sweep that does not depend on the recursion: IA_i c_i and U_i . c_i, parked in the
+    // DQ block (7 doubles per body) until the derivative columns overwrite it
+    double Iac[6];
+    sym6_mul(qrec + Q::IA + 21 * i, c, Iac);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) vrec[V::DQ + 7 * i + k] = Iac[k];
+    vrec[V::DQ + 7 * i + 6] = dot6(qrec + Q::U + 6 * i, c);
+  }
+}
+template <int NJ> DDPB_HD void v_sweeps(const ModelDev& m, const double* qrec, const double* tau, double* qdd_out, double* vrec) {
+  using Q = QRec<NJ>;
+  using V = VRec<NJ>;
+  double u[NJ];
+#pragma unroll
+  for (int i = NJ - 1; i >= 0; --i) {
+    const double* S = qrec + Q::S + 6 * i;
+    double pa[6], c[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { pa[k] = vrec[V::F + 6 * i + k]; c[k] = vrec[V::A + 6 * i + k]; }
+    u[i] = tau[i] - dot6(S, pa);
+    if (i > 0) {
+      const double* U = qrec + Q::U + 6 * i;
+      const double t = qrec[Q::DINV + i] * (u[i] - vrec[V::DQ + 7 * i + 6]);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double add = pa[k] + vrec[V::DQ + 7 * i + k] + U[k] * t;
+        vrec[V::F + 6 * (i - 1) + k] += add;
+      }
+    }
+  }
+  double a[6] = {0.0, 0.0, 0.0, -m.grav[0], -m.grav[1], -m.grav[2]};
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    const double* S = qrec + Q::S + 6 * i;
+    const double* U = qrec + Q::U + 6 * i;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] += vrec[V::A + 6 * i + k];
+    const double qdd = qrec[Q::DINV + i] * (u[i] - dot6(U, a));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { a[k] += S[k] * qdd; vrec[V::A + 6 * i + k] = a[k]; }
+    qdd_out[i] = qdd;
+  }
+}
+template <int NJ> DDPB_HD void v_force(const double* qrec, int i, double* vrec) {
+  using Q = QRec<NJ>;
+  using V = VRec<NJ>;
+  double ak[6], vk[6], hk[6], Ya[6], vh[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { ak[k] = vrec[V::A + 6 * i + k]; vk[k] = vrec[V::V + 6 * i + k]; hk[k] = vrec[V::H + 6 * i + k]; }
+  y_mul(qrec + Q::Y + 10 * i, ak, Ya);
+  crf(vk, hk, vh);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) vrec[V::F + 6 * i + k] = Ya[k] + vh[k];
+}
+template <int NJ> DDPB_HD void v_suffix(double* vrec) {
+  using V = VRec<NJ>;
+  double F[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = NJ - 1; i >= 0; --i) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { F[k] += vrec[V::F + 6 * i + k]; vrec[V::F + 6 * i + k] = F[k]; }
   }
 }
 
