@@ -324,7 +324,7 @@ def main():
                        "hess_mode": "fd_of_jacobians" if w.hess_mode == 0 else "fd_of_values", "mu": w.mu,
                        "l2": "working set (derivative slabs %.2f GB per GPU) is larger than L2" % (lin_b * B * T / 1e9),
                        "parallelism": f"dp{world} (independent problem shards, NCCL gathers per-problem scalars only)"},
-            "e2e": {"value": e2e_val, "unit": "knots/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_val, "unit": "knots/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": e2e_ms / args.steps, "timer": "wall clock between synchronisations"},
             "gpu_launches": int(launches),
             "clocks": clocks,

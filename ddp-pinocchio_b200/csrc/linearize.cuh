@@ -138,16 +138,19 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       for (int k = 0; k < 9; ++k) dst[k] = Rl[k];
     }
     ex.sync();
+    DDPB_PHASE_MARK(bd, 8, pc_);
     for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
       const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
       q_chain<NJ>(m, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
     }
     ex.sync();
+    DDPB_PHASE_MARK(bd, 9, pc_);
     for (int idx = tid; idx < nk * pl.NQ * NJ; idx += nthr) {
       const int kk = idx / (pl.NQ * NJ), r = idx - kk * (pl.NQ * NJ), s = r / NJ, jn = r - s * NJ;
       q_body<NJ>(m, jn, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
     }
     ex.sync();
+    DDPB_PHASE_MARK(bd, 10, pc_);
     for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
       const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
       q_articulate<NJ>(SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
@@ -178,6 +181,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       v_prefix<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, qd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
     }
     ex.sync();
+    DDPB_PHASE_MARK(bd, 11, pc_);
     for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
       const int kk = idx / (pl.NT * NJ), r = idx - kk * (pl.NT * NJ), p = r / NJ, jn = r - p * NJ;
       int i, j;
@@ -186,6 +190,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       v_bias<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, jn, qdj, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
     }
     ex.sync();
+    DDPB_PHASE_MARK(bd, 12, pc_);
   }
   for (int idx = tid; idx < nk * pl.P; idx += nthr) {
     const int kk = idx / pl.P, p = idx - kk * pl.P;
@@ -209,11 +214,13 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   }
   if (SPLIT) {
     ex.sync();
+    DDPB_PHASE_MARK(bd, 13, pc_);
     for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
       const int kk = idx / (pl.NT * NJ), r = idx - kk * (pl.NT * NJ), p = r / NJ, jn = r - p * NJ;
       v_force<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, jn, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
     }
     ex.sync();
+    DDPB_PHASE_MARK(bd, 14, pc_);
     for (int idx = tid; idx < nk * pl.NT; idx += nthr) {
       const int kk = idx / pl.NT, p = idx - kk * pl.NT;
       v_suffix<NJ>(SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);

@@ -16,7 +16,8 @@ for name in sys.argv[1:] or ["c3"]:
     bt.compute_derivatives()
     capi.lib().ddpb_debug_phase_cycles(bt._h, 1, out)
     v = np.array(list(out), dtype=float)
-    names = ["stage", "q_task", "v_task", "columns", "products", "eq_values", "eq_jac", "assemble"]
-    tot = v[:8].sum()
-    print(w.name, " ".join(f"{n}={100*x/tot:.1f}%" for n, x in zip(names, v[:8])), f"| cycles/CTA {tot / (w.B * w.T / max(1, int(os.environ.get('DDPB_LIN_KPB', '1')))):.0f}")
+    names = ["stage", "q_task(last sub-phase)", "v_task(last sub-phase)", "columns", "products", "eq_values", "eq_jac", "assemble",
+             "q:local_rot", "q:chain", "q:body", "v:prefix", "v:bias", "v:sweeps", "v:force"]
+    tot = v[:15].sum()
+    print(w.name, " ".join(f"{n}={100*x/tot:.1f}%" for n, x in zip(names, v[:15])), f"| cycles/CTA {tot / (w.B * w.T / max(1, int(os.environ.get('DDPB_LIN_KPB', '1')))):.0f}")
     bt.close()
