@@ -109,3 +109,47 @@ def test_full_size_properties_c3():
     assert np.isfinite(xs2[sc["status"] == 0]).all() and (sc["iterations"][sc["status"] == 0] == 3).all()
     assert (sc["status"] == 2).sum() <= w.B // 50
     bt.close()
+
+
+@pytest.mark.parametrize("name,B,T", [("c2", 200, 30), ("c3", 160, 12)])
+def test_solve_does_not_depend_on_subbatches(name, B, T):
+    """ddpb_set_subbatches only changes how the batch is scheduled (streams); problems are independent, so every
+    trajectory, scalar and counter is bit-identical for 1, 2 and 5 sub-batches (ragged last sub-batch included)."""
+    w = pc.S.workload(name, B=B, T=T)
+    g = w.generate()
+    ref = None
+    for nsub in (1, 2, 5):
+        bt = make(w)
+        bt.set_subbatches(nsub)
+        bt.set_targets(g["targets"]); bt.make_trajectory(g["x0"], g["us"]); bt.set_multipliers(None, g["mult_jac"])
+        sc = bt.solve(4, w.mu)
+        xs, us = bt.get_trajectory()
+        bt.close()
+        cur = (xs, us, sc["mu"], sc["reg"], sc["rollouts"], sc["restarts"], sc["merit"])
+        if ref is None:
+            ref = cur
+        else:
+            for a, b in zip(ref, cur):
+                assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_full_size_roundtrip_properties_c2():
+    """BASELINE.json configs[1] at full size (4096 x 200, 2R chain): size-independent properties -- the derivative
+    record's f(x_t,u_t) equals the rollout bit for bit, rows k < n of f_xx and all of f_uu are exact zeros, a solve keeps
+    every non-diverged trajectory finite and counts exactly the requested iterations."""
+    w = pc.S.workload("c2")
+    g = w.generate()
+    bt = make(w)
+    bt.set_targets(g["targets"]); bt.make_trajectory(g["x0"], g["us"]); bt.set_multipliers(None, g["mult_jac"])
+    xs, us = bt.get_trajectory()
+    bt.compute_derivatives()
+    D = bt.get_derivatives(["f_val", "fxx", "fuu"])
+    n, nd = w.n, w.ndx
+    assert np.array_equal(D["f_val"].reshape(w.B, w.T, w.nx), xs[:, 1:, :])
+    fxx = D["fxx"].reshape(w.B, w.T, nd, nd, nd)
+    assert not fxx[..., :n].any() and fxx[..., n:].any() and not D["fuu"].any()
+    sc = bt.solve(2, w.mu)
+    xs2, _ = bt.get_trajectory()
+    ok = sc["status"] == 0
+    assert np.isfinite(xs2[ok]).all() and (sc["iterations"][ok] == 2).all() and (sc["status"] == 2).sum() <= w.B // 50
+    bt.close()
