@@ -9,8 +9,11 @@
 //
 // The recursion is a latency chain (T dependent knots) fed by 8 * rec_size bytes per knot, so the design keeps the
 // dependent path of one knot short and the memory system busy ahead of it:
-//   * the record of knot t-1 is pulled into L2 with one bulk prefetch (cp.async.bulk.prefetch.L2) while knot t is
-//     being processed, so the loads at the start of a knot are L2 hits;
+//   * while knot t is being processed, the head of the record of knot t-1 goes into the idle head buffer and round 0
+//     of every warp's tensor share into its staging buffer with cp.async (no registers held), so a knot starts with
+//     its first operands already in shared memory; later rounds are loaded one round ahead.  (A bulk L2 prefetch of
+//     the record after next was measured to re-fetch ~50 % of the bytes from DRAM without shortening the pass and
+//     was removed: DRAM reads now equal the algorithmic bytes.)
 //   * the third-order tensors are used once: every warp streams its share with fully coalesced 16-byte loads through
 //     a small warp-private staging buffer and contracts the k-run of one output element per lane with V_x;
 //   * every matrix product is a list of inner products over CONTIGUOUS shared-memory runs (V_xx is kept row-major,
@@ -83,15 +86,6 @@ DDPB_HD void cp_async16(void* smem_dst, const void* gmem_src) {
 DDPB_HD void cp_async_wait_all() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-#endif
-}
-
-// one bulk request that pulls `bytes` (multiple of 16) starting at the 16-byte aligned `p` into L2
-DDPB_HD void l2_prefetch_bulk(const void* p, unsigned bytes) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-#else
-  (void)p; (void)bytes;
 #endif
 }
 
@@ -258,11 +252,6 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       const int ne = bd.ne[t], eo = bd.eq_off[t];
       const RecLayout L = rec_layout(nd, nu, nx, ne);
       const double* rec = slab_rec(bd, t, b, L.size);
-      if (tid == 0 && t > 1) {
-        // the record after next -> L2 (one bulk request), so that the prefetch issued at the next knot hits L2
-        const int sz = rec_layout(nd, nu, nx, bd.ne[t - 2]).size;
-        l2_prefetch_bulk(slab_rec(bd, t - 2, b, sz), (unsigned)(sz * sizeof(double)));
-      }
       // ---- phase A: head of the record (prefetched) ; tensors -> V_x contraction ----------------------------------------
       const double* hd = sm + (hcur ? S::head2 : S::head);
       double xorg = 0.0;

@@ -226,11 +226,18 @@ static int launch_backward(const LaunchCtx& c) {
   DISPATCH(h->nj, L::backward(c.bd, h->bwd_threads, h->bwd_smem, c.s));
   return check_launch(h, "backward");
 }
-static int launch_forward(const LaunchCtx& c) {
+static int launch_cost_old(const LaunchCtx& c) {
   ddpb_batch* h = c.h;
   PhaseScope ps(h, 2, c.s);
+  DISPATCH(h->mt, L::cost_old(h->model, c.bd, h->costs_old, c.s));
+  return check_launch(h, "cost_old");
+}
+// with_cost_old = false: cost_seq_aug of the current trajectory was already launched (on another stream) and joined
+static int launch_forward(const LaunchCtx& c, bool with_cost_old = true) {
+  ddpb_batch* h = c.h;
+  if (with_cost_old) { int rc = launch_cost_old(c); if (rc) return rc; }
+  PhaseScope ps(h, 2, c.s);
   DISPATCH(h->mt, L::forward(h->model, c.bd, h->costs_old, h->ls_xs, h->ls_us, c.s));
-  h->launches += 1;  // cost_seq_aug of the current trajectory + the concurrent line search
   return check_launch(h, "forward");
 }
 static int launch_al_update(const LaunchCtx& c, double thr) {

@@ -159,8 +159,10 @@ template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t s
   (void)bd; (void)threads; (void)smem; (void)s;
 #endif
 }
-template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, cudaStream_t s) {
+template <> void Launch<KNJ>::cost_old(const ModelDev& m, const BatchDev& bd, double* costs_old, cudaStream_t s) {
   cost_old_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd, costs_old);
+}
+template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, cudaStream_t s) {
   forward_kernel<KNJ><<<(bd.nb + 31) / 32, 32 * LS_NC, scr_bytes(32 * LS_NC), s>>>(m, bd, costs_old, xs_c, us_c);
 }
 template <> int Launch<KNJ>::linesearch_slots() { return LS_NC; }

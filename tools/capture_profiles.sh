@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round-end evidence (run under gpurun): ncu --set full of the main launch of every hot kernel for C2 and C3 with the
+# solver on one stream, the launch list of the bench command, bench lines.  Outputs under gpurun_out/.
+set -x
+O=gpurun_out
+for w in c2:4096 c3:1024; do n=${w%:*}; b=${w#*:}
+  for k in linearize_kernel backward_kernel forward_kernel; do
+    skip=4; [ $k = linearize_kernel ] && skip=12
+    DDPB_SUBBATCHES=1 ncu --set full --import-source on --clock-control none --kernel-name regex:^$k --launch-skip $skip --launch-count 1 \
+      -o $O/full_${n}_$k -f python tools/bwd_scan.py $n $b > $O/full_${n}_$k.log 2>&1
+  done
+done
+M="smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum"
+for w in c2:4096 c3:1024 c5:1024; do n=${w%:*}; b=${w#*:}
+  DDPB_SUBBATCHES=1 ncu --metrics $M --clock-control none --kernel-name regex:'^(linearize_kernel|backward_kernel|forward_kernel|cost_old_kernel)' --launch-skip 12 --launch-count 6 --csv \
+    --log-file $O/metrics_$n.csv python tools/bwd_scan.py $n $b > /dev/null 2>&1
+done
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/b.log 2>&1 && \
+DDPB_SUBBATCHES=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/launches_bench_c2_onestream.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/launches_bench_c2_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench4.log 2>&1
+echo capture done
