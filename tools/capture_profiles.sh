@@ -19,3 +19,9 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/b.log 2>&1 && \
 DDPB_SUBBATCHES=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/launches_bench_c2_onestream.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench1.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/launches_bench_c2_default.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench4.log 2>&1
 echo capture done
+python bench.py > $O/bench_c2.json 2> $O/bench_c2.err
+python bench.py --workload c3 --steps 10 > $O/bench_c3.json 2> $O/bench_c3.err
+python bench.py --workload c5 --steps 3 > $O/bench_c5.json 2> $O/bench_c5.err
+python bench.py --workload c4 --steps 5 > $O/bench_c4.json 2> $O/bench_c4.err
+python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_c2.json 2> $O/bench_ref_c2.err
+echo benches done
