@@ -31,7 +31,10 @@ template <int NJ> struct LinPlan {
   int ne;               // equality rows at this knot
   bool u_points;        // whether the u-perturbed evaluation points exist
   // shared-memory offsets (doubles)
-  int o_base, o_tgt, o_qrec, o_vrec, o_fval, o_eqv, o_J, o_eqxu, total;
+  int o_base, o_tgt, o_qrec, o_vrec, o_fval, o_eqv, o_J, o_eqxu, o_cterm, o_dg, o_minv0, total;
+  // stride of the q-records: the value-based mode needs M^-1 of the base configuration only, so its records end before
+  // the MINV block and the one M^-1 lives in its own slot
+  DDPB_HD static int qstride(int mode) { return mode == HESS_FD_VALUES ? (QRec<NJ>::MINV | 1) : QRec<NJ>::SIZE; }
   DDPB_HD static int points(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + N : 1 + N + N * (N - 1) / 2; }
   DDPB_HD static int qsets(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + NJ : 1 + NJ + NJ * (NJ - 1) / 2; }
   // FD-of-Jacobians mode: the reference evaluates (f_x, f_u) at the u-perturbed points only to difference f_u
@@ -47,12 +50,16 @@ template <int NJ> struct LinPlan {
     int o = 0;
     o_base = o; o += 4 * NJ;
     o_tgt = o; o += (ne_max + 1) & ~1;
-    o_qrec = o; o += NQ * QRec<NJ>::SIZE;
+    o_qrec = o; o += NQ * qstride(mode);
     o_vrec = o; o += NT * VRec<NJ>::SIZE;
     o_fval = o; o += P * 2 * NJ;
     o_eqv = o; o += P * ne_max;
     o_J = o; o += NT * 3 * NJ;
     o_eqxu = o; o += NT * ne_max * N;
+    // value-based mode only: per-body column terms of the base point, diagonal second differences of f and eq
+    o_cterm = o; o += mode == HESS_FD_VALUES ? 2 * NJ * NJ * 6 : 0;
+    o_dg = o; o += mode == HESS_FD_VALUES ? 2 * N * (2 * NJ + ne_max) : 0;  // second differences | Jacobian entries
+    o_minv0 = o; o += mode == HESS_FD_VALUES ? NJ * NJ : 0;
     total = o;
   }
   // which tangent index/indices a point perturbs (-1 = none)
@@ -95,6 +102,11 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   const double dt = bd.dt;
   const int tid = ex.tid(), nthr = ex.nthr();
   const size_t KS = (size_t)pl.total;  // shared-memory stride between the knots of this CTA
+  constexpr int QS = MODE == HESS_FD_VALUES ? (Q::MINV | 1) : Q::SIZE;  // stride between q-records (LinPlan::qstride)
+  // M^-1 of q-set s of knot kk (value-based mode: the base configuration's only)
+  auto minv_of = [&](int kk, int s) -> double* {
+    return MODE == HESS_FD_VALUES ? sm_all + (size_t)kk * KS + pl.o_minv0 : sm_all + (size_t)kk * KS + pl.o_qrec + (size_t)s * QS + Q::MINV;
+  };
 #define SM(kk, off) (sm_all + (size_t)(kk) * KS + (off))
 
   DDPB_PHASE_START(bd, pc_);
@@ -120,7 +132,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       double q[NJ];
 #pragma unroll
       for (int k = 0; k < NJ; ++k) q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
-      q_task<NJ>(m, q, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+      q_task<NJ>(m, q, SM(kk, pl.o_qrec) + (size_t)s * QS);
     }
   } else {
     // phase 1: q-only data for every distinct configuration, as four sub-phases (rbd.cuh "q_task"): the local joint
@@ -133,7 +145,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const double qj = SM(kk, pl.o_base)[jn] + ((jn == i || jn == j) ? eps : 0.0);
       double Rl[9];
       joint_local_rot(m, jn, qj, Rl);
-      double* dst = SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE + Q::IA + QScratch<NJ>::RL + 9 * jn;
+      double* dst = SM(kk, pl.o_qrec) + (size_t)s * QS + Q::IA + QScratch<NJ>::RL + 9 * jn;
   #pragma unroll
       for (int k = 0; k < 9; ++k) dst[k] = Rl[k];
     }
@@ -141,19 +153,19 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     DDPB_PHASE_MARK(bd, 8, pc_);
     for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
       const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
-      q_chain<NJ>(m, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+      q_chain<NJ>(m, SM(kk, pl.o_qrec) + (size_t)s * QS);
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 9, pc_);
     for (int idx = tid; idx < nk * pl.NQ * NJ; idx += nthr) {
       const int kk = idx / (pl.NQ * NJ), r = idx - kk * (pl.NQ * NJ), s = r / NJ, jn = r - s * NJ;
-      q_body<NJ>(m, jn, SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+      q_body<NJ>(m, jn, SM(kk, pl.o_qrec) + (size_t)s * QS);
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 10, pc_);
     for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
       const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
-      q_articulate<NJ>(SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE);
+      q_articulate<NJ>(SM(kk, pl.o_qrec) + (size_t)s * QS);
     }
   }
   ex.sync();
@@ -178,7 +190,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const int kk = idx / pl.NT, p = idx - kk * pl.NT;
       double q[NJ], qd[NJ], tau[NJ];
       point_state(kk, p, q, qd, tau);
-      v_prefix<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, qd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      v_prefix<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS, qd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 11, pc_);
@@ -187,7 +199,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       int i, j;
       pl.point_pert(p, &i, &j);
       const double qdj = SM(kk, pl.o_base)[n + jn] + ((n + jn == i || n + jn == j) ? eps : 0.0);
-      v_bias<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, jn, qdj, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      v_bias<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS, jn, qdj, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 12, pc_);
@@ -197,7 +209,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     double* fval = SM(kk, pl.o_fval);
     double q[NJ], qd[NJ], tau[NJ], qdd[NJ];
     point_state(kk, p, q, qd, tau);
-    const double* qr = SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE;
+    const double* qr = SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS;
     if (p < pl.NT) {
       if (SPLIT) v_sweeps<NJ>(m, qr, tau, qdd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
       else v_task<NJ, true>(m, qr, qd, tau, qdd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
@@ -217,7 +229,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     DDPB_PHASE_MARK(bd, 13, pc_);
     for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
       const int kk = idx / (pl.NT * NJ), r = idx - kk * (pl.NT * NJ), p = r / NJ, jn = r - p * NJ;
-      v_force<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, jn, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      v_force<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS, jn, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 14, pc_);
@@ -230,7 +242,42 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   DDPB_PHASE_MARK(bd, 2, pc_);
 
   // phase 3: tangent columns of inverse dynamics and columns of M^-1
-  {
+  if (MODE == HESS_FD_VALUES) {
+    // only the base point needs columns: too few tasks to fill even one warp, so every column is split by body
+    // (col_term, NJ * NJ slots per derivative kind of which k >= j are used) and reduced afterwards (col_reduce)
+    for (int idx = tid; idx < nk * (2 * NJ * NJ + NJ); idx += nthr) {
+      const int kk = idx / (2 * NJ * NJ + NJ), r = idx - kk * (2 * NJ * NJ + NJ);
+      double* qr = SM(kk, pl.o_qrec);
+      if (r < 2 * NJ * NJ) {
+        const int wrt = r / (NJ * NJ), r2 = r - wrt * NJ * NJ, j = r2 / NJ, k = r2 - j * NJ;
+        if (k >= j) {
+          double g[6];
+          col_term<NJ>(qr, SM(kk, pl.o_vrec), j, k, wrt, g);
+          double* dst = SM(kk, pl.o_cterm) + (size_t)(wrt * NJ + j) * NJ * 6 + 6 * k;
+#pragma unroll
+          for (int e = 0; e < 6; ++e) dst[e] = g[e];
+        }
+      } else {
+        const int c = r - 2 * NJ * NJ;
+        double col[NJ];
+        minv_col<NJ>(qr, c, col);
+        double* mi = minv_of(kk, 0);
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) mi[c * NJ + k] = col[k];
+      }
+    }
+    ex.sync();
+    for (int idx = tid; idx < nk * 2 * NJ; idx += nthr) {
+      const int kk = idx / (2 * NJ), r = idx - kk * 2 * NJ, wrt = r / NJ, j = r - wrt * NJ;
+      double col[NJ];
+      double* vr = SM(kk, pl.o_vrec);
+      col_reduce<NJ>(SM(kk, pl.o_qrec), vr, SM(kk, pl.o_cterm) + (size_t)(wrt * NJ + j) * NJ * 6, j, wrt, col);
+      double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) dst[k] = col[k];
+    }
+  } else {
+
     const int n_tan = pl.NT * 2 * NJ;
     const int n_minv = (MODE == HESS_FD_JACOBIANS ? pl.NQ : 1) * NJ;
     // tangent tasks of all knots first (j-major inside a knot), then the M^-1 tasks
@@ -242,7 +289,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const int kk = rem / (2 * pl.NT), rem2 = rem - kk * 2 * pl.NT;
         const int wrt = rem2 / pl.NT, p = rem2 - wrt * pl.NT;
         double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
-        col_task<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE, vr, j, wrt, col);
+        col_task<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS, vr, j, wrt, col);
         double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
 #pragma unroll
         for (int k = 0; k < NJ; ++k) dst[k] = col[k];
@@ -250,7 +297,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const int r = idx - nk * n_tan;
         const int kk = r / n_minv, r2 = r - kk * n_minv;
         const int c = r2 % NJ, s = r2 / NJ;
-        double* qr = SM(kk, pl.o_qrec) + (size_t)s * Q::SIZE;
+        double* qr = SM(kk, pl.o_qrec) + (size_t)s * QS;
         minv_col<NJ>(qr, c, col);
 #pragma unroll
         for (int k = 0; k < NJ; ++k) qr[Q::MINV + c * NJ + k] = col[k];
@@ -268,7 +315,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     const int wrt = rem / NJ, c = rem - wrt * NJ;
     double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
     double* colp = vr + (wrt ? V::DV : V::DQ) + c * NJ;
-    const double* Mi = SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * Q::SIZE + Q::MINV;
+    const double* Mi = minv_of(kk, pl.point_qset(p));
     double src[NJ], dst[NJ];
 #pragma unroll
     for (int k = 0; k < NJ; ++k) src[k] = colp[k];
@@ -294,7 +341,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   };
   auto fu_at = [&](int kk, int p, int r, int c) -> double {
     if (r < n) return 0.0;
-    return SM(kk, pl.o_qrec)[(size_t)pl.point_qset(p) * Q::SIZE + Q::MINV + c * NJ + (r - n)] * dt;
+    return minv_of(kk, pl.point_qset(p))[c * NJ + (r - n)] * dt;
   };
 
   // phase 5: the doubly advanced equality constraint at every point (empty loops when the knot has no rows)
@@ -392,7 +439,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const double* qr = SM(kk, pl.o_qrec) + Q::MINV + j * NJ + (k - n);
         const double base = qr[0] * dt;
 #pragma unroll
-        for (int i = 0; i < n; ++i) dst[(size_t)i * nd * nu] = (qr[(size_t)(1 + i) * Q::SIZE] * dt - base) * inv_eps;
+        for (int i = 0; i < n; ++i) dst[(size_t)i * nd * nu] = (qr[(size_t)(1 + i) * QS] * dt - base) * inv_eps;
 #pragma unroll
         for (int i = n; i < nd; ++i) dst[(size_t)i * nd * nu] = 0.0;
       } else {
@@ -435,31 +482,65 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       df *= 2.0;
       return 0.5 * (df * inv_eps2 - d1 - d2);
     };
-    auto hess = [&](int kk, int which, int k, int ga, int gb) -> double {
-      const double* fval = SM(kk, pl.o_fval);
-      const double* eqv = SM(kk, pl.o_eqv);
-      const double* eqxu = SM(kk, pl.o_eqxu);
-      auto jcol = [&](int g) -> double {
-        if (which == 0) return g < nd ? fx_at(kk, 0, k, g) : fu_at(kk, 0, k, g - nd);
-        return eqxu[g * ne + k];
-      };
-      auto val = [&](int p) -> double { return which == 0 ? fval[p * nx + k] : eqv[p * ne_sm + k]; };
-      const double f0 = val(0);
-      if (ga == gb) return diag(val(1 + ga), f0, jcol(ga));
-      const int i = ga < gb ? ga : gb, j = ga < gb ? gb : ga;
-      const double ci = jcol(i), cj = jcol(j);
-      const double di = diag(val(1 + i), f0, ci), dj = diag(val(1 + j), f0, cj);
-      return offd(val(1 + N + pair_rank(i, j, N)), f0, ci, cj, di, dj);
+    // Jacobian entry (row k of function `which`, tangent index g) and function value at point p
+    auto jcol = [&](int kk, int which, int k, int g) -> double {
+      if (which == 0) return g < nd ? fx_at(kk, 0, k, g) : fu_at(kk, 0, k, g - nd);
+      return SM(kk, pl.o_eqxu)[g * ne + k];
     };
-    FOR_BLOCK(kk, e, nd * nd * nd) { const int k = e % nd, j = (e / nd) % nd, i = e / (nd * nd); REC(kk, L.fxx + e) = hess(kk, 0, k, j, i); }
-    FOR_BLOCK(kk, e, nd * nu * nd) { const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu); REC(kk, L.fux + e) = hess(kk, 0, k, nd + j, i); }
-    FOR_BLOCK(kk, e, nd * nu * nu) { const int k = e % nd, j = (e / nd) % nu, i = e / (nd * nu); REC(kk, L.fuu + e) = hess(kk, 0, k, nd + j, nd + i); }
+    auto val = [&](int kk, int which, int k, int p) -> double {
+      return which == 0 ? SM(kk, pl.o_fval)[p * nx + k] : SM(kk, pl.o_eqv)[p * ne_sm + k];
+    };
+    // Two tables per knot, indexed [tangent index g][row: f rows, then eq rows]: the Jacobian entries and the diagonal
+    // second differences (shared by every off-diagonal entry of their row / column, so computed once).  The tensors are
+    // then filled by two-level loops: a thread owns (row k, left index a) and walks the right index b -- three
+    // shared-memory loads and a handful of flops per entry, consecutive threads writing consecutive doubles.
+    const int dgs = nd + ne_sm;  // stride of the tables per tangent index
+    for (int idx = tid; idx < nk * N * (nd + ne); idx += nthr) {
+      const int kk = idx / (N * (nd + ne)), r = idx - kk * (N * (nd + ne));
+      const int g = r / (nd + ne), k0 = r - g * (nd + ne);
+      const int which = k0 < nd ? 0 : 1, k = which ? k0 - nd : k0;
+      const double jc = jcol(kk, which, k, g);
+      SM(kk, pl.o_dg)[g * dgs + k0] = diag(val(kk, which, k, 1 + g), val(kk, which, k, 0), jc);
+      SM(kk, pl.o_dg)[(N + g) * dgs + k0] = jc;
+    }
+    ex.sync();
+    // block of a tensor: rows R (f: nd, eq: ne) of function `which`, left indices a0 .. a0+LA-1, right indices b0 .. b0+LB-1,
+    // element (k, a, b) at off + k + R * a + R * LA * b
+    auto fill = [&](int which, int off, int R, int a0, int LA, int b0, int LB) {
+      for (int idx = tid; idx < nk * R * LA; idx += nthr) {
+        const int kk = idx / (R * LA), r = idx - kk * (R * LA);
+        const int k = r % R, ga = a0 + r / R;
+        const int row = which ? nd + k : k;
+        const double* dg = SM(kk, pl.o_dg) + row;
+        const double* jc = dg + (size_t)N * dgs;
+        const double* vals = which == 0 ? SM(kk, pl.o_fval) + k : SM(kk, pl.o_eqv) + k;
+        const int vs = which == 0 ? nx : ne_sm;
+        const double f0 = vals[0], ca = jc[ga * dgs], da = dg[ga * dgs];
+        double* dst = &REC(kk, off + r);
+        for (int bl = 0; bl < LB; ++bl) {
+          const int gb = b0 + bl;
+          double v;
+          if (gb == ga) {
+            v = da;
+          } else {
+            const double cb = jc[gb * dgs], db = dg[gb * dgs];
+            const bool lo = gb < ga;  // the smaller tangent index is subtracted first (problem.hpp:226-296)
+            const int i = lo ? gb : ga, j = lo ? ga : gb;
+            v = offd(vals[(size_t)(1 + N + pair_rank(i, j, N)) * vs], f0, lo ? cb : ca, lo ? ca : cb, lo ? db : da, lo ? da : db);
+          }
+          dst[(size_t)bl * R * LA] = v;
+        }
+      }
+    };
+    fill(0, L.fxx, nd, 0, nd, 0, nd);
+    fill(0, L.fux, nd, nd, nu, 0, nd);
+    fill(0, L.fuu, nd, nd, nu, nd, nu);
     if (ne > 0) {
       FOR_BLOCK(kk, e, ne) REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e];
       FOR_BLOCK(kk, e, ne * N) REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e];
-      FOR_BLOCK(kk, e, ne * nd * nd) { const int k = e % ne, j = (e / ne) % nd, i = e / (ne * nd); REC(kk, L.eq_xx + e) = hess(kk, 1, k, j, i); }
-      FOR_BLOCK(kk, e, ne * nu * nd) { const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu); REC(kk, L.eq_ux + e) = hess(kk, 1, k, nd + j, i); }
-      FOR_BLOCK(kk, e, ne * nu * nu) { const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu); REC(kk, L.eq_uu + e) = hess(kk, 1, k, nd + j, nd + i); }
+      fill(1, L.eq_xx, ne, 0, nd, 0, nd);
+      fill(1, L.eq_ux, ne, nd, nu, 0, nd);
+      fill(1, L.eq_uu, ne, nd, nu, nd, nu);
     }
   }
 #undef FOR_BLOCK

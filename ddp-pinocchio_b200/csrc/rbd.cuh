@@ -667,6 +667,66 @@ template <int NJ> DDPB_HD void col_task(const double* qrec, const double* vrec, 
     if (i < j) out[i] = dot6(qrec + Q::S + 6 * i, G);
 }
 
+// col_task split by body for the narrow case (one point per knot needs columns, value-based Hessians): col_term is the
+// contribution g_k of one body to column (j, wrt), col_reduce the suffix sums and projections -- the same arithmetic
+// in the same order as col_task, with 2 * NJ(NJ+1)/2 terms in parallel instead of 2 * NJ columns.
+template <int NJ> DDPB_HD void col_term(const double* qrec, const double* vrec, int j, int k, int wrt_v, double* g /*[6]*/) {
+  using Q = QRec<NJ>;
+  using V = VRec<NJ>;
+  double Sj[6], vj[6], d[6], al[6], be[6];
+#pragma unroll
+  for (int e = 0; e < 6; ++e) { Sj[e] = qrec[Q::S + 6 * j + e]; vj[e] = vrec[V::V + 6 * j + e]; }
+  crm(vj, Sj, d);
+  if (!wrt_v) {
+    double aj[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) aj[e] = vrec[V::A + 6 * j + e];
+    crm(aj, Sj, al);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) be[e] = d[e];
+  } else {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { al[e] = d[e]; be[e] = Sj[e]; }
+  }
+  const double* Yk = qrec + Q::Y + 10 * k;
+  double vk[6], hk[6], dv[6], t[6], g1[6], g2[6], Yg[6], g3[6];
+#pragma unroll
+  for (int e = 0; e < 6; ++e) { vk[e] = vrec[V::V + 6 * k + e]; hk[e] = vrec[V::H + 6 * k + e]; dv[e] = vk[e] - vj[e]; }
+  crm(be, dv, t);
+#pragma unroll
+  for (int e = 0; e < 6; ++e) t[e] += al[e];
+  y_mul(Yk, t, g1);
+  crf(be, hk, g2);
+  y_mul(Yk, be, Yg);
+  crf(vk, Yg, g3);
+#pragma unroll
+  for (int e = 0; e < 6; ++e) g[e] = g1[e] + g2[e] + g3[e];
+}
+// terms: g_k of this column at terms[6 * k] for k >= j
+template <int NJ> DDPB_HD void col_reduce(const double* qrec, const double* vrec, const double* terms, int j, int wrt_v, double* out /*[NJ]*/) {
+  using Q = QRec<NJ>;
+  using V = VRec<NJ>;
+  double G[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = NJ - 1; k >= 0; --k) {
+    if (k < j) continue;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) G[e] += terms[6 * k + e];
+    out[k] = dot6(qrec + Q::S + 6 * k, G);
+  }
+  if (!wrt_v) {
+    double Sj[6], Fj[6], x[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { Sj[e] = qrec[Q::S + 6 * j + e]; Fj[e] = vrec[V::F + 6 * j + e]; }
+    crf(Sj, Fj, x);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) G[e] += x[e];
+  }
+#pragma unroll
+  for (int i = 0; i < NJ; ++i)
+    if (i < j) out[i] = dot6(qrec + Q::S + 6 * i, G);
+}
+
 // ---- minv_col ---------------------------------------------------------------------------------------
 // column `col` of M^-1(q): unit-torque articulated-body sweeps on the cached S, U, 1/D
 template <int NJ> DDPB_HD void minv_col(const double* qrec, int col, double* out /*[NJ]*/) {
