@@ -19,14 +19,15 @@ constexpr int KNJ = DDPB_NJ;
 // grid: (knots t0..t1-1) x (groups of `kpb` consecutive problems); all knots of a launch have the same ne
 // FD-of-Jacobians kernels are compiled for 512 resident threads per SM (128 registers): 4 CTAs of <= 128 threads for
 // small models, 2 CTAs of 256 threads (two knots each, so the narrow q / v phases serve two knots) from 5 joints on;
-// the value-based mode has 1 + n + n(n-1)/2 evaluation points per knot and runs two 256-thread CTAs per SM (its records
-// carry no per-configuration M^-1, which keeps 7 joints under half of the shared memory).
+// the value-based mode has 1 + n + n(n-1)/2 evaluation points per knot and runs one 256-thread CTA per SM: two would fit
+// the shared memory (its records carry no per-configuration M^-1) but at 128 registers the value-only ABA tasks spill
+// ~1.6 KB per thread and ncu shows 6x the algorithmic DRAM traffic for a 5 % gain (DDPB_LIN_LB_BLOCKS_FDV=2).
 #ifndef DDPB_LIN_LB_THREADS
 #define DDPB_LIN_LB_THREADS (DDPB_NJ >= 5 ? 256 : 128)
 #define DDPB_LIN_LB_BLOCKS (DDPB_NJ >= 5 ? 2 : 4)
 #endif
 #ifndef DDPB_LIN_LB_BLOCKS_FDV
-#define DDPB_LIN_LB_BLOCKS_FDV 2
+#define DDPB_LIN_LB_BLOCKS_FDV 1
 #endif
 template <int NJ, int MODE> __global__ void __launch_bounds__(MODE == HESS_FD_JACOBIANS ? DDPB_LIN_LB_THREADS : 256, MODE == HESS_FD_JACOBIANS ? DDPB_LIN_LB_BLOCKS : DDPB_LIN_LB_BLOCKS_FDV) linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
                                                                           int t0, int kpb, int ne_sm) {
