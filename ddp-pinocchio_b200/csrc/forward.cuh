@@ -1,7 +1,8 @@
 // forward.cuh -- closed-loop rollouts with backtracking line search on the augmented-Lagrangian merit,
 // plus the per-problem sequential sweeps of the outer loop (re-centering, optimality measures,
-// multiplier update).  One thread per problem; all per-knot vectors are SoA-by-batch so every access
-// of a warp is one coalesced span.
+// multiplier update).  One thread per problem (the device versions of the line search and of the sweeps, with their
+// own work split, are in outer_warp.cuh; the bodies here are also what tests/hostemu runs on the CPU); all per-knot
+// vectors are SoA-by-batch so every access of a warp is one coalesced span.
 //
 // Restates (all under /root/reference/include/ddp/):
 //   forward_pass                ddp_fwd.ipp:10-67

@@ -76,23 +76,6 @@ DDPB_HD void sym3v(const double* S, const double* v, double* o) {  // S = xx,xy,
   double z = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
   o[0] = x; o[1] = y; o[2] = z;
 }
-// motion transform parent -> child:  [E w ; E (v - r x w)]
-DDPB_HD void xf_motion(const double* E, const double* r, const double* m, double* o) {
-  double t[3], u[3];
-  cross3(r, m, t);
-  u[0] = m[3] - t[0]; u[1] = m[4] - t[1]; u[2] = m[5] - t[2];
-  m3v(E, m, o);
-  m3v(E, u, o + 3);
-}
-// force transform child -> parent (transpose):  [E^T n + r x E^T f ; E^T f], accumulated into o
-DDPB_HD void xf_force_T_add(const double* E, const double* r, const double* f, double* o) {
-  double n[3], l[3];
-  m3tv(E, f, n);
-  m3tv(E, f + 3, l);
-  cross3_add(r, l, n);
-  o[0] += n[0]; o[1] += n[1]; o[2] += n[2];
-  o[3] += l[0]; o[4] += l[1]; o[5] += l[2];
-}
 // motion cross a x b, force cross a x* f
 DDPB_HD void crm(const double* a, const double* b, double* o) {
   double t0[3], t1[3];
@@ -108,22 +91,6 @@ DDPB_HD void crf(const double* a, const double* f, double* o) {
   cross3(a, f + 3, t1);
   o[0] = t0[0]; o[1] = t0[1]; o[2] = t0[2]; o[3] = t1[0]; o[4] = t1[1]; o[5] = t1[2];
 }
-// motion cross with a pure-rotation second operand b = [ax*s; 0]
-DDPB_HD void crm_axis(const double* a, const double* ax, double s, double* o) {
-  double b[3] = {ax[0] * s, ax[1] * s, ax[2] * s};
-  cross3(a, b, o);
-  cross3(a + 3, b, o + 3);
-}
-// rigid-body spatial inertia times motion vector: [Io w + h x v ; m v - h x w]
-DDPB_HD void inertia_mul(const ModelDev& m, int i, const double* v, double* o) {
-  double a[3], l[3];
-  sym3v(m.Io[i], v, a);
-  cross3_add(m.h[i], v + 3, a);
-  cross3(m.h[i], v, l);
-  o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
-  o[3] = m.mass[i] * v[3] - l[0]; o[4] = m.mass[i] * v[4] - l[1]; o[5] = m.mass[i] * v[5] - l[2];
-}
-
 DDPB_HD void sincos_(double q, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
   sincos(q, s, c);
@@ -132,7 +99,8 @@ DDPB_HD void sincos_(double q, double* s, double* c) {
 #endif
 }
 
-// E_i(q) = (Rp_i * R_axis(q))^T, row-major
+// E_i(q) = (Rp_i * R_axis(q))^T, row-major (used by frame_task only: frame positions follow the body-frame recursion
+// of the reference's forward kinematics)
 DDPB_HD void joint_E(const ModelDev& m, int i, double q, double* E) {
   double s, c;
   sincos_(q, &s, &c);
