@@ -111,6 +111,10 @@ struct ddpb_model {
 };
 
 struct PhaseEv { cudaEvent_t a, b; int phase; };
+struct SolveGraph {
+  int iters, nsub; double thr, mu, reg, w, n; double* xs; cudaStream_t stream;
+  cudaGraphExec_t exec = nullptr; unsigned long long launches = 0;
+};
 
 struct ddpb_batch {
   ModelDev model;
@@ -143,6 +147,7 @@ struct ddpb_batch {
   std::vector<cudaStream_t> sub_streams_lo;  // low priority: linearization (throughput-bound, fills whatever is free)
   std::vector<cudaEvent_t> sub_done, sub_lin, sub_hi;
   cudaEvent_t fork_ev = nullptr;
+  std::vector<SolveGraph> graphs;  // captured solves (ddpb_solve_async)
   size_t bwd_smem = 0;
 };
 
@@ -413,6 +418,7 @@ void ddpb_batch_destroy(ddpb_batch* h) {
   if (h->stage) cudaFree(h->stage);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (auto& e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   for (auto st : h->sub_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (auto st : h->sub_streams_lo) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (auto ev : h->sub_done) cudaEventDestroy(ev);
@@ -773,9 +779,8 @@ int ddpb_measure_fp64_peak(int device, double* tflops) {
   return DDPB_OK;
 }
 
-int ddpb_solve_async(ddpb_batch* h, const ddpb_solver_params* p) {
-  ENTER(h);
-  if (!p || p->max_iterations < 0) return fail(DDPB_ERR_INVALID, "bad solver parameters");
+// enqueue the whole fixed-iteration solve on h->stream and the sub-batch streams (forked from / joined into h->stream)
+static int enqueue_solve(ddpb_batch* h, const ddpb_solver_params* p) {
   BatchDev& bd = h->bd;
   const size_t B = bd.B;
   int rc = DDPB_OK;
@@ -840,6 +845,54 @@ int ddpb_solve_async(ddpb_batch* h, const ddpb_solver_params* p) {
     }
   }
 #undef R
+  return DDPB_OK;
+}
+// The solve is a fixed sequence of ~10^3 launches and stream dependencies: it is captured once into a CUDA graph per
+// (parameters, sub-batch count, trajectory-buffer roles) and replayed, so the host cost of a solve is one graph launch.
+// Per-launch timing (ddpb_enable_phase_timing) and DDPB_NO_GRAPH=1 use the direct path.
+int ddpb_solve_async(ddpb_batch* h, const ddpb_solver_params* p) {
+  ENTER(h);
+  if (!p || p->max_iterations < 0) return fail(DDPB_ERR_INVALID, "bad solver parameters");
+  static const bool no_graph = getenv("DDPB_NO_GRAPH") != nullptr;
+  if (h->timing || no_graph) return enqueue_solve(h, p);
+  for (auto& g : h->graphs) {
+    if (g.iters == p->max_iterations && g.thr == p->optimality_stopping_threshold && g.mu == p->mu && g.reg == p->reg && g.w == p->w &&
+        g.n == p->n && g.nsub == h->nsub && g.xs == h->bd.xs && g.stream == h->stream) {
+      CU(cudaGraphLaunch(g.exec, h->stream));
+      h->launches += g.launches;
+      if (p->max_iterations & 1) { std::swap(h->bd.xs, h->bd.xs_new); std::swap(h->bd.us, h->bd.us_new); }
+      return DDPB_OK;
+    }
+  }
+  SolveGraph g;
+  g.iters = p->max_iterations; g.thr = p->optimality_stopping_threshold; g.mu = p->mu; g.reg = p->reg; g.w = p->w; g.n = p->n;
+  g.nsub = h->nsub; g.xs = h->bd.xs; g.stream = h->stream;
+  const unsigned long long l0 = h->launches;
+  double* const xs0 = h->bd.xs; double* const xsn0 = h->bd.xs_new; double* const us0 = h->bd.us; double* const usn0 = h->bd.us_new;
+  CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_solve(h, p);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+  if (rc != DDPB_OK || ce != cudaSuccess || !graph) {
+    // capture failed: restore the host-side state and run the sequence directly
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    h->bd.xs = xs0; h->bd.xs_new = xsn0; h->bd.us = us0; h->bd.us_new = usn0;
+    h->launches = l0;
+    return enqueue_solve(h, p);
+  }
+  g.launches = h->launches - l0;
+  const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    h->bd.xs = xs0; h->bd.xs_new = xsn0; h->bd.us = us0; h->bd.us_new = usn0;
+    h->launches = l0;
+    return enqueue_solve(h, p);
+  }
+  if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+  h->graphs.push_back(g);
+  CU(cudaGraphLaunch(g.exec, h->stream));  // the capture itself executed nothing
   return DDPB_OK;
 }
 int ddpb_solve(ddpb_batch* h, const ddpb_solver_params* p, double* scalars_out) {

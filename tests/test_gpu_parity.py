@@ -153,3 +153,25 @@ def test_full_size_roundtrip_properties_c2():
     ok = sc["status"] == 0
     assert np.isfinite(xs2[ok]).all() and (sc["iterations"][ok] == 2).all() and (sc["status"] == 2).sum() <= w.B // 50
     bt.close()
+
+
+def test_repeated_solves_replay_identically():
+    """ddpb_solve replays a captured CUDA graph; an odd iteration count leaves the trajectory buffers swapped, so the
+    next solve runs with the roles exchanged.  Every repetition from the same start must give the same bits, and
+    the phase-timed (direct, ungraphed) path must agree with the replayed one."""
+    w = pc.S.workload("c3", B=96, T=10)
+    g = w.generate()
+    bt = make(w)
+    outs = []
+    for rep in range(5):
+        if rep == 4:
+            bt.enable_phase_timing(True)   # direct enqueue instead of the graph
+        bt.set_targets(g["targets"]); bt.make_trajectory(g["x0"], g["us"]); bt.set_multipliers(None, g["mult_jac"])
+        sc = bt.solve(3, w.mu)
+        xs, us = bt.get_trajectory()
+        outs.append((xs, us, sc["mu"], sc["rollouts"], sc["restarts"], sc["merit"]))
+    bt.phase_times()
+    bt.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b, equal_nan=True)
