@@ -49,7 +49,10 @@ template <int NJ> struct BwdSmem {
 };
 
 // threads per problem on the device
-template <int NJ> struct BwdGeom { static constexpr int BT = NJ <= 3 ? 32 : (NJ <= 5 ? 64 : 128); };
+#ifndef DDPB_BWD_BT_LARGE
+#define DDPB_BWD_BT_LARGE 128
+#endif
+template <int NJ> struct BwdGeom { static constexpr int BT = NJ <= 3 ? 32 : (NJ <= 5 ? 64 : DDPB_BWD_BT_LARGE); };
 
 // inner product over N contiguous doubles with four interleaved partial sums (the dependent chain is N/4 FMAs instead
 // of N); 16-byte loads on the device when both runs are 16-byte aligned (ALIGNED) and N is even.  Host and device use
