@@ -38,7 +38,7 @@ template <int NJ, int MODE> __global__ void __launch_bounds__(MODE == HESS_FD_JA
   bool any = false;
   for (int k = 0; k < nk; ++k) any = any || bd.scal[(size_t)S_STATUS * bd.B + b0 + k] == 0.0;
   if (!any) return;  // every problem of the group is frozen (converged / diverged)
-  linearize_group<NJ, MODE>(m, bd, t, b0, nk, ne_sm, sm, DevExec{});
+  linearize_group<NJ, MODE>(m, bd, t, b0, nk, kpb, ne_sm, sm, DevExec{});
 }
 // one CTA of BwdGeom<NJ>::BT threads per problem; enough CTAs per SM that a whole batch is resident in one wave
 template <int NJ> __global__ void __launch_bounds__(BwdGeom<NJ>::BT, NJ <= 2 ? 28 : (NJ <= 3 ? 16 : (NJ <= 5 ? 8 : 7))) backward_kernel(const __grid_constant__ BatchDev bd) {

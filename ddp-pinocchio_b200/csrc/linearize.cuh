@@ -31,7 +31,10 @@ template <int NJ> struct LinPlan {
   int ne;               // equality rows at this knot
   bool u_points;        // whether the u-perturbed evaluation points exist
   // shared-memory offsets (doubles)
-  int o_base, o_tgt, o_qrec, o_vrec, o_fval, o_eqv, o_J, o_eqxu, o_cterm, o_dg, o_minv0, total;
+  // Shared memory of a CTA that owns kpb knots: [kpb][NQ] q-records | [kpb][NT] v-records | [kpb] everything else.  The
+  // two record arrays are region-major with one odd stride each, so the tasks of a phase (consecutive threads ->
+  // consecutive records, whatever knot they belong to) hit different banks.
+  int o_base, o_tgt, o_fval, o_eqv, o_J, o_eqxu, o_cterm, o_dg, o_minv0, q_sz, v_sz, rest, total;
   // stride of the q-records: the value-based mode needs M^-1 of the base configuration only, so its records end before
   // the MINV block and the one M^-1 lives in its own slot
   DDPB_HD static int qstride(int mode) { return mode == HESS_FD_VALUES ? (QRec<NJ>::MINV | 1) : QRec<NJ>::SIZE; }
@@ -50,8 +53,8 @@ template <int NJ> struct LinPlan {
     int o = 0;
     o_base = o; o += 4 * NJ;
     o_tgt = o; o += (ne_max + 1) & ~1;
-    o_qrec = o; o += NQ * qstride(mode);
-    o_vrec = o; o += NT * VRec<NJ>::SIZE;
+    q_sz = NQ * qstride(mode);
+    v_sz = NT * VRec<NJ>::SIZE;
     o_fval = o; o += P * 2 * NJ;
     o_eqv = o; o += P * ne_max;
     o_J = o; o += NT * 3 * NJ;
@@ -60,7 +63,8 @@ template <int NJ> struct LinPlan {
     o_cterm = o; o += mode == HESS_FD_VALUES ? 2 * NJ * NJ * 6 : 0;
     o_dg = o; o += mode == HESS_FD_VALUES ? 2 * N * (2 * NJ + ne_max) : 0;  // second differences | Jacobian entries
     o_minv0 = o; o += mode == HESS_FD_VALUES ? NJ * NJ : 0;
-    total = o;
+    rest = o;
+    total = q_sz + v_sz + rest;
   }
   // which tangent index/indices a point perturbs (-1 = none)
   DDPB_HD void point_pert(int p, int* i, int* j) const {
@@ -90,7 +94,7 @@ template <int NJ> struct LinPlan {
 // MODE = HESS_FD_JACOBIANS / HESS_FD_VALUES at compile time: the two modes are separate kernels, so the register
 // allocation of one does not pay for the code paths of the other.
 template <int NJ, int MODE, class Ex>
-DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b0, int nk, int ne_sm, double* sm_all, const Ex& ex) {
+DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b0, int nk, int kpb, int ne_sm, double* sm_all, const Ex& ex) {
   constexpr int n = NJ, nd = 2 * NJ, nu = NJ, nx = 2 * NJ, N = 3 * NJ;
   using Q = QRec<NJ>;
   using V = VRec<NJ>;
@@ -101,13 +105,15 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   const double eps = pl.eps();
   const double dt = bd.dt;
   const int tid = ex.tid(), nthr = ex.nthr();
-  const size_t KS = (size_t)pl.total;  // shared-memory stride between the knots of this CTA
+  double* const qbase = sm_all;                                        // [kpb][NQ] records of QS doubles
+  double* const vbase = sm_all + (size_t)kpb * pl.q_sz;                // [kpb][NT] records of V::SIZE doubles
+  double* const rbase = vbase + (size_t)kpb * pl.v_sz;                 // [kpb] x pl.rest
   constexpr int QS = MODE == HESS_FD_VALUES ? (Q::MINV | 1) : Q::SIZE;  // stride between q-records (LinPlan::qstride)
   // M^-1 of q-set s of knot kk (value-based mode: the base configuration's only)
-  auto minv_of = [&](int kk, int s) -> double* {
-    return MODE == HESS_FD_VALUES ? sm_all + (size_t)kk * KS + pl.o_minv0 : sm_all + (size_t)kk * KS + pl.o_qrec + (size_t)s * QS + Q::MINV;
-  };
-#define SM(kk, off) (sm_all + (size_t)(kk) * KS + (off))
+#define SM(kk, off) (rbase + (size_t)(kk) * pl.rest + (off))
+#define QR(kk, s) (qbase + ((size_t)(kk) * pl.NQ + (s)) * QS)
+#define VR(kk, p) (vbase + ((size_t)(kk) * pl.NT + (p)) * V::SIZE)
+  auto minv_of = [&](int kk, int s) -> double* { return MODE == HESS_FD_VALUES ? SM(kk, pl.o_minv0) : QR(kk, s) + Q::MINV; };
 
   DDPB_PHASE_START(bd, pc_);
   // phase 0: stage x_t, u_t and the target
@@ -132,7 +138,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       double q[NJ];
 #pragma unroll
       for (int k = 0; k < NJ; ++k) q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
-      q_task<NJ>(m, q, SM(kk, pl.o_qrec) + (size_t)s * QS);
+      q_task<NJ>(m, q, QR(kk, s));
     }
   } else {
     // phase 1: q-only data for every distinct configuration, as four sub-phases (rbd.cuh "q_task"): the local joint
@@ -145,7 +151,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const double qj = SM(kk, pl.o_base)[jn] + ((jn == i || jn == j) ? eps : 0.0);
       double Rl[9];
       joint_local_rot(m, jn, qj, Rl);
-      double* dst = SM(kk, pl.o_qrec) + (size_t)s * QS + Q::IA + QScratch<NJ>::RL + 9 * jn;
+      double* dst = QR(kk, s) + Q::IA + QScratch<NJ>::RL + 9 * jn;
   #pragma unroll
       for (int k = 0; k < 9; ++k) dst[k] = Rl[k];
     }
@@ -153,19 +159,19 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     DDPB_PHASE_MARK(bd, 8, pc_);
     for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
       const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
-      q_chain<NJ>(m, SM(kk, pl.o_qrec) + (size_t)s * QS);
+      q_chain<NJ>(m, QR(kk, s));
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 9, pc_);
     for (int idx = tid; idx < nk * pl.NQ * NJ; idx += nthr) {
       const int kk = idx / (pl.NQ * NJ), r = idx - kk * (pl.NQ * NJ), s = r / NJ, jn = r - s * NJ;
-      q_body<NJ>(m, jn, SM(kk, pl.o_qrec) + (size_t)s * QS);
+      q_body<NJ>(m, jn, QR(kk, s));
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 10, pc_);
     for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
       const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
-      q_articulate<NJ>(SM(kk, pl.o_qrec) + (size_t)s * QS);
+      q_articulate<NJ>(QR(kk, s));
     }
   }
   ex.sync();
@@ -190,7 +196,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const int kk = idx / pl.NT, p = idx - kk * pl.NT;
       double q[NJ], qd[NJ], tau[NJ];
       point_state(kk, p, q, qd, tau);
-      v_prefix<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS, qd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      v_prefix<NJ>(QR(kk, pl.point_qset(p)), qd, VR(kk, p));
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 11, pc_);
@@ -199,7 +205,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       int i, j;
       pl.point_pert(p, &i, &j);
       const double qdj = SM(kk, pl.o_base)[n + jn] + ((n + jn == i || n + jn == j) ? eps : 0.0);
-      v_bias<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS, jn, qdj, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      v_bias<NJ>(QR(kk, pl.point_qset(p)), jn, qdj, VR(kk, p));
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 12, pc_);
@@ -209,10 +215,10 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     double* fval = SM(kk, pl.o_fval);
     double q[NJ], qd[NJ], tau[NJ], qdd[NJ];
     point_state(kk, p, q, qd, tau);
-    const double* qr = SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS;
+    const double* qr = QR(kk, pl.point_qset(p));
     if (p < pl.NT) {
-      if (SPLIT) v_sweeps<NJ>(m, qr, tau, qdd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
-      else v_task<NJ, true>(m, qr, qd, tau, qdd, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      if (SPLIT) v_sweeps<NJ>(m, qr, tau, qdd, VR(kk, p));
+      else v_task<NJ, true>(m, qr, qd, tau, qdd, VR(kk, p));
     } else {
       v_task<NJ, false>(m, qr, qd, tau, qdd, nullptr);
     }
@@ -229,13 +235,13 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     DDPB_PHASE_MARK(bd, 13, pc_);
     for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
       const int kk = idx / (pl.NT * NJ), r = idx - kk * (pl.NT * NJ), p = r / NJ, jn = r - p * NJ;
-      v_force<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS, jn, SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      v_force<NJ>(QR(kk, pl.point_qset(p)), jn, VR(kk, p));
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 14, pc_);
     for (int idx = tid; idx < nk * pl.NT; idx += nthr) {
       const int kk = idx / pl.NT, p = idx - kk * pl.NT;
-      v_suffix<NJ>(SM(kk, pl.o_vrec) + (size_t)p * V::SIZE);
+      v_suffix<NJ>(VR(kk, p));
     }
   }
   ex.sync();
@@ -247,12 +253,12 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     // (col_term, NJ * NJ slots per derivative kind of which k >= j are used) and reduced afterwards (col_reduce)
     for (int idx = tid; idx < nk * (2 * NJ * NJ + NJ); idx += nthr) {
       const int kk = idx / (2 * NJ * NJ + NJ), r = idx - kk * (2 * NJ * NJ + NJ);
-      double* qr = SM(kk, pl.o_qrec);
+      double* qr = QR(kk, 0);
       if (r < 2 * NJ * NJ) {
         const int wrt = r / (NJ * NJ), r2 = r - wrt * NJ * NJ, j = r2 / NJ, k = r2 - j * NJ;
         if (k >= j) {
           double g[6];
-          col_term<NJ>(qr, SM(kk, pl.o_vrec), j, k, wrt, g);
+          col_term<NJ>(qr, VR(kk, 0), j, k, wrt, g);
           double* dst = SM(kk, pl.o_cterm) + (size_t)(wrt * NJ + j) * NJ * 6 + 6 * k;
 #pragma unroll
           for (int e = 0; e < 6; ++e) dst[e] = g[e];
@@ -270,8 +276,8 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     for (int idx = tid; idx < nk * 2 * NJ; idx += nthr) {
       const int kk = idx / (2 * NJ), r = idx - kk * 2 * NJ, wrt = r / NJ, j = r - wrt * NJ;
       double col[NJ];
-      double* vr = SM(kk, pl.o_vrec);
-      col_reduce<NJ>(SM(kk, pl.o_qrec), vr, SM(kk, pl.o_cterm) + (size_t)(wrt * NJ + j) * NJ * 6, j, wrt, col);
+      double* vr = VR(kk, 0);
+      col_reduce<NJ>(QR(kk, 0), vr, SM(kk, pl.o_cterm) + (size_t)(wrt * NJ + j) * NJ * 6, j, wrt, col);
       double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
 #pragma unroll
       for (int k = 0; k < NJ; ++k) dst[k] = col[k];
@@ -288,8 +294,8 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const int j = idx / (nk * 2 * pl.NT), rem = idx - j * nk * 2 * pl.NT;
         const int kk = rem / (2 * pl.NT), rem2 = rem - kk * 2 * pl.NT;
         const int wrt = rem2 / pl.NT, p = rem2 - wrt * pl.NT;
-        double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
-        col_task<NJ>(SM(kk, pl.o_qrec) + (size_t)pl.point_qset(p) * QS, vr, j, wrt, col);
+        double* vr = VR(kk, p);
+        col_task<NJ>(QR(kk, pl.point_qset(p)), vr, j, wrt, col);
         double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
 #pragma unroll
         for (int k = 0; k < NJ; ++k) dst[k] = col[k];
@@ -297,7 +303,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const int r = idx - nk * n_tan;
         const int kk = r / n_minv, r2 = r - kk * n_minv;
         const int c = r2 % NJ, s = r2 / NJ;
-        double* qr = SM(kk, pl.o_qrec) + (size_t)s * QS;
+        double* qr = QR(kk, s);
         minv_col<NJ>(qr, c, col);
 #pragma unroll
         for (int k = 0; k < NJ; ++k) qr[Q::MINV + c * NJ + k] = col[k];
@@ -313,7 +319,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     const int kk = idx / (pl.NT * 2 * NJ), task = idx - kk * pl.NT * 2 * NJ;
     const int p = task / (2 * NJ), rem = task - p * 2 * NJ;
     const int wrt = rem / NJ, c = rem - wrt * NJ;
-    double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
+    double* vr = VR(kk, p);
     double* colp = vr + (wrt ? V::DV : V::DQ) + c * NJ;
     const double* Mi = minv_of(kk, pl.point_qset(p));
     double src[NJ], dst[NJ];
@@ -336,7 +342,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   // element accessors of fx / fu at point p (p < NT) of knot kk
   auto fx_at = [&](int kk, int p, int r, int c) -> double {
     if (r < n) return c < n ? (r == c ? 1.0 : 0.0) : (r == c - n ? dt : 0.0);
-    const double* vr = SM(kk, pl.o_vrec) + (size_t)p * V::SIZE;
+    const double* vr = VR(kk, p);
     return c < n ? vr[V::DQ + c * NJ + (r - n)] : vr[V::DV + (c - n) * NJ + (r - n)];
   };
   auto fu_at = [&](int kk, int p, int r, int c) -> double {
@@ -421,7 +427,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       double* dst = &REC(kk, L.fxx + r);
       if (k >= n) {
         const int off = (j < n ? V::DQ + j * NJ : V::DV + (j - n) * NJ) + (k - n);
-        const double* vr = SM(kk, pl.o_vrec) + off;
+        const double* vr = VR(kk, 0) + off;
         const double base = vr[0];
 #pragma unroll
         for (int i = 0; i < nd; ++i) dst[(size_t)i * nd * nd] = (vr[(size_t)(1 + i) * V::SIZE] - base) * inv_eps;
@@ -436,7 +442,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       double* dst = &REC(kk, L.fux + r);
       if (k >= n) {
         // only a q-perturbation changes M^-1; v-perturbed points share the base q-set (exact zero)
-        const double* qr = SM(kk, pl.o_qrec) + Q::MINV + j * NJ + (k - n);
+        const double* qr = QR(kk, 0) + Q::MINV + j * NJ + (k - n);
         const double base = qr[0] * dt;
 #pragma unroll
         for (int i = 0; i < n; ++i) dst[(size_t)i * nd * nu] = (qr[(size_t)(1 + i) * QS] * dt - base) * inv_eps;
@@ -547,6 +553,8 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
 #undef REC
   DDPB_PHASE_MARK(bd, 7, pc_);
 #undef SM
+#undef QR
+#undef VR
 }
 
 // ---- pendulum (nx = 2, nu = 1): one thread per knot, following the oracle statement by statement ----

@@ -50,9 +50,9 @@ struct Emu {
     default: break;                                \
   }
 
-template <int NJ> static void linearize_host(const ModelDev& m, const BatchDev& bd, int t, int b0, int nk, double* sm) {
-  if (bd.hess_mode == HESS_FD_JACOBIANS) linearize_group<NJ, HESS_FD_JACOBIANS>(m, bd, t, b0, nk, bd.ne[t], sm, DevExec{});
-  else linearize_group<NJ, HESS_FD_VALUES>(m, bd, t, b0, nk, bd.ne[t], sm, DevExec{});
+template <int NJ> static void linearize_host(const ModelDev& m, const BatchDev& bd, int t, int b0, int nk, int kpb, double* sm) {
+  if (bd.hess_mode == HESS_FD_JACOBIANS) linearize_group<NJ, HESS_FD_JACOBIANS>(m, bd, t, b0, nk, kpb, bd.ne[t], sm, DevExec{});
+  else linearize_group<NJ, HESS_FD_VALUES>(m, bd, t, b0, nk, kpb, bd.ne[t], sm, DevExec{});
 }
 template <int NJ> static void backward_host(const BatchDev& bd, int b, double* sm) { backward_problem<NJ, 1>(bd, b, sm, DevExec{}); }
 
@@ -121,7 +121,7 @@ void emu_linearize(void* hv) {
         const int nk = bd.B - b0 < kpb ? bd.B - b0 : kpb;
         bool any = false;
         for (int k = 0; k < nk; ++k) any = any || bd.scal[(size_t)S_STATUS * bd.B + b0 + k] == 0.0;
-        if (any) linearize_host<NJ>(h->model, bd, t, b0, nk, sm.data());
+        if (any) linearize_host<NJ>(h->model, bd, t, b0, nk, kpb, sm.data());
       }
     }
   });
