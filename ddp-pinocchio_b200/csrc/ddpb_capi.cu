@@ -386,7 +386,7 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   // launch geometry
   const bool fdv = p->hess_mode == DDPB_HESS_FD_VALUES;
   // measured on B200 (tools/sweep_geometry.sh, profiles/): small CTAs keep more knots / problems resident per SM
-  h->lin_threads = fdv ? (n <= 2 ? 32 : (n <= 4 ? 128 : 256)) : (n >= 5 ? 256 : 64);
+  h->lin_threads = fdv ? (n <= 2 ? 32 : (n <= 4 ? 128 : 256)) : (n >= 5 ? 256 : 128);
   h->bwd_threads = 32;  // informational: the backward kernel fixes its own CTA size (BwdGeom in backward.cuh)
   // development knobs (launch geometry sweeps); not part of the interface
   if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->lin_threads = v; }
