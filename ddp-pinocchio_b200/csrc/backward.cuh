@@ -154,6 +154,8 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
   constexpr bool AL = S::head_aligned;  // fx / fu columns of the head copy start on 16-byte boundaries
   const int B = bd.B, T = bd.T;
   const int tid = ex.tid();
+  // a one-warp group needs no CTA barrier: warp-level synchronisation orders its shared-memory traffic
+  auto bsync = [&]() { if (BT == 32) ex.sync_warp(); else ex.sync(); };
   double mu = bd.scal[(size_t)S_MU * B + b];
   double reg = bd.scal[(size_t)S_REG * B + b];
   int restarts = 0;
@@ -217,7 +219,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
   while (!success) {
     // V_xx = lfxx = 0, V_x = lfx = 0  (problem.hpp:958-959)
     FOR_ELEMS(e, nd * nd + nd) sm[S::VxxR + e] = 0.0;
-    ex.sync();
+    bsync();
     bool failed = false;
     // software pipeline: what knot t needs first -- the head of its record (registers) and round 0 of every warp's
     // tensor share (warp-private staging buffer, cp.async) -- is fetched while knot t+1 is being processed
@@ -334,7 +336,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         if (t > 0) prefetch(t - 1, hcur ^ 1);  // the staging buffer and the other head buffer are free
         hcur ^= 1;
       }
-      ex.sync();
+      bsync();
       DDPB_PHASE_MARK(bd, 8, pc_);
       // ---- phase B: tmp, tmp2, VF = V_xx f_x, VU = V_xx f_u ----------------------------------------------------
       for (int e = tid; e < ne; e += BT) sm[S::tmp + e] = sm[S::pe + e] + mu * sm[S::eqv + e];
@@ -349,7 +351,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         }
         FOR_ELEMS(e, NB) sm[S::VF + e] = acc[u_];  // VF | VU are adjacent
       }
-      ex.sync();
+      bsync();
       DDPB_PHASE_MARK(bd, 9, pc_);
       const double* Vx = sm + S::Vx;
       const double* eqv = sm + S::eqv;
@@ -422,7 +424,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
           if ((ld & 0x7fffu) != 0x7fffu) sm[ld & 0x7fffu] = qacc[u_] + ((ld & 0x8000u) ? reg : 0.0);
         }
       }
-      ex.sync();
+      bsync();
       DDPB_PHASE_MARK(bd, 10, pc_);
       // ---- phase D (first warp): Cholesky of Q_uu + reg I, then k = -(LL^T)^-1 Q_u, K = -(LL^T)^-1 Q_ux, one
       // right-hand side per lane ------------------------------------------------------------------------------------
@@ -469,7 +471,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         }
       }
       if (tid < nx) bd.fb_origin[((size_t)t * nx + tid) * B + b] = xorg;
-      ex.sync();
+      bsync();
       DDPB_PHASE_MARK(bd, 11, pc_);
       if (sm[S::flags] == 0.0) {
         if (reg < mu) reg = mu;
@@ -477,7 +479,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         reg *= 2.0;
         ++restarts;
         failed = true;
-        ex.sync();
+        bsync();
         break;
       }
       // ---- phase F: V_x = Q_x + Q_ux^T k ; V_xx = Q_xx + Q_ux^T K  (V_xx stored row-major) ----------------------------
@@ -497,7 +499,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         }
         FOR_ELEMS(e, NF) sm[vdst[u_]] = vacc[u_];  // V_xx (row-major) | V_x are adjacent
       }
-      ex.sync();
+      bsync();
       DDPB_PHASE_MARK(bd, 12, pc_);
     }
     if (!failed) success = true;
