@@ -10,8 +10,9 @@
 // The recursion is a latency chain (T dependent knots) fed by 8 * rec_size bytes per knot, so the design keeps the
 // dependent path of one knot short and the memory system busy ahead of it:
 //   * while knot t is being processed, the head of the record of knot t-1 goes into the idle head buffer and round 0
-//     of every warp's tensor share into its staging buffer with cp.async (no registers held), so a knot starts with
-//     its first operands already in shared memory; later rounds are loaded one round ahead.  (A bulk L2 prefetch of
+//     of every warp's tensor share into its staging buffer by TMA (cp.async.bulk global -> shared completing on an
+//     mbarrier; one thread issues 1 + #warps bulk copies, no registers held), so a knot starts with its first operands
+//     already in shared memory; later rounds are loaded one round ahead.  (A bulk L2 prefetch of
 //     the record after next was measured to re-fetch ~50 % of the bytes from DRAM without shortening the pass and
 //     was removed: DRAM reads now equal the algorithmic bytes.)
 //   * the third-order tensors are used once: every warp streams its share with fully coalesced 16-byte loads through
@@ -41,7 +42,8 @@ template <int NJ> struct BwdSmem {
                        eqv = even(KK + nu * nd), eqx = eqv + MAXE, equ = eqx + MAXE * nd, pe = equ + MAXE * nu,
                        pex = pe + MAXE, tmp = pex + MAXE * nd, tmp2 = tmp + MAXE, flags = tmp2 + MAXE * nd,
                        zero = flags + 2,  // one double that stays 0.0 (tasks without a tensor term add it)
-                       stage = even(zero + 2),  // device: NW warp-private staging buffers of RS * nd doubles
+                       mbar = zero + 2,   // the mbarrier of the record staging (8 bytes, 16-byte slot)
+                       stage = even(mbar + 2),  // device: NW warp-private staging buffers of RS * nd doubles
                        SIZE = stage;
   static constexpr int size_for(int threads) { return SIZE + (threads >= 32 ? (threads / 32) * RS * nd : 0); }
   // head offset of fx must be even for the 16-byte inner products: nd + nu + nd*nd + nu*nd + nu*nu + nd = nu (mod 2)
@@ -77,6 +79,36 @@ template <int N, bool ALIGNED> DDPB_HD double dot_run(const double* a, const dou
   }
   return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
+
+// ---- TMA (bulk asynchronous copy) staging of a slab record: cp.async.bulk global -> shared, completion counted in bytes
+// on an mbarrier.  One thread issues the copies of a whole knot (record head + every warp's first staging round); all
+// threads wait on the barrier's phase.  The wait is bounded: a byte-count bug traps instead of hanging the device.
+#ifndef DDPB_BWD_TMA
+#define DDPB_BWD_TMA 1
+#endif
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; ++spin) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 // 16-byte asynchronous copy global -> shared (LDGSTS) and its completion fence
 DDPB_HD void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -216,6 +248,12 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
     FOR_ELEMS(e, NF) mkF(e, dF0[PRE ? u_ : 0], dF1[PRE ? u_ : 0]);
   }
   if (tid == 0) { sm[S::zero] = 0.0; sm[S::zero + 1] = 0.0; }
+  unsigned tma_phase = 0;     // parity of the staging mbarrier's current phase
+  bool tma_pending = false;   // a prefetch has been issued and not yet waited for
+#if defined(__CUDA_ARCH__) && DDPB_BWD_TMA
+  if (tid == 0) { mbar_init(sm + S::mbar, 1); fence_proxy_async(); }
+#endif
+  (void)tma_phase;
   while (!success) {
     // V_xx = lfxx = 0, V_x = lfx = 0  (problem.hpp:958-959)
     FOR_ELEMS(e, nd * nd + nd) sm[S::VxxR + e] = 0.0;
@@ -231,12 +269,35 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
     const int e_beg = warp * EW, e_end = (warp + 1) * EW < NTEN ? (warp + 1) * EW : NTEN;
 #endif
     // fetch what knot tp needs first into the buffers that are idle while the current knot is processed: the head of
-    // its record -> the other head buffer, round 0 of every warp's tensor share -> the warp's staging buffer
+    // its record -> the other head buffer, round 0 of every warp's tensor share -> the warp's staging buffer.
+    // TMA path: thread 0 issues one bulk copy per buffer, all completing on the CTA's mbarrier; it is called after a
+    // barrier that follows the last read of the target buffers (the staging buffers were also written with ordinary
+    // stores, hence the proxy fence).
     auto prefetch = [&](int tp, int hnext) {
       const RecLayout Lp = rec_layout(nd, nu, nx, bd.ne[tp]);
       const double* recp = slab_rec(bd, tp, b, Lp.size);
       double* hdst = sm + (hnext ? S::head2 : S::head);
 #if defined(__CUDA_ARCH__)
+#if DDPB_BWD_TMA
+      if (tid == 0) {
+        unsigned bytes = S::NHEAD * 8;
+#pragma unroll
+        for (int wq = 0; wq < NW; ++wq) {
+          const int eb = wq * EW, ee = (wq + 1) * EW < NTEN ? (wq + 1) * EW : NTEN;
+          const int nr = ee - eb < RS ? ee - eb : RS;
+          if (nr > 0) bytes += (unsigned)(nr * nd * 8);
+        }
+        fence_proxy_async();
+        mbar_expect_tx(sm + S::mbar, bytes);
+        tma_bulk_g2s(hdst, recp, S::NHEAD * 8, sm + S::mbar);
+#pragma unroll
+        for (int wq = 0; wq < NW; ++wq) {
+          const int eb = wq * EW, ee = (wq + 1) * EW < NTEN ? (wq + 1) * EW : NTEN;
+          const int nr = ee - eb < RS ? ee - eb : RS;
+          if (nr > 0) tma_bulk_g2s(sm + S::stage + wq * RS * nd, recp + Lp.fxx + (size_t)eb * nd, (unsigned)(nr * nd * 8), sm + S::mbar);
+        }
+      }
+#else
       FOR_ELEMS(c, S::NHEAD / 2) cp_async16(hdst + 2 * c, recp + 2 * c);
       const int ne_round = e_end - e_beg < RS ? e_end - e_beg : RS;
       const double2* src = reinterpret_cast<const double2*>(recp + Lp.fxx + (size_t)e_beg * nd);
@@ -245,13 +306,27 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         const int c = lane + 32 * i;
         if (c < ne_round * CPE) cp_async16(reinterpret_cast<double2*>(stg) + c, src + c);
       }
+#endif
 #else
       for (int e = 0; e < S::NHEAD; ++e) hdst[e] = recp[e];
 #endif
     };
-    cp_async_wait_all();  // a restarted pass may still have the aborted knot's prefetch in flight
-    ex.sync_warp();
+    // wait for the staged data of the knot about to be processed
+    auto staged_wait = [&]() {
+#if defined(__CUDA_ARCH__)
+#if DDPB_BWD_TMA
+      mbar_wait(sm + S::mbar, tma_phase);
+      tma_phase ^= 1u;
+#else
+      cp_async_wait_all();
+      ex.sync_warp();
+#endif
+#endif
+    };
+    if (tma_pending) staged_wait();  // a restarted pass still has the aborted knot's prefetch in flight
+    bsync();
     prefetch(T - 1, hcur);
+    tma_pending = true;
     for (int t = T - 1; t >= 0; --t) {
       DDPB_PHASE_START(bd, pc_);
       const int ne = bd.ne[t], eo = bd.eq_off[t];
@@ -282,8 +357,8 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
           };
           if (e_beg + RS < e_end) load_round(e_beg + RS);
           DDPB_PHASE_MARK(bd, 13, pc_);
-          cp_async_wait_all();
-          __syncwarp();
+          staged_wait();
+          tma_pending = false;
           DDPB_PHASE_MARK(bd, 14, pc_);
           for (int e0 = e_beg; e0 < e_end; e0 += RS) {
             const int ne_round = e_end - e0 < RS ? e_end - e0 : RS;
@@ -333,11 +408,17 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
           for (int e = tid; e < ne * nu; e += BT) sm[S::equ + e] = rec[L.eq_u + e];
         }
         DDPB_PHASE_MARK(bd, 15, pc_);
-        if (t > 0) prefetch(t - 1, hcur ^ 1);  // the staging buffer and the other head buffer are free
+#if !(defined(__CUDA_ARCH__) && DDPB_BWD_TMA)
+        if (t > 0) { prefetch(t - 1, hcur ^ 1); tma_pending = true; }  // the staging buffer and the other head buffer are free
+#endif
         hcur ^= 1;
       }
       bsync();
       DDPB_PHASE_MARK(bd, 8, pc_);
+#if defined(__CUDA_ARCH__) && DDPB_BWD_TMA
+      // every warp is past its last read of the staging buffers: stage the next knot (hcur now names the idle head buffer)
+      if (t > 0) { prefetch(t - 1, hcur); tma_pending = true; }
+#endif
       // ---- phase B: tmp, tmp2, VF = V_xx f_x, VU = V_xx f_u ----------------------------------------------------
       for (int e = tid; e < ne; e += BT) sm[S::tmp + e] = sm[S::pe + e] + mu * sm[S::eqv + e];
       for (int e = tid; e < ne * nd; e += BT) sm[S::tmp2 + e] = sm[S::pex + e] + mu * sm[S::eqx + e];
