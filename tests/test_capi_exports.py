@@ -55,3 +55,17 @@ def test_fails_loudly_without_a_gpu(pkg):
     from ddp_pinocchio_b200 import capi, synthetic
     with pytest.raises(capi.DdpbError, match="no CUDA device"):
         capi.Batch.from_workload(synthetic.workload("c2", B=2, T=4))
+
+
+def test_backward_kernel_uses_tma_bulk_copies():
+    """The backward pass stages slab records with TMA (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier (SYNCS);
+    checked on the built library's SASS (skipped where cuobjdump is not installed)."""
+    import shutil
+    import subprocess
+    import pytest
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ddp-pinocchio_b200", "libddpb.so")
+    sass = subprocess.run([exe, "-sass", "-fun", "_ZN4ddpb15backward_kernelILi6EEEvNS_8BatchDevE", lib], capture_output=True, text=True).stdout
+    assert "UBLKCP.S.G" in sass and "SYNCS.PHASECHK" in sass
