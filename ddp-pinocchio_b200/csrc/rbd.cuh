@@ -353,12 +353,17 @@ template <int NJ, bool REC> DDPB_HD void v_task(const ModelDev& m, const double*
       }
     }
   }
+  double carry[6] = {0, 0, 0, 0, 0, 0};  // child -> parent bias force, in registers (see v_sweeps)
 #pragma unroll
   for (int i = NJ - 1; i >= 0; --i) {
     const double* S = qrec + Q::S + 6 * i;
     double pa[6], c[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { pa[k] = REC ? vrec[V::F + 6 * i + k] : pl[REC ? 0 : i][k]; c[k] = REC ? vrec[V::A + 6 * i + k] : cl[REC ? 0 : i][k]; }
+    for (int k = 0; k < 6; ++k) {
+      pa[k] = REC ? vrec[V::F + 6 * i + k] : pl[REC ? 0 : i][k];
+      if (i < NJ - 1) pa[k] += carry[k];
+      c[k] = REC ? vrec[V::A + 6 * i + k] : cl[REC ? 0 : i][k];
+    }
     u[i] = tau[i] - dot6(S, pa);
     if (i > 0) {
       const double* U = qrec + Q::U + 6 * i;
@@ -366,10 +371,7 @@ template <int NJ, bool REC> DDPB_HD void v_task(const ModelDev& m, const double*
       const double t = qrec[Q::DINV + i] * (u[i] - dot6(U, c));
       sym6_mul(qrec + Q::IA + 21 * i, c, Iac);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double add = pa[k] + Iac[k] + U[k] * t;
-        if (REC) vrec[V::F + 6 * (i - 1) + k] += add; else pl[REC ? 0 : i - 1][k] += add;
-      }
+      for (int k = 0; k < 6; ++k) carry[k] = pa[k] + Iac[k] + U[k] * t;
     }
   }
   double a[6] = {0.0, 0.0, 0.0, -m.grav[0], -m.grav[1], -m.grav[2]};
@@ -447,21 +449,21 @@ template <int NJ> DDPB_HD void v_sweeps(const ModelDev& m, const double* qrec, c
   using Q = QRec<NJ>;
   using V = VRec<NJ>;
   double u[NJ];
+  // what the child hands to its parent is carried in registers (parent bias force = its own + carry: the same single
+  // addition as accumulating into the parent's slot, without the shared-memory round trip on the dependent path)
+  double carry[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int i = NJ - 1; i >= 0; --i) {
     const double* S = qrec + Q::S + 6 * i;
-    double pa[6], c[6];
+    double pa[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { pa[k] = vrec[V::F + 6 * i + k]; c[k] = vrec[V::A + 6 * i + k]; }
+    for (int k = 0; k < 6; ++k) { pa[k] = vrec[V::F + 6 * i + k]; if (i < NJ - 1) pa[k] += carry[k]; }
     u[i] = tau[i] - dot6(S, pa);
     if (i > 0) {
       const double* U = qrec + Q::U + 6 * i;
       const double t = qrec[Q::DINV + i] * (u[i] - vrec[V::DQ + 7 * i + 6]);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double add = pa[k] + vrec[V::DQ + 7 * i + k] + U[k] * t;
-        vrec[V::F + 6 * (i - 1) + k] += add;
-      }
+      for (int k = 0; k < 6; ++k) carry[k] = pa[k] + vrec[V::DQ + 7 * i + k] + U[k] * t;
     }
   }
   double a[6] = {0.0, 0.0, 0.0, -m.grav[0], -m.grav[1], -m.grav[2]};
@@ -530,13 +532,14 @@ template <int NJ> DDPB_HD void aba_fused(const ModelDev& m, const double* q, con
     double IA[21];
 #pragma unroll
     for (int k = 0; k < 21; ++k) IA[k] = 0.0;
+    double carry[6] = {0, 0, 0, 0, 0, 0};  // child -> parent bias force, in registers (see v_sweeps)
 #pragma unroll
     for (int i = NJ - 1; i >= 0; --i) {
       double Y[10], S[6], U[6], pa[6], c[6];
 #pragma unroll
       for (int k = 0; k < 10; ++k) Y[k] = SCR(i, 18 + k);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { S[k] = SCR(i, k); c[k] = SCR(i, 6 + k); pa[k] = SCR(i, 12 + k); }
+      for (int k = 0; k < 6; ++k) { S[k] = SCR(i, k); c[k] = SCR(i, 6 + k); pa[k] = SCR(i, 12 + k); if (i < NJ - 1) pa[k] += carry[k]; }
       ia_add_body(IA, Y);
       sym6_mul(IA, S, U);
       const double Dinv = 1.0 / dot6(S, U);
@@ -550,10 +553,7 @@ template <int NJ> DDPB_HD void aba_fused(const ModelDev& m, const double* q, con
         const double t = Dinv * (u - dot6(U, c));
         sym6_mul(IA, c, Iac);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const double add = pa[k] + Iac[k] + U[k] * t;
-          SCR(i - 1, 12 + k) += add;
-        }
+        for (int k = 0; k < 6; ++k) carry[k] = pa[k] + Iac[k] + U[k] * t;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
           const double sr = U[r] * Dinv;
