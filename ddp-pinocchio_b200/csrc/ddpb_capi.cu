@@ -385,16 +385,23 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   CU(cudaHostAlloc((void**)&h->h_stage, (size_t)NSCALARS * B * sizeof(double), cudaHostAllocDefault));
   // launch geometry
   const bool fdv = p->hess_mode == DDPB_HESS_FD_VALUES;
-  // measured on B200 (tools/sweep_geometry.sh, profiles/): small CTAs keep more knots / problems resident per SM
-  h->lin_threads = fdv ? (n <= 2 ? 32 : (n <= 4 ? 128 : 256)) : (n >= 5 ? 256 : 128);
+  // measured on B200 (tools/lin_geom_sweep.sh): small CTAs keep more knots / problems resident per SM.
+  // Value-based Hessians: one knot per CTA; from 5 joints on 128 threads, so that two CTAs
+  // (255 registers per thread) share an SM and the narrow phases of one knot overlap the wide phases of another.
+  h->lin_threads = fdv ? (n <= 2 ? 32 : 128) : (n >= 5 ? 256 : 128);
   h->bwd_threads = 32;  // informational: the backward kernel fixes its own CTA size (BwdGeom in backward.cuh)
   // development knobs (launch geometry sweeps); not part of the interface
   if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->lin_threads = v; }
 
-  // problems per CTA of the linearization: small models leave most lanes of a one-knot CTA idle
-  h->lin_kpb = fdv ? 1 : (n <= 1 ? 16 : (n == 2 ? 8 : 2));
+  // problems per CTA of the linearization: the serial sub-phases of a knot occupy a handful of lanes, so a CTA owns as
+  // many knots as shared memory allows while two (256-thread) or three (128-thread) CTAs still fit an SM
+  size_t knot_smem = 0, knot_smem_max = 0;  // workspace of an unconstrained knot / of the knot with the most rows
+  DISPATCH(h->mt, { knot_smem = L::lin_smem_bytes(p->hess_mode, 0, p->eq_kind); knot_smem_max = L::lin_smem_bytes(p->hess_mode, bd.ne_max, p->eq_kind); });
+  h->lin_kpb = fdv ? 1 : (n <= 1 ? 16 : (n == 2 ? 16 : 2));
+  if (!fdv && n >= 5 && knot_smem > 0) h->lin_kpb = (int)std::min<size_t>(3, std::max<size_t>(1, ((size_t)113 << 10) / knot_smem));
   if (const char* e = getenv("DDPB_LIN_KPB")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->lin_kpb = v; }
-  DISPATCH(h->mt, { h->lin_smem = L::lin_smem_bytes(p->hess_mode, bd.ne_max, p->eq_kind) * h->lin_kpb; });
+  while (h->lin_kpb > 1 && knot_smem_max * h->lin_kpb > (size_t)prop.sharedMemPerBlockOptin) --h->lin_kpb;
+  h->lin_smem = knot_smem_max * h->lin_kpb;
   if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) { ddpb_batch_destroy(h); return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory"); }
   DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });
   DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(); });

@@ -35,16 +35,16 @@ template <int NJ> struct LinPlan {
   // two record arrays are region-major with one odd stride each, so the tasks of a phase (consecutive threads ->
   // consecutive records, whatever knot they belong to) hit different banks.
   int o_base, o_tgt, o_fval, o_eqv, o_J, o_eqxu, o_cterm, o_dg, o_minv0, q_sz, v_sz, rest, total;
-  // stride of the q-records: the value-based mode needs M^-1 of the base configuration only, so its records end before
-  // the MINV block and the one M^-1 lives in its own slot
-  DDPB_HD static int qstride(int mode) { return mode == HESS_FD_VALUES ? (QRec<NJ>::MINV | 1) : QRec<NJ>::SIZE; }
+  // stride of the q-records (M^-1 aliases the articulated inertias inside a record; the value-based mode needs M^-1 of
+  // the base configuration only, while its value-only points still read IA, so that one M^-1 lives in its own slot)
+  DDPB_HD static int qstride(int) { return QRec<NJ>::SIZE; }
   DDPB_HD static int points(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + N : 1 + N + N * (N - 1) / 2; }
   DDPB_HD static int qsets(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + NJ : 1 + NJ + NJ * (NJ - 1) / 2; }
   // FD-of-Jacobians mode: the reference evaluates (f_x, f_u) at the u-perturbed points only to difference f_u
   // (problem.hpp:138-145), and f_u = dt M^-1(q) cannot change when only u moves: f_uu (and eq_uu of a configuration
   // constraint) are exact zeros there too.  Those N/3 points are therefore dropped unless a spatial constraint needs
   // the frame Jacobian at their q_{t+2}.
-  DDPB_HD void init(int mode_, int ne_max, int ne_, int eq_kind = EQ_NONE) {
+  DDPB_HD void init(int mode_, int ne_max, int ne_, int eq_kind) {
     mode = mode_; ne = ne_;
     P = points(mode); NQ = qsets(mode);
     u_points = !(mode == HESS_FD_JACOBIANS && !(eq_kind == EQ_SPATIAL && ne_ > 0));
@@ -57,7 +57,7 @@ template <int NJ> struct LinPlan {
     v_sz = NT * VRec<NJ>::SIZE;
     o_fval = o; o += P * 2 * NJ;
     o_eqv = o; o += P * ne_max;
-    o_J = o; o += NT * 3 * NJ;
+    o_J = o; o += eq_kind == EQ_SPATIAL ? NT * 3 * NJ : 0;  // frame Jacobians of a spatial constraint
     o_eqxu = o; o += NT * ne_max * N;
     // value-based mode only: per-body column terms of the base point, diagonal second differences of f and eq
     o_cterm = o; o += mode == HESS_FD_VALUES ? 2 * NJ * NJ * 6 : 0;
@@ -108,7 +108,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   double* const qbase = sm_all;                                        // [kpb][NQ] records of QS doubles
   double* const vbase = sm_all + (size_t)kpb * pl.q_sz;                // [kpb][NT] records of V::SIZE doubles
   double* const rbase = vbase + (size_t)kpb * pl.v_sz;                 // [kpb] x pl.rest
-  constexpr int QS = MODE == HESS_FD_VALUES ? (Q::MINV | 1) : Q::SIZE;  // stride between q-records (LinPlan::qstride)
+  constexpr int QS = Q::SIZE;  // stride between q-records (LinPlan::qstride)
   // M^-1 of q-set s of knot kk (value-based mode: the base configuration's only)
 #define SM(kk, off) (rbase + (size_t)(kk) * pl.rest + (off))
 #define QR(kk, s) (qbase + ((size_t)(kk) * pl.NQ + (s)) * QS)
@@ -151,7 +151,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const double qj = SM(kk, pl.o_base)[jn] + ((jn == i || jn == j) ? eps : 0.0);
       double Rl[9];
       joint_local_rot(m, jn, qj, Rl);
-      double* dst = QR(kk, s) + Q::IA + QScratch<NJ>::RL + 9 * jn;
+      double* dst = QR(kk, s) + Q::SCR + QScratch<NJ>::RL + 9 * jn;
   #pragma unroll
       for (int k = 0; k < 9; ++k) dst[k] = Rl[k];
     }
@@ -216,7 +216,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     double q[NJ], qd[NJ], tau[NJ], qdd[NJ];
     point_state(kk, p, q, qd, tau);
     const double* qr = QR(kk, pl.point_qset(p));
-    if (p < pl.NT) {
+    if (MODE == HESS_FD_JACOBIANS || p < pl.NT) {  // every point has a record in FD-of-Jacobians mode (NT == P)
       if (SPLIT) v_sweeps<NJ>(m, qr, tau, qdd, VR(kk, p));
       else v_task<NJ, true>(m, qr, qd, tau, qdd, VR(kk, p));
     } else {
@@ -230,6 +230,22 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       fval[p * nx + n + k] = qd[k] + qdd[k] * dt;
     }
   }
+  // M^-1 columns need S, U and 1/D of their configuration only, and their destination (aliased onto the articulated
+  // inertias, QRec::MINV) has had its last reader in v_bias: in split FD-of-Jacobians mode they run here, on the threads
+  // the serial sweeps above leave idle (taken from the top of the CTA), instead of lengthening the column phase.
+  constexpr bool MINV_EARLY = SPLIT && MODE == HESS_FD_JACOBIANS;
+  auto minv_task = [&](int r) {
+    const int n_minv = pl.NQ * NJ;
+    const int kk = r / n_minv, r2 = r - kk * n_minv;
+    const int c = r2 % NJ, s = r2 / NJ;
+    double* qr = QR(kk, s);
+    double col[NJ];
+    minv_col<NJ>(qr, c, col);
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) qr[Q::MINV + c * NJ + k] = col[k];
+  };
+  if (MINV_EARLY)
+    for (int idx = nthr - 1 - tid; idx < nk * pl.NQ * NJ; idx += nthr) minv_task(idx);
   if (SPLIT) {
     ex.sync();
     DDPB_PHASE_MARK(bd, 13, pc_);
@@ -285,11 +301,16 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   } else {
 
     const int n_tan = pl.NT * 2 * NJ;
-    const int n_minv = (MODE == HESS_FD_JACOBIANS ? pl.NQ : 1) * NJ;
-    // tangent tasks of all knots first (j-major inside a knot), then the M^-1 tasks
-    for (int idx = tid; idx < nk * (n_tan + n_minv); idx += nthr) {
-      double col[NJ];
+    const int n_minv = MINV_EARLY ? 0 : pl.NQ * NJ;
+    // tangent tasks of all knots first (j-major inside a knot), then the M^-1 tasks.  A column costs one term per body
+    // k >= j, so the task list runs from expensive to cheap: every other round walks it backwards, which hands the
+    // cheap tail to the threads that had the expensive head (critical path ~ the mean instead of head + tail).
+    const int n_all = nk * (n_tan + n_minv);
+    for (int base = 0, rnd = 0; base < n_all; base += nthr, ++rnd) {
+      const int idx = base + ((rnd & 1) ? nthr - 1 - tid : tid);
+      if (idx >= n_all) continue;
       if (idx < nk * n_tan) {
+        double col[NJ];
         // order: j slowest so that the threads of a warp share the loop bounds of col_task
         const int j = idx / (nk * 2 * pl.NT), rem = idx - j * nk * 2 * pl.NT;
         const int kk = rem / (2 * pl.NT), rem2 = rem - kk * 2 * pl.NT;
@@ -300,13 +321,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
 #pragma unroll
         for (int k = 0; k < NJ; ++k) dst[k] = col[k];
       } else {
-        const int r = idx - nk * n_tan;
-        const int kk = r / n_minv, r2 = r - kk * n_minv;
-        const int c = r2 % NJ, s = r2 / NJ;
-        double* qr = QR(kk, s);
-        minv_col<NJ>(qr, c, col);
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) qr[Q::MINV + c * NJ + k] = col[k];
+        minv_task(idx - nk * n_tan);
       }
     }
   }

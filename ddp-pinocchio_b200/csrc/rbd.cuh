@@ -151,9 +151,16 @@ template <int NJ> struct QRec {
   static constexpr int Y = S + 6 * NJ;        // [NJ][10] rigid-body inertias (world)
   static constexpr int U = Y + 10 * NJ;       // [NJ][6]  IA_i S_i
   static constexpr int DINV = U + 6 * NJ;     // [NJ]     1 / (S_i . U_i)
-  static constexpr int IA = DINV + NJ;        // [NJ][21] articulated inertias (packed symmetric)
-  static constexpr int MINV = IA + 21 * NJ;   // [NJ][NJ] column-major
-  static constexpr int RAW = MINV + NJ * NJ;
+  // [NJ-1][21] articulated inertias (packed symmetric) of bodies 1 .. NJ-1, body i at IA + 21 (i - 1): the v-sweeps
+  // need IA_i only to hand body i's bias force to its parent, so the root's is never stored
+  static constexpr int IA = DINV + NJ;
+  // [NJ][NJ] column-major, ALIASED onto the IA block: M^-1 is computed (minv_col: S, U, 1/D only) in the phase after
+  // the last reader of IA, so the two never live at the same time -- 8 NJ^2 bytes of shared memory less per record
+  static constexpr int MINV = IA;
+  // scratch of the q sub-phases (QScratch, 21 NJ doubles): over U | DINV | IA, all written by q_articulate afterwards
+  static constexpr int SCR = U;
+  static constexpr int END_IA = IA + 21 * (NJ - 1), END_MINV = MINV + NJ * NJ, END_SCR = SCR + 21 * NJ;
+  static constexpr int RAW = END_IA > END_MINV ? (END_IA > END_SCR ? END_IA : END_SCR) : (END_MINV > END_SCR ? END_MINV : END_SCR);
   static constexpr int SIZE = RAW | 1;
 };
 template <int NJ> struct VRec {
@@ -244,10 +251,9 @@ DDPB_HD void ia_add_body(double* IA, const double* Y) {
 //   body_world       per (configuration, body)    -> S_i, Y_i        (parallel)
 //   q_articulate     per configuration            -> IA_i, U_i, 1/D_i (serial, leaf to root)
 // q_task is the same arithmetic in one call (rollouts of small models, tests).
-template <int NJ> struct QScratch {  // scratch inside the IA block (21 * NJ doubles) until q_articulate overwrites it
+template <int NJ> struct QScratch {  // scratch at QRec::SCR (21 * NJ doubles) until q_articulate overwrites it
   static constexpr int RL = 0;            // [NJ][9]
   static constexpr int RP = 9 * NJ;       // [NJ][12]: R_i (9) | p_i (3)
-  static_assert(9 * NJ + 12 * NJ <= 21 * NJ, "scratch must fit the IA block");
 };
 template <int NJ> DDPB_HD void q_chain(const ModelDev& m, double* rec) {
   using Q = QRec<NJ>;
@@ -257,12 +263,12 @@ template <int NJ> DDPB_HD void q_chain(const ModelDev& m, double* rec) {
   for (int i = 0; i < NJ; ++i) {
     double Rl[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Rl[k] = rec[Q::IA + X::RL + 9 * i + k];
+    for (int k = 0; k < 9; ++k) Rl[k] = rec[Q::SCR + X::RL + 9 * i + k];
     joint_compose(m, i, Rl, R, p);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) rec[Q::IA + X::RP + 12 * i + k] = R[k];
+    for (int k = 0; k < 9; ++k) rec[Q::SCR + X::RP + 12 * i + k] = R[k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) rec[Q::IA + X::RP + 12 * i + 9 + k] = p[k];
+    for (int k = 0; k < 3; ++k) rec[Q::SCR + X::RP + 12 * i + 9 + k] = p[k];
   }
 }
 template <int NJ> DDPB_HD void q_body(const ModelDev& m, int i, double* rec) {
@@ -270,9 +276,9 @@ template <int NJ> DDPB_HD void q_body(const ModelDev& m, int i, double* rec) {
   using X = QScratch<NJ>;
   double R[9], p[3], S[6], Y[10];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = rec[Q::IA + X::RP + 12 * i + k];
+  for (int k = 0; k < 9; ++k) R[k] = rec[Q::SCR + X::RP + 12 * i + k];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) p[k] = rec[Q::IA + X::RP + 12 * i + 9 + k];
+  for (int k = 0; k < 3; ++k) p[k] = rec[Q::SCR + X::RP + 12 * i + 9 + k];
   body_world(m, i, R, p, S, Y);
 #pragma unroll
   for (int k = 0; k < 6; ++k) rec[Q::S + 6 * i + k] = S[k];
@@ -292,8 +298,10 @@ template <int NJ> DDPB_HD void q_articulate(double* rec) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) S[k] = rec[Q::S + 6 * i + k];
     ia_add_body(IA, Y);
+    if (i > 0) {
 #pragma unroll
-    for (int k = 0; k < 21; ++k) rec[Q::IA + 21 * i + k] = IA[k];
+      for (int k = 0; k < 21; ++k) rec[Q::IA + 21 * (i - 1) + k] = IA[k];
+    }
     sym6_mul(IA, S, U);
     const double Dinv = 1.0 / dot6(S, U);
 #pragma unroll
@@ -369,7 +377,7 @@ template <int NJ, bool REC> DDPB_HD void v_task(const ModelDev& m, const double*
       const double* U = qrec + Q::U + 6 * i;
       double Iac[6];
       const double t = qrec[Q::DINV + i] * (u[i] - dot6(U, c));
-      sym6_mul(qrec + Q::IA + 21 * i, c, Iac);
+      sym6_mul(qrec + Q::IA + 21 * (i - 1), c, Iac);
 #pragma unroll
       for (int k = 0; k < 6; ++k) carry[k] = pa[k] + Iac[k] + U[k] * t;
     }
@@ -439,7 +447,7 @@ template <int NJ> DDPB_HD void v_bias(const double* qrec, int i, double qdi, dou
     // the part of the leaf-to-root sweep that does not depend on the recursion: IA_i c_i and U_i . c_i, parked in the
     // DQ block (7 doubles per body) until the derivative columns overwrite it
     double Iac[6];
-    sym6_mul(qrec + Q::IA + 21 * i, c, Iac);
+    sym6_mul(qrec + Q::IA + 21 * (i - 1), c, Iac);
 #pragma unroll
     for (int k = 0; k < 6; ++k) vrec[V::DQ + 7 * i + k] = Iac[k];
     vrec[V::DQ + 7 * i + 6] = dot6(qrec + Q::U + 6 * i, c);
