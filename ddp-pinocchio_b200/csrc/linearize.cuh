@@ -126,6 +126,18 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   ex.sync();
   DDPB_PHASE_MARK(bd, 0, pc_);
 
+  // state of evaluation point p of knot kk: the base (x, u) with its tangent perturbation(s)
+  auto point_state = [&](int kk, int p, double* q, double* qd, double* tau) {
+    const double* base = SM(kk, pl.o_base);
+    int i, j;
+    pl.point_pert(p, &i, &j);
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
+      qd[k] = base[n + k] + ((n + k == i || n + k == j) ? eps : 0.0);
+      tau[k] = base[2 * n + k] + ((2 * n + k == i || 2 * n + k == j) ? eps : 0.0);
+    }
+  };
   // Short tasks (<= 3 joints) run each narrow phase as one task per configuration / point; longer chains split them
   // into parallel and serial sub-phases (more barriers, much shorter serial parts).
   constexpr bool SPLIT = NJ >= 4;
@@ -144,8 +156,9 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     // phase 1: q-only data for every distinct configuration, as four sub-phases (rbd.cuh "q_task"): the local joint
     // rotations and the per-body world inertias are parallel over (configuration, joint / body); only the kinematic chain
     // and the articulated-inertia recursion are serial per configuration
+    // (record index fastest over the lanes in the per-(record, body) loops: records have odd strides, bodies even ones)
     for (int idx = tid; idx < nk * pl.NQ * NJ; idx += nthr) {
-      const int kk = idx / (pl.NQ * NJ), r = idx - kk * (pl.NQ * NJ), s = r / NJ, jn = r - s * NJ;
+      const int jn = idx / (nk * pl.NQ), r = idx - jn * (nk * pl.NQ), kk = r / pl.NQ, s = r - kk * pl.NQ;
       int i, j;
       pl.qset_pert(s, &i, &j);
       const double qj = SM(kk, pl.o_base)[jn] + ((jn == i || jn == j) ? eps : 0.0);
@@ -164,7 +177,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     ex.sync();
     DDPB_PHASE_MARK(bd, 9, pc_);
     for (int idx = tid; idx < nk * pl.NQ * NJ; idx += nthr) {
-      const int kk = idx / (pl.NQ * NJ), r = idx - kk * (pl.NQ * NJ), s = r / NJ, jn = r - s * NJ;
+      const int jn = idx / (nk * pl.NQ), r = idx - jn * (nk * pl.NQ), kk = r / pl.NQ, s = r - kk * pl.NQ;
       q_body<NJ>(m, jn, QR(kk, s));
     }
     ex.sync();
@@ -173,6 +186,14 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
       q_articulate<NJ>(QR(kk, s));
     }
+    // the body velocities of every recorded point (v_prefix: S and qd only) are as serial and as narrow as the
+    // articulated-inertia recursion and independent of it: they run beside it, on threads taken from the top of the CTA
+    for (int idx = nthr - 1 - tid; idx < nk * pl.NT; idx += nthr) {
+      const int kk = idx / pl.NT, p = idx - kk * pl.NT;
+      double q[NJ], qd[NJ], tau[NJ];
+      point_state(kk, p, q, qd, tau);
+      v_prefix<NJ>(QR(kk, pl.point_qset(p)), qd, VR(kk, p));
+    }
   }
   ex.sync();
   DDPB_PHASE_MARK(bd, 1, pc_);
@@ -180,28 +201,9 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   // phase 2: accelerations (and body data where derivative columns are needed) at every evaluation point.  Points with
   // a record (all of them in FD-of-Jacobians mode, the base point otherwise) run as sub-phases (rbd.cuh "v_task as
   // sub-phases"); value-only points run the whole of v_task<false> in the serial sub-phase.
-  auto point_state = [&](int kk, int p, double* q, double* qd, double* tau) {
-    const double* base = SM(kk, pl.o_base);
-    int i, j;
-    pl.point_pert(p, &i, &j);
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
-      qd[k] = base[n + k] + ((n + k == i || n + k == j) ? eps : 0.0);
-      tau[k] = base[2 * n + k] + ((2 * n + k == i || 2 * n + k == j) ? eps : 0.0);
-    }
-  };
   if (SPLIT) {
-    for (int idx = tid; idx < nk * pl.NT; idx += nthr) {
-      const int kk = idx / pl.NT, p = idx - kk * pl.NT;
-      double q[NJ], qd[NJ], tau[NJ];
-      point_state(kk, p, q, qd, tau);
-      v_prefix<NJ>(QR(kk, pl.point_qset(p)), qd, VR(kk, p));
-    }
-    ex.sync();
-    DDPB_PHASE_MARK(bd, 11, pc_);
     for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
-      const int kk = idx / (pl.NT * NJ), r = idx - kk * (pl.NT * NJ), p = r / NJ, jn = r - p * NJ;
+      const int jn = idx / (nk * pl.NT), r = idx - jn * (nk * pl.NT), kk = r / pl.NT, p = r - kk * pl.NT;
       int i, j;
       pl.point_pert(p, &i, &j);
       const double qdj = SM(kk, pl.o_base)[n + jn] + ((n + jn == i || n + jn == j) ? eps : 0.0);
@@ -250,7 +252,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     ex.sync();
     DDPB_PHASE_MARK(bd, 13, pc_);
     for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
-      const int kk = idx / (pl.NT * NJ), r = idx - kk * (pl.NT * NJ), p = r / NJ, jn = r - p * NJ;
+      const int jn = idx / (nk * pl.NT), r = idx - jn * (nk * pl.NT), kk = r / pl.NT, p = r - kk * pl.NT;
       v_force<NJ>(QR(kk, pl.point_qset(p)), jn, VR(kk, p));
     }
     ex.sync();
@@ -331,9 +333,9 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   // phase 4: da/dq = -M^-1 dtau/dq, da/dv = -M^-1 dtau/dv, already scaled into the bottom blocks of
   // fx (problem.hpp:495-502): DQ <- dt * da/dq ; DV <- dt * da/dv + I
   for (int idx = tid; idx < nk * pl.NT * 2 * NJ; idx += nthr) {
-    const int kk = idx / (pl.NT * 2 * NJ), task = idx - kk * pl.NT * 2 * NJ;
-    const int p = task / (2 * NJ), rem = task - p * 2 * NJ;
-    const int wrt = rem / NJ, c = rem - wrt * NJ;
+    const int wc = idx / (nk * pl.NT), task = idx - wc * (nk * pl.NT);  // (derivative kind, column) slowest, point fastest
+    const int kk = task / pl.NT, p = task - kk * pl.NT;
+    const int wrt = wc / NJ, c = wc - wrt * NJ;
     double* vr = VR(kk, p);
     double* colp = vr + (wrt ? V::DV : V::DQ) + c * NJ;
     const double* Mi = minv_of(kk, pl.point_qset(p));
