@@ -16,4 +16,5 @@ timeout 300 python bench.py > $O/bench_c2.json 2> $O/bench_c2.err
 timeout 300 python bench.py --workload c3 --steps 10 > $O/bench_c3.json 2> $O/bench_c3.err
 timeout 400 python bench.py --workload c5 --steps 3 > $O/bench_c5.json 2> $O/bench_c5.err
 DDPB_SUBBATCHES=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/launches_bench_c2_onestream.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench1.log 2>&1
+timeout 300 python bench.py --workload c4 --steps 5 > $O/bench_c4.json 2> $O/bench_c4.err
 echo capture done
