@@ -302,7 +302,15 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     }
   } else {
 
-    const int n_tan = pl.NT * 2 * NJ;
+#ifndef DDPB_COL_MERGED
+#define DDPB_COL_MERGED -1  // -1: by model size; 0 / 1 force one form (geometry sweeps)
+#endif
+    // short chains: one tangent task = both derivative kinds of column j at point p (col_task2 loads the body data
+    // once: 2R chain 1.62 -> 1.56 ms).  From 4 joints on the two kinds stay separate tasks: together they spill at 128
+    // registers (6R: 656 B of spill stores per thread) and measured slower (3.04 -> 3.30 ms).
+    constexpr bool MERGED = DDPB_COL_MERGED < 0 ? NJ <= 3 : DDPB_COL_MERGED != 0;
+    constexpr int KINDS = MERGED ? 1 : 2;
+    const int n_tan = pl.NT * KINDS * NJ;
     const int n_minv = MINV_EARLY ? 0 : pl.NQ * NJ;
     // tangent tasks of all knots first (j-major inside a knot), then the M^-1 tasks.  A column costs one term per body
     // k >= j, so the task list runs from expensive to cheap: every other round walks it backwards, which hands the
@@ -312,16 +320,23 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const int idx = base + ((rnd & 1) ? nthr - 1 - tid : tid);
       if (idx >= n_all) continue;
       if (idx < nk * n_tan) {
-        double col[NJ];
         // order: j slowest so that the threads of a warp share the loop bounds of col_task
-        const int j = idx / (nk * 2 * pl.NT), rem = idx - j * nk * 2 * pl.NT;
-        const int kk = rem / (2 * pl.NT), rem2 = rem - kk * 2 * pl.NT;
+        const int j = idx / (nk * KINDS * pl.NT), rem = idx - j * nk * KINDS * pl.NT;
+        const int kk = rem / (KINDS * pl.NT), rem2 = rem - kk * KINDS * pl.NT;
         const int wrt = rem2 / pl.NT, p = rem2 - wrt * pl.NT;
         double* vr = VR(kk, p);
-        col_task<NJ>(QR(kk, pl.point_qset(p)), vr, j, wrt, col);
-        double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
+        if (MERGED) {
+          double cq[NJ], cv[NJ];
+          col_task2<NJ>(QR(kk, pl.point_qset(p)), vr, j, cq, cv);
 #pragma unroll
-        for (int k = 0; k < NJ; ++k) dst[k] = col[k];
+          for (int k = 0; k < NJ; ++k) { vr[V::DQ + j * NJ + k] = cq[k]; vr[V::DV + j * NJ + k] = cv[k]; }
+        } else {
+          double col[NJ];
+          col_task<NJ>(QR(kk, pl.point_qset(p)), vr, j, wrt, col);
+          double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
+#pragma unroll
+          for (int k = 0; k < NJ; ++k) dst[k] = col[k];
+        }
       } else {
         minv_task(idx - nk * n_tan);
       }

@@ -643,6 +643,74 @@ template <int NJ> DDPB_HD void col_task(const double* qrec, const double* vrec, 
     if (i < j) out[i] = dot6(qrec + Q::S + 6 * i, G);
 }
 
+// Both derivative kinds of column j in one task: d tau/d q_j -> out_q, d tau/d qdot_j -> out_v.  The same arithmetic in the
+// same order as two col_task calls (bit-identical results); the body data (v_k, h_k, Y_k, S_k) is loaded once for both.
+template <int NJ> DDPB_HD void col_task2(const double* qrec, const double* vrec, int j, double* out_q /*[NJ]*/, double* out_v /*[NJ]*/) {
+  using Q = QRec<NJ>;
+  using V = VRec<NJ>;
+  double Sj[6], vj[6], d[6], al[6];
+  {
+    double aj[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { Sj[k] = qrec[Q::S + 6 * j + k]; vj[k] = vrec[V::V + 6 * j + k]; aj[k] = vrec[V::A + 6 * j + k]; }
+    crm(vj, Sj, d);
+    crm(aj, Sj, al);
+  }
+  double Gq[6] = {0, 0, 0, 0, 0, 0}, Gv[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = NJ - 1; k >= 0; --k) {
+    if (k < j) continue;
+    double Yk[10], Sk[6], vk[6], hk[6], dv[6];
+#pragma unroll
+    for (int e = 0; e < 10; ++e) Yk[e] = qrec[Q::Y + 10 * k + e];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { Sk[e] = qrec[Q::S + 6 * k + e]; vk[e] = vrec[V::V + 6 * k + e]; hk[e] = vrec[V::H + 6 * k + e]; dv[e] = vk[e] - vj[e]; }
+    {  // wrt q_j: alpha = a_j x S_j, beta = gamma = d
+      double t[6], g1[6], g2[6], Yg[6], g3[6];
+      crm(d, dv, t);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) t[e] += al[e];
+      y_mul(Yk, t, g1);
+      crf(d, hk, g2);
+      y_mul(Yk, d, Yg);
+      crf(vk, Yg, g3);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) Gq[e] += g1[e] + g2[e] + g3[e];
+      out_q[k] = dot6(Sk, Gq);
+    }
+    {  // wrt qdot_j: alpha = d, beta = gamma = S_j
+      double t[6], g1[6], g2[6], Yg[6], g3[6];
+      crm(Sj, dv, t);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) t[e] += d[e];
+      y_mul(Yk, t, g1);
+      crf(Sj, hk, g2);
+      y_mul(Yk, Sj, Yg);
+      crf(vk, Yg, g3);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) Gv[e] += g1[e] + g2[e] + g3[e];
+      out_v[k] = dot6(Sk, Gv);
+    }
+  }
+  {
+    double Fj[6], x[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) Fj[e] = vrec[V::F + 6 * j + e];
+    crf(Sj, Fj, x);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) Gq[e] += x[e];
+  }
+#pragma unroll
+  for (int i = 0; i < NJ; ++i)
+    if (i < j) {
+      double Si[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) Si[e] = qrec[Q::S + 6 * i + e];
+      out_q[i] = dot6(Si, Gq);
+      out_v[i] = dot6(Si, Gv);
+    }
+}
+
 // col_task split by body for the narrow case (one point per knot needs columns, value-based Hessians): col_term is the
 // contribution g_k of one body to column (j, wrt), col_reduce the suffix sums and projections -- the same arithmetic
 // in the same order as col_task, with 2 * NJ(NJ+1)/2 terms in parallel instead of 2 * NJ columns.
