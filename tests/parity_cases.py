@@ -93,6 +93,49 @@ def check_linearization(make, w):
     bt.close()
 
 
+def planar_2r_closed_form(m, q, v, tau):
+    """Textbook equations of motion of a planar two-link arm (e.g. Spong, Hutchinson, Vidyasagar, "Robot Modeling and
+    Control", the planar elbow manipulator), angles measured from the hanging position:
+        M11 = m1 lc1^2 + m2 (l1^2 + lc2^2 + 2 l1 lc2 cos q2) + I1 + I2,  M12 = m2 (lc2^2 + l1 lc2 cos q2) + I2,
+        M22 = m2 lc2^2 + I2,  h = -m2 l1 lc2 sin q2,
+        tau1 = M11 a1 + M12 a2 + h (2 v1 v2 + v2^2) + g1,   tau2 = M12 a1 + M22 a2 - h v1^2 + g2,
+        g1 = (m1 lc1 + m2 l1) g sin q1 + m2 lc2 g sin(q1 + q2),  g2 = m2 lc2 g sin(q1 + q2).
+    Written from the published formulas only -- no spatial algebra, nothing shared with the oracle or the kernels."""
+    m1, m2 = m.mass
+    l1 = -m.placement_trans[1][2]
+    lc1, lc2 = -m.com[0][2], -m.com[1][2]
+    I1, I2 = m.inertia[0][3], m.inertia[1][3]          # yy: about the joint axis direction, at the COM
+    g = -m.gravity[2]
+    c2, s2 = np.cos(q[1]), np.sin(q[1])
+    M = np.array([[m1 * lc1**2 + m2 * (l1**2 + lc2**2 + 2 * l1 * lc2 * c2) + I1 + I2, m2 * (lc2**2 + l1 * lc2 * c2) + I2],
+                  [m2 * (lc2**2 + l1 * lc2 * c2) + I2, m2 * lc2**2 + I2]])
+    h = -m2 * l1 * lc2 * s2
+    cor = np.array([h * (2 * v[0] * v[1] + v[1]**2), -h * v[0]**2])
+    grav = np.array([(m1 * lc1 + m2 * l1) * g * np.sin(q[0]) + m2 * lc2 * g * np.sin(q[0] + q[1]), m2 * lc2 * g * np.sin(q[0] + q[1])])
+    return np.linalg.solve(M, tau - cor - grav), M
+
+
+def check_2r_vs_textbook(make, w):
+    """f(x,u) and f_u = dt M^-1 of the 2R chain records against the published closed-form dynamics of the planar
+    double pendulum (planar_2r_closed_form) -- an external pin that involves neither the oracle
+    nor any spatial algebra."""
+    g, bt, us, _, _ = setup(make, w)
+    xs, _ = bt.get_trajectory()
+    bt.compute_derivatives()
+    D = bt.get_derivatives(["f_val", "fu"])
+    m = w.model
+    for b in range(w.B):
+        for t in range(w.T):
+            f = np.asarray(D["f_val"][b]).reshape(w.T, 4)[t]
+            fu = np.asarray(D["fu"][b]).reshape(w.T, 2, 4)[t].T          # 4 x 2, stored column-major
+            q, v = xs[b].reshape(w.T + 1, 4)[t, :2], xs[b].reshape(w.T + 1, 4)[t, 2:]
+            a, M = planar_2r_closed_form(m, q, v, us[b].reshape(w.T, 2)[t])
+            ref = np.concatenate([q + w.dt * v, v + w.dt * a])           # dynamics_t::eval_to, problem.hpp:441-461
+            assert relerr(f, ref) < 1e-12, (b, t, relerr(f, ref))
+            assert np.abs(fu[:2]).max() == 0.0 and relerr(fu[2:], w.dt * np.linalg.inv(M)) < 1e-12
+    bt.close()
+
+
 def check_tensors_vs_quad(make, w):
     """The product's FD tensors are as close to the __float128 oracle as the double oracle's are."""
     g, bt, us, orcs, _ = setup(make, w)

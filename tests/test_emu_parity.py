@@ -34,6 +34,10 @@ def test_tensors_vs_quad(tag, w):
     pc.check_tensors_vs_quad(make, w)
 
 
+def test_2r_chain_vs_textbook_closed_form():
+    pc.check_2r_vs_textbook(make, pc.S.workload("c2", B=3, T=8))
+
+
 @pytest.mark.parametrize("name,T,iters", [("c2", 40, 6), ("c3", 20, 5), ("c4", 12, 4), ("c5", 10, 3)])
 def test_solve(name, T, iters):
     w = pc.S.workload(name, B=3, T=T)

@@ -11,6 +11,7 @@ import ddpb_loader
 
 P = ddpb_loader.load()
 import oracle_lib as ol  # noqa: E402
+from parity_cases import planar_2r_closed_form  # noqa: E402
 
 S = P.synthetic
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -48,6 +49,22 @@ def test_aba_derivatives_vs_quad_central_differences(mk):
             fd[:, j] = (o.aba(*ap, prec=1) - o.aba(*am, prec=1)) / (2 * h)
         assert np.abs(J - fd).max() <= 2e-8 * max(1.0, np.abs(J).max())
     assert np.abs(dt - dt.T).max() < 1e-12 * np.abs(dt).max()  # full symmetric M^-1 (pinocchio_model.ipp:391-399)
+
+
+def test_aba_2r_chain_vs_textbook_closed_form():
+    """External pin of the rigid-body arithmetic on the bench model (BASELINE.json configs[1]): the oracle's ABA and
+    M^-1 against the published closed-form dynamics of the planar double pendulum."""
+    m = P.models.chain_2r()
+    assert np.allclose(m.axis, [[0, 1, 0], [0, 1, 0]]) and np.allclose(m.com[:, :2], 0) and np.allclose(m.placement_trans[:, :2], 0)
+    o = ol.Oracle(m, 4)
+    rng = np.random.RandomState(11)
+    for _ in range(20):
+        q, v, tau = rng.uniform(-3, 3, 2), rng.uniform(-2, 2, 2), rng.uniform(-5, 5, 2)
+        a_ref, M = planar_2r_closed_form(m, q, v, tau)
+        a = o.aba(q, v, tau)
+        assert np.abs(a - a_ref).max() < 1e-12 * max(1.0, np.abs(a_ref).max())
+        _, _, minv = o.d_aba(q, v, tau)
+        assert np.abs(minv - np.linalg.inv(M)).max() < 1e-12 * np.abs(minv).max()
 
 
 def test_frame_jacobian_conventions():
