@@ -17,11 +17,13 @@ constexpr int KNJ = DDPB_NJ;
 // throughput-bound linearization of another and a straggling problem delays only its own sub-batch.
 #if DDPB_NJ > 0
 // grid: (knots t0..t1-1) x (groups of `kpb` consecutive problems); all knots of a launch have the same ne
-// FD-of-Jacobians kernels are compiled for 512 resident threads per SM (128 registers): 4 CTAs of <= 128 threads for
-// small models, 2 CTAs of 256 threads (two knots each, so the narrow q / v phases serve two knots) from 5 joints on;
-// the value-based mode has 1 + n + n(n-1)/2 evaluation points per knot and runs one 256-thread CTA per SM: two would fit
-// the shared memory (its records carry no per-configuration M^-1) but at 128 registers the value-only ABA tasks spill
-// ~1.6 KB per thread and ncu shows 6x the algorithmic DRAM traffic for a 5 % gain (DDPB_LIN_LB_BLOCKS_FDV=2).
+// FD-of-Jacobians kernels are compiled for 512 resident threads per SM (128 registers): CTAs of <= 128 threads for small
+// models (2R chain: 16 knots each, 3 per SM by shared memory), 2 CTAs of 256 threads from 5 joints on (6R arm: three knots
+// each, so the narrow serial sub-phases serve three knots and an SM holds six).  The value-based mode has
+// 1 + n + n(n-1)/2 evaluation points per knot and is compiled for 255 registers; it is LAUNCHED with 128 threads from 5
+// joints on, so two CTAs share an SM and overlap each other's narrow phases (7R: 26.0 -> 16.1 ms).  At 128 registers its
+// value-only ABA tasks spill ~1.6 KB per thread and ncu shows 6x the algorithmic DRAM traffic (DDPB_LIN_LB_BLOCKS_FDV=2).
+// The launch geometry (threads, knots per CTA) is chosen in ddpb_batch_create (ddpb_capi.cu).
 #ifndef DDPB_LIN_LB_THREADS
 #define DDPB_LIN_LB_THREADS (DDPB_NJ >= 5 ? 256 : 128)
 #define DDPB_LIN_LB_BLOCKS (DDPB_NJ >= 5 ? 2 : 4)

@@ -1,5 +1,5 @@
-// linearize.cuh -- per-knot linearization: one CTA computes the complete derivative record of
-// one (problem, knot): cost derivatives, Euler-discretised dynamics value / Jacobians / finite-
+// linearize.cuh -- per-knot linearization: one CTA computes the complete derivative records of a
+// group of (problem, knot) pairs of one time index: cost derivatives, Euler-discretised dynamics value / Jacobians / finite-
 // difference Hessians, and the doubly time-advanced equality constraint with its derivatives.
 //
 // Restates problem_t::compute_derivatives (/root/reference/include/ddp/problem.hpp:956-997) with
