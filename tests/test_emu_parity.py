@@ -38,6 +38,11 @@ def test_2r_chain_vs_textbook_closed_form():
     pc.check_2r_vs_textbook(make, pc.S.workload("c2", B=3, T=8))
 
 
+@pytest.mark.parametrize("name", ["c3", "c5"])
+def test_arm_records_vs_lagrangian_mechanics(name):
+    pc.check_vs_lagrangian(make, pc.S.workload(name, B=2, T=4))
+
+
 @pytest.mark.parametrize("name,T,iters", [("c2", 40, 6), ("c3", 20, 5), ("c4", 12, 4), ("c5", 10, 3)])
 def test_solve(name, T, iters):
     w = pc.S.workload(name, B=3, T=T)
