@@ -28,11 +28,10 @@
 namespace ddpb {
 
 template <int NJ> struct BwdSmem {
-  static constexpr int nd = 2 * NJ, nu = NJ;
+  static constexpr int n = NJ, nd = 2 * NJ, nu = NJ;
   static constexpr int NTEN = nd * nd + nu * nd + nu * nu;  // Q_xx | Q_ux | Q_uu task list
-  // head of the slab record, copied verbatim: lx | lu | lxx | lux | luu | f | fx | fu  (batch.cuh rec_layout)
-  static constexpr int h_lx = 0, h_lu = h_lx + nd, h_lxx = h_lu + nu, h_lux = h_lxx + nd * nd, h_luu = h_lux + nu * nd,
-                       h_f = h_luu + nu * nu, h_fx = h_f + nd, h_fu = h_fx + nd * nd, NHEAD = h_fu + nd * nu;
+  // stored head of the slab record without f, copied verbatim: fx_B[n x nd] | fu_B[n x nu] | lu[nu]  (batch.cuh rec_layout)
+  static constexpr int h_fx = 0, h_fu = h_fx + n * nd, h_lu = h_fu + n * nu, NHEAD = h_lu + nu;  // NHEAD is even
   static constexpr int even(int x) { return (x + 1) & ~1; }
   static constexpr int RS = NJ <= 6 ? 32 : 16;  // tensor elements per staging round and warp
   static constexpr int head = 0, head2 = even(head + NHEAD), VxxR = even(head2 + NHEAD), Vx = VxxR + nd * nd, VF = even(Vx + nd), VU = VF + nd * nd,
@@ -41,13 +40,14 @@ template <int NJ> struct BwdSmem {
                        L = even(Wf + NTEN), dinv = L + nu * nu, kk = even(dinv + nu), KK = even(kk + nu),
                        eqv = even(KK + nu * nd), eqx = eqv + MAXE, equ = eqx + MAXE * nd, pe = equ + MAXE * nu,
                        pex = pe + MAXE, tmp = pex + MAXE * nd, tmp2 = tmp + MAXE, flags = tmp2 + MAXE * nd,
-                       zero = flags + 2,  // one double that stays 0.0 (tasks without a tensor term add it)
-                       mbar = zero + 2,   // the mbarrier of the record staging (8 bytes, 16-byte slot)
+                       cst = even(flags + 2),  // constants: 0.0, c, 1.0, dt (operands of the structural entries)
+                       mbar = cst + 4,         // the mbarrier of the record staging (8 bytes, 16-byte slot)
                        stage = even(mbar + 2),  // device: NW warp-private staging buffers of RS * nd doubles
                        SIZE = stage;
+  static constexpr int c_zero = cst, c_c = cst + 1, c_one = cst + 2, c_dt = cst + 3;
   static constexpr int size_for(int threads) { return SIZE + (threads >= 32 ? (threads / 32) * RS * nd : 0); }
-  // head offset of fx must be even for the 16-byte inner products: nd + nu + nd*nd + nu*nd + nu*nu + nd = nu (mod 2)
-  static constexpr bool head_aligned = (h_fx % 2) == 0 && (h_fu % 2) == 0;
+  // 16-byte inner products need even run lengths and even offsets: the stored columns have n rows
+  static constexpr bool head_aligned = (n % 2) == 0;
 };
 
 // threads per problem on the device
@@ -177,15 +177,47 @@ template <int NU> DDPB_HD bool chol_warp(double* A, double* dinv, int lane) {
 #endif
 }
 
-// BT = compile-time thread count of the executor (BwdGeom<NJ>::BT on the device, 1 in the CPU emulation)
+template <int V> struct IntC { static constexpr int value = V; };
+
+// sum_k vx[k] * f3[k] over a run of RL doubles with two interleaved partial sums (even / odd k); 16-byte loads on the
+// device when the run is even-sized and 16-byte aligned (ALIGNED).  Host and device use the same association.
+template <int RL, bool ALIGNED> DDPB_HD double contract_run(const double* vx, const double* f3) {
+  double a0 = 0.0, a1 = 0.0;
+#if defined(__CUDA_ARCH__)
+  if (ALIGNED && (RL % 2) == 0) {
+    const double2* f2 = reinterpret_cast<const double2*>(f3);
+    const double2* x2 = reinterpret_cast<const double2*>(vx);
+#pragma unroll
+    for (int k = 0; k < RL / 2; ++k) {
+      const double2 v = f2[k], x = x2[k];
+      a0 += x.x * v.x;
+      a1 += x.y * v.y;
+    }
+    return a0 + a1;
+  }
+#endif
+#pragma unroll
+  for (int k = 0; k < RL; k += 2) {
+    a0 += vx[k] * f3[k];
+    if (k + 1 < RL) a1 += vx[k + 1] * f3[k + 1];
+  }
+  return a0 + a1;
+}
+
+// BT = compile-time thread count of the executor (BwdGeom<NJ>::BT on the device, 1 in the CPU emulation).
+// Record-major slabs only (chains of >= 3 joints on the device; backward_tpp.cuh covers the element-major ones).
 template <int NJ, int BT, class Ex>
 DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& ex) {
-  constexpr int nd = 2 * NJ, nu = NJ, nx = 2 * NJ;
+  constexpr int n = NJ, nd = 2 * NJ, nu = NJ, nx = 2 * NJ;
   using S = BwdSmem<NJ>;
   constexpr int nQxx = nd * nd, nQux = nu * nd, NTEN = S::NTEN;
-  constexpr bool AL = S::head_aligned;  // fx / fu columns of the head copy start on 16-byte boundaries
+  constexpr bool AL = S::head_aligned;  // stored columns (n rows) start on 16-byte boundaries and have even length
   const int B = bd.B, T = bd.T;
   const int tid = ex.tid();
+  // stored tensors (batch.cuh): FD-of-Jacobians mode keeps rows k >= n of f_xx | f_ux(:, :, i < n) only -- n doubles per
+  // (j, i) pair, contracted with V_x[n..] -- value-based mode keeps f_xx | f_ux | f_uu dense
+  const bool dense = bd.hess_mode == HESS_FD_VALUES;
+  const int NEL = dense ? NTEN : nd * nd + nu * n;  // tensor elements (k-runs) of a record, contiguous from L.fxx
   // a one-warp group needs no CTA barrier: warp-level synchronisation orders its shared-memory traffic
   auto bsync = [&]() { if (BT == 32) ex.sync_warp(); else ex.sync(); };
   double mu = bd.scal[(size_t)S_MU * B + b];
@@ -195,39 +227,55 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
 #define FOR_ELEMS(e, N) _Pragma("unroll") for (int u_ = 0; u_ < ((N) + BT - 1) / BT; ++u_) if (const int e = tid + u_ * BT; e < (N))
   // Per-thread task descriptors (shared-memory offsets of the operands of every inner product this thread owns),
   // computed once: the knot loop then runs one branch-free code path per phase instead of re-deriving row / column /
-  // block from the task index at every knot.
+  // block from the task index at every knot.  Every product with f_x / f_u is "constant rows + stored rows":
+  //   sum_k f(k, r) y(k) = y(r) [r < n]  or  dt y(r - n) [r >= n]  (f_x; nothing for f_u)  +  sum_{k >= n} f_B(k - n, r) y(k)
+  // so a descriptor names the stored column (a), the run of y it meets (b), the top element of y and its scale (1 or dt).
   constexpr int NB = nd * nd + nd * nu;    // phase B: VF | VU
   constexpr int NC = NTEN + nd + nu;       // phase C: Q_xx | Q_ux | Q_uu | Q_x | Q_u
   constexpr int NF = nd * nd + nd;         // phase F: V_xx | V_x
   // PRE: descriptors live in registers for the whole kernel (small models, where the register budget of a resident
   // wave allows it); otherwise they are re-derived at every use.
   constexpr bool PRE = NJ <= 5 || BT == 1;
-  auto mkB = [&](int e) -> unsigned {  // a | b << 16
-    const int r = e % nd, c = e / nd;  // c runs over the columns of f_x, then of f_u (adjacent in the head)
-    return (unsigned)(S::VxxR + r * nd) | ((unsigned)(S::h_fx + c * nd) << 16);  // b relative to the current head buffer
+  auto mkB = [&](int e, unsigned& d0, unsigned& d1) {  // a | b << 16 ; top | scale << 16  (b relative to the current head buffer)
+    const int r = e % nd, c = e / nd;  // c runs over the columns of f_x, then of f_u
+    int bo, top = S::c_zero, ts = S::c_one;
+    if (c < nd) {
+      bo = S::h_fx + c * n;
+      if (c < n) top = S::VxxR + r * nd + c; else { top = S::VxxR + r * nd + (c - n); ts = S::c_dt; }
+    } else {
+      bo = S::h_fu + (c - nd) * n;
+    }
+    d0 = (unsigned)(S::VxxR + r * nd + n) | ((unsigned)bo << 16);
+    d1 = (unsigned)top | ((unsigned)ts << 16);
   };
-  auto mkC = [&](int e, unsigned& d0, unsigned& d1, unsigned& d2) {  // a|b , l|w , dst|ldst (bit 15 of ldst: diagonal)
-    int a, bo, l, w = S::zero, dst, ldst = 0x7fff, diag = 0;
+  // a|b , l|w , dst|ldst (bit 15 of ldst: diagonal), top|scale.  a relative to the current head buffer; bit 15 of l: l is
+  // relative to the head buffer too (l_u), otherwise an absolute offset (constants)
+  auto mkC = [&](int e, unsigned& d0, unsigned& d1, unsigned& d2, unsigned& d3) {
+    int a, bo, l = S::c_zero, w = S::c_zero, dst, ldst = 0x7fff, diag = 0, top = S::c_zero, ts = S::c_one;
     if (e < nQxx) {
       const int r = e % nd, c = e / nd;
-      a = S::h_fx + r * nd; bo = S::VF + c * nd; l = S::h_lxx + e; w = S::Wf + e; dst = S::Qxx + e;
+      a = S::h_fx + r * n; bo = S::VF + c * nd + n; w = S::Wf + e; dst = S::Qxx + e;
+      if (r < n) top = S::VF + c * nd + r; else { top = S::VF + c * nd + (r - n); ts = S::c_dt; }
     } else if (e < nQxx + nQux) {
-      const int ee = e - nQxx, r = ee % nu, c = ee / nu;
-      a = S::h_fu + r * nd; bo = S::VF + c * nd; l = S::h_lux + ee; w = S::Wf + e; dst = S::Qux + ee;
+      const int ee = e - nQxx, c = ee / nu, r = ee % nu;
+      a = S::h_fu + r * n; bo = S::VF + c * nd + n; w = S::Wf + e; dst = S::Qux + ee;
     } else if (e < NTEN) {
       const int ee = e - nQxx - nQux, r = ee % nu, c = ee / nu;
-      a = S::h_fu + r * nd; bo = S::VU + c * nd; l = S::h_luu + ee; w = S::Wf + e; dst = S::Quu + ee;
+      a = S::h_fu + r * n; bo = S::VU + c * nd + n; w = S::Wf + e; dst = S::Quu + ee;
+      l = r == c ? S::c_c : S::c_zero;  // l_uu = c I
       ldst = S::L + ee; diag = r == c;
     } else if (e < NTEN + nd) {
       const int i = e - NTEN;
-      a = S::h_fx + i * nd; bo = S::Vx; l = S::h_lx + i; dst = S::Qx + i;
+      a = S::h_fx + i * n; bo = S::Vx + n; dst = S::Qx + i;
+      if (i < n) top = S::Vx + i; else { top = S::Vx + (i - n); ts = S::c_dt; }
     } else {
       const int i = e - NTEN - nd;
-      a = S::h_fu + i * nd; bo = S::Vx; l = S::h_lu + i; dst = S::Qu + i;
+      a = S::h_fu + i * n; bo = S::Vx + n; l = (S::h_lu + i) | 0x8000; dst = S::Qu + i;
     }
-    d0 = (unsigned)a | ((unsigned)bo << 16);  // a and l relative to the current head buffer
+    d0 = (unsigned)a | ((unsigned)bo << 16);
     d1 = (unsigned)l | ((unsigned)w << 16);
     d2 = (unsigned)dst | ((unsigned)(ldst | (diag << 15)) << 16);
+    d3 = (unsigned)top | ((unsigned)ts << 16);
   };
   auto mkF = [&](int e, unsigned& d0, unsigned& d1) {  // a|b , q|dst
     if (e < nd * nd) {
@@ -241,13 +289,15 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
     }
   };
   constexpr int PB = PRE ? (NB + BT - 1) / BT : 1, PC = PRE ? (NC + BT - 1) / BT : 1, PF = PRE ? (NF + BT - 1) / BT : 1;
-  unsigned dB[PB], dC0[PC], dC1[PC], dC2[PC], dF0[PF], dF1[PF];
+  unsigned dB0[PB], dB1[PB], dC0[PC], dC1[PC], dC2[PC], dC3[PC], dF0[PF], dF1[PF];
   if (PRE) {
-    FOR_ELEMS(e, NB) dB[PRE ? u_ : 0] = mkB(e);
-    FOR_ELEMS(e, NC) mkC(e, dC0[PRE ? u_ : 0], dC1[PRE ? u_ : 0], dC2[PRE ? u_ : 0]);
+    FOR_ELEMS(e, NB) mkB(e, dB0[PRE ? u_ : 0], dB1[PRE ? u_ : 0]);
+    FOR_ELEMS(e, NC) mkC(e, dC0[PRE ? u_ : 0], dC1[PRE ? u_ : 0], dC2[PRE ? u_ : 0], dC3[PRE ? u_ : 0]);
     FOR_ELEMS(e, NF) mkF(e, dF0[PRE ? u_ : 0], dF1[PRE ? u_ : 0]);
   }
-  if (tid == 0) { sm[S::zero] = 0.0; sm[S::zero + 1] = 0.0; }
+  if (tid == 0) { sm[S::c_zero] = 0.0; sm[S::c_c] = bd.c; sm[S::c_one] = 1.0; sm[S::c_dt] = bd.dt; }
+  // tensor terms that do not exist in FD-of-Jacobians mode (f_ux slices i >= n, f_uu) stay exact zeros
+  FOR_ELEMS(e, NTEN) sm[S::Wf + e] = 0.0;
   unsigned tma_phase = 0;     // parity of the staging mbarrier's current phase
   bool tma_pending = false;   // a prefetch has been issued and not yet waited for
 #if defined(__CUDA_ARCH__) && DDPB_BWD_TMA
@@ -259,56 +309,56 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
     FOR_ELEMS(e, nd * nd + nd) sm[S::VxxR + e] = 0.0;
     bsync();
     bool failed = false;
-    // software pipeline: what knot t needs first -- the head of its record (registers) and round 0 of every warp's
-    // tensor share (warp-private staging buffer, cp.async) -- is fetched while knot t+1 is being processed
+    // software pipeline: what knot t needs first -- the head of its record and round 0 of every warp's tensor share
+    // (warp-private staging buffer) -- is fetched while knot t+1 is being processed
     int hcur = 0;  // which head buffer holds the knot being processed
 #if defined(__CUDA_ARCH__)
-    constexpr int RS = S::RS, NW = BT / 32, EW = (NTEN + NW - 1) / NW, CPE = nd / 2;  // CPE: 16-byte chunks per tensor element
+    constexpr int RS = S::RS, NW = BT / 32;
+    const int EW = (((NEL + NW - 1) / NW) + 1) & ~1;  // elements per warp, even: every warp's share starts 16-byte aligned
     const int warp = tid >> 5, lane = tid & 31;
     double* stg = sm + S::stage + warp * RS * nd;
-    const int e_beg = warp * EW, e_end = (warp + 1) * EW < NTEN ? (warp + 1) * EW : NTEN;
+    const int e_beg = warp * EW < NEL ? warp * EW : NEL, e_end = (warp + 1) * EW < NEL ? (warp + 1) * EW : NEL;
 #endif
     // fetch what knot tp needs first into the buffers that are idle while the current knot is processed: the head of
     // its record -> the other head buffer, round 0 of every warp's tensor share -> the warp's staging buffer.
     // TMA path: thread 0 issues one bulk copy per buffer, all completing on the CTA's mbarrier; it is called after a
     // barrier that follows the last read of the target buffers (the staging buffers were also written with ordinary
-    // stores, hence the proxy fence).
+    // stores, hence the proxy fence).  Copies are whole 16-byte units: a round with an odd number of doubles takes the
+    // next double of the (even-sized) record along.
     auto prefetch = [&](int tp, int hnext) {
-      const RecLayout Lp = rec_layout(nd, nu, nx, bd.ne[tp]);
+      const RecLayout Lp = rec_layout(n, bd.ne[tp], bd.hess_mode);
       const double* recp = slab_rec(bd, tp, b, Lp.size);
       double* hdst = sm + (hnext ? S::head2 : S::head);
 #if defined(__CUDA_ARCH__)
+      const int RL = Lp.rt;
 #if DDPB_BWD_TMA
       if (tid == 0) {
         unsigned bytes = S::NHEAD * 8;
 #pragma unroll
         for (int wq = 0; wq < NW; ++wq) {
-          const int eb = wq * EW, ee = (wq + 1) * EW < NTEN ? (wq + 1) * EW : NTEN;
+          const int eb = wq * EW, ee = (wq + 1) * EW < NEL ? (wq + 1) * EW : NEL;
           const int nr = ee - eb < RS ? ee - eb : RS;
-          if (nr > 0) bytes += (unsigned)(nr * nd * 8);
+          if (nr > 0) bytes += (unsigned)(((nr * RL + 1) & ~1) * 8);
         }
         fence_proxy_async();
         mbar_expect_tx(sm + S::mbar, bytes);
-        tma_bulk_g2s(hdst, recp, S::NHEAD * 8, sm + S::mbar);
+        tma_bulk_g2s(hdst, recp + Lp.fx, S::NHEAD * 8, sm + S::mbar);
 #pragma unroll
         for (int wq = 0; wq < NW; ++wq) {
-          const int eb = wq * EW, ee = (wq + 1) * EW < NTEN ? (wq + 1) * EW : NTEN;
+          const int eb = wq * EW, ee = (wq + 1) * EW < NEL ? (wq + 1) * EW : NEL;
           const int nr = ee - eb < RS ? ee - eb : RS;
-          if (nr > 0) tma_bulk_g2s(sm + S::stage + wq * RS * nd, recp + Lp.fxx + (size_t)eb * nd, (unsigned)(nr * nd * 8), sm + S::mbar);
+          if (nr > 0) tma_bulk_g2s(sm + S::stage + wq * RS * nd, recp + Lp.fxx + (size_t)eb * RL, (unsigned)(((nr * RL + 1) & ~1) * 8), sm + S::mbar);
         }
       }
 #else
-      FOR_ELEMS(c, S::NHEAD / 2) cp_async16(hdst + 2 * c, recp + 2 * c);
+      FOR_ELEMS(c, S::NHEAD / 2) cp_async16(hdst + 2 * c, recp + Lp.fx + 2 * c);
       const int ne_round = e_end - e_beg < RS ? e_end - e_beg : RS;
-      const double2* src = reinterpret_cast<const double2*>(recp + Lp.fxx + (size_t)e_beg * nd);
-#pragma unroll
-      for (int i = 0; i < (RS * CPE + 31) / 32; ++i) {
-        const int c = lane + 32 * i;
-        if (c < ne_round * CPE) cp_async16(reinterpret_cast<double2*>(stg) + c, src + c);
-      }
+      const int nch = (ne_round * RL + 1) / 2;
+      const double2* src = reinterpret_cast<const double2*>(recp + Lp.fxx + (size_t)e_beg * RL);
+      for (int c = lane; c < nch; c += 32) cp_async16(reinterpret_cast<double2*>(stg) + c, src + c);
 #endif
 #else
-      for (int e = 0; e < S::NHEAD; ++e) hdst[e] = recp[e];
+      for (int e = 0; e < S::NHEAD; ++e) hdst[e] = recp[Lp.fx + e];
 #endif
     };
     // wait for the staged data of the knot about to be processed
@@ -323,36 +373,41 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
 #endif
 #endif
     };
-    if (tma_pending) staged_wait();  // a restarted pass still has the aborted knot's prefetch in flight
+    if (tma_pending) { staged_wait(); tma_pending = false; }  // a restarted pass still has the aborted knot's prefetch in flight
     bsync();
     prefetch(T - 1, hcur);
     tma_pending = true;
     for (int t = T - 1; t >= 0; --t) {
       DDPB_PHASE_START(bd, pc_);
       const int ne = bd.ne[t], eo = bd.eq_off[t];
-      const RecLayout L = rec_layout(nd, nu, nx, ne);
+      const RecLayout L = rec_layout(n, ne, bd.hess_mode);
       const double* rec = slab_rec(bd, t, b, L.size);
       // ---- phase A: head of the record (prefetched) ; tensors -> V_x contraction ----------------------------------------
       const double* hd = sm + (hcur ? S::head2 : S::head);
       double xorg = 0.0;
       if (tid < nx) xorg = bd.xs[((size_t)t * nx + tid) * B + b];
       {
+        // W(e) = sum_k V_x[r0 + k] T_e[k] for every stored tensor element e (a run of RL doubles at L.fxx + e RL)
+        auto contract = [&](auto rl_c) {
+          constexpr int RL = decltype(rl_c)::value;
+          const double* vx = sm + S::Vx + (RL == nd ? 0 : n);
 #if defined(__CUDA_ARCH__)
-        // Each warp owns a contiguous range of the Q_xx | Q_ux | Q_uu task list (= a contiguous piece of the adjacent
-        // fxx | fux | fuu blocks) and streams it in rounds of RS elements: fully coalesced 16-byte loads (consecutive
-        // lanes -> consecutive chunks) into the warp's staging buffer, then every lane contracts the k-run of its own
-        // element with V_x.  Only __syncwarp is needed: the buffer is private to the warp.  Round 0 was fetched
-        // asynchronously during the previous knot; the loads of round r+1 are in flight while round r is contracted.
-        {
-          constexpr int LPR = (RS * CPE + 31) / 32;  // 16-byte loads per lane and round
+          // Each warp owns a contiguous range of the element list (= a contiguous piece of the adjacent tensor blocks) and
+          // streams it in rounds of RS elements: fully coalesced 16-byte loads (consecutive lanes -> consecutive chunks)
+          // into the warp's staging buffer, then every lane contracts the k-run of its own element with V_x.  Only
+          // __syncwarp is needed: the buffer is private to the warp.  Round 0 was fetched asynchronously during the
+          // previous knot; the loads of round r+1 are in flight while round r is contracted.
+          constexpr int LPR = (RS * RL / 2 + 31) / 32;  // 16-byte loads per lane and round
+          constexpr bool RAL = (RL % 2) == 0;
           double2 buf[LPR];
           auto load_round = [&](int e0) {
             const int ne_round = e_end - e0 < RS ? e_end - e0 : RS;
-            const double2* src = reinterpret_cast<const double2*>(rec + L.fxx + (size_t)e0 * nd);
+            const int nch = (ne_round * RL + 1) / 2;
+            const double2* src = reinterpret_cast<const double2*>(rec + L.fxx + (size_t)e0 * RL);
 #pragma unroll
             for (int i = 0; i < LPR; ++i) {
               const int c = lane + 32 * i;
-              if (c < ne_round * CPE) buf[i] = src[c];
+              if (c < nch) buf[i] = src[c];
             }
           };
           if (e_beg + RS < e_end) load_round(e_beg + RS);
@@ -362,40 +417,25 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
           DDPB_PHASE_MARK(bd, 14, pc_);
           for (int e0 = e_beg; e0 < e_end; e0 += RS) {
             const int ne_round = e_end - e0 < RS ? e_end - e0 : RS;
-            if (lane < ne_round) {
-              const double2* mine = reinterpret_cast<const double2*>(stg + lane * nd);
-              const double2* vx2 = reinterpret_cast<const double2*>(sm + S::Vx);  // broadcast reads
-              double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-              for (int k = 0; k < CPE; ++k) {
-                const double2 v = mine[k], x = vx2[k];
-                a0 += x.x * v.x;
-                a1 += x.y * v.y;
-              }
-              sm[S::Wf + e0 + lane] = a0 + a1;
-            }
+            if (lane < ne_round) sm[S::Wf + e0 + lane] = contract_run<RL, RAL>(vx, stg + lane * RL);
             __syncwarp();
             if (e0 + RS < e_end) {
               const int nn = e_end - (e0 + RS) < RS ? e_end - (e0 + RS) : RS;
+              const int nch = (nn * RL + 1) / 2;
 #pragma unroll
               for (int i = 0; i < LPR; ++i) {
                 const int c = lane + 32 * i;
-                if (c < nn * CPE) reinterpret_cast<double2*>(stg)[c] = buf[i];
+                if (c < nch) reinterpret_cast<double2*>(stg)[c] = buf[i];
               }
               if (e0 + 2 * RS < e_end) load_round(e0 + 2 * RS);
               __syncwarp();
             }
           }
-        }
 #else
-        for (int e = 0; e < NTEN; ++e) {
-          const double* f3 = rec + L.fxx + (size_t)e * nd;
-          const double* vx = sm + S::Vx;
-          double a0 = 0.0, a1 = 0.0;
-          for (int k = 0; k < nd; k += 2) { a0 += vx[k] * f3[k]; a1 += vx[k + 1] * f3[k + 1]; }
-          sm[S::Wf + e] = a0 + a1;
-        }
+          for (int e = 0; e < NEL; ++e) sm[S::Wf + e] = contract_run<RL, false>(vx, rec + L.fxx + (size_t)e * RL);
 #endif
+        };
+        if (dense) contract(IntC<nd>{}); else contract(IntC<n>{});
         if (ne > 0) {
           for (int e = tid; e < ne; e += BT) {
             sm[S::eqv + e] = rec[L.eq + e];
@@ -427,14 +467,15 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         // chains would order them (possible aliasing) and serialise the FMA latencies
         double acc[(NB + BT - 1) / BT];
         FOR_ELEMS(e, NB) {
-          const unsigned d = PRE ? dB[PRE ? u_ : 0] : mkB(e);
-          acc[u_] = dot_run<nd, AL>(sm + (d & 0xffffu), hd + (d >> 16));
+          unsigned d0, d1;
+          if (PRE) { d0 = dB0[PRE ? u_ : 0]; d1 = dB1[PRE ? u_ : 0]; } else mkB(e, d0, d1);
+          const double run = dot_run<n, AL>(sm + (d0 & 0xffffu), hd + (d0 >> 16));
+          acc[u_] = sm[d1 & 0xffffu] * sm[d1 >> 16] + run;
         }
         FOR_ELEMS(e, NB) sm[S::VF + e] = acc[u_];  // VF | VU are adjacent
       }
       bsync();
       DDPB_PHASE_MARK(bd, 9, pc_);
-      const double* Vx = sm + S::Vx;
       const double* eqv = sm + S::eqv;
       const double* eqx = sm + S::eqx;
       const double* equ = sm + S::equ;
@@ -447,11 +488,13 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         double qacc[(NC + BT - 1) / BT];
         unsigned qdst[(NC + BT - 1) / BT];
         FOR_ELEMS(e, NC) {
-          unsigned c0, c1, c2;
-          if (PRE) { c0 = dC0[PRE ? u_ : 0]; c1 = dC1[PRE ? u_ : 0]; c2 = dC2[PRE ? u_ : 0]; } else mkC(e, c0, c1, c2);
+          unsigned c0, c1, c2, c3;
+          if (PRE) { c0 = dC0[PRE ? u_ : 0]; c1 = dC1[PRE ? u_ : 0]; c2 = dC2[PRE ? u_ : 0]; c3 = dC3[PRE ? u_ : 0]; } else mkC(e, c0, c1, c2, c3);
           qdst[u_] = c2;
-          double q = hd[c1 & 0xffffu];
-          q += dot_run<nd, AL>(hd + (c0 & 0xffffu), sm + (c0 >> 16));
+          const unsigned lo = c1 & 0xffffu;
+          double q = (lo & 0x8000u) ? hd[lo & 0x7fffu] : sm[lo];
+          const double run = dot_run<n, AL>(hd + (c0 & 0xffffu), sm + (c0 >> 16));
+          q += sm[c3 & 0xffffu] * sm[c3 >> 16] + run;
           if (ne > 0) {
             // knots with equality rows (rare): terms by block
             double a = 0.0;
@@ -585,7 +628,9 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
     }
     if (!failed) success = true;
     else if (bd.max_restarts > 0 && (restarts > bd.max_restarts || !(mu < 1.79e308))) {
-      // guarded mode: this problem's Q_uu cannot be made positive definite by the reference's mu/reg schedule
+      // guarded mode: this problem's Q_uu cannot be made positive definite by the reference's mu/reg schedule.
+      // The copy staged for the knot after the failing one must land before the CTA (and its shared memory) goes away.
+      if (tma_pending) { staged_wait(); tma_pending = false; }
       if (tid == 0) bd.scal[(size_t)S_STATUS * B + b] = 2.0;
       break;
     }

@@ -3,10 +3,22 @@
 //  * small per-knot vectors (x, u, k, K, multipliers, targets) and per-problem scalars are
 //    SoA-by-batch: element e of knot t of problem b lives at ((t * E + e) * B + b), problem index
 //    fastest, so thread-per-problem kernels (rollouts, adjoint sweeps) are fully coalesced;
-//  * derivative slabs (>= 90% of all bytes) are one contiguous record per (knot, problem), ordered
-//    [knot][problem], holding the 17 sequences of the reference's derivative_storage_t
-//    (/root/reference/include/ddp/ddp.hpp:84-105) back to back, each block in the reference's element
-//    order (column-major matrices, tensors k + i*O + j*O*L).
+//  * derivative slabs (>= 90% of all bytes) hold, per (knot, problem), the STATE-DEPENDENT entries of the 17 sequences
+//    of the reference's derivative_storage_t (/root/reference/include/ddp/ddp.hpp:84-105).  The reference's
+//    problem_t fixes the cost (l = c/2 |u|^2, problem.hpp:932-942 => lx = lxx = lux = 0, luu = c I) and the Euler
+//    scheme on a vector-space configuration (problem.hpp:441-503 => rows k < n of f_x, f_u are the constants
+//    [I, dt I], 0, and with FD-of-Jacobians Hessians rows k < n of f_xx / f_ux, the v-slices of f_ux and all of f_uu are
+//    exact zeros): those entries are never stored -- every consumer uses the constants -- which cuts a record of the
+//    6R arm from 3522 to 1206 doubles.  What is stored, each block in the reference's element order restricted to the
+//    stored rows (column-major, row index fastest):
+//        f[nx] | fx_B[n x ndx] | fu_B[n x nu] | lu[nu] | tensors | eq | eq_x | eq_u | eq_xx | eq_ux | eq_uu
+//    tensors, FD-of-Jacobians mode: fxx_B[(k-n) + n (j + ndx i)] | fux_B[(k-n) + n (j + nu i)], i < n
+//    tensors, value-based mode    : fxx | fux | fuu dense (their "structural" entries carry the reference's FD
+//                                   rounding noise there, so they are data)
+//    Two orders of the slab: record-major ("AoS", one contiguous record per (knot, problem), [knot][problem][element],
+//    for the CTA-per-problem backward pass which streams records with TMA) and element-major ("SoA",
+//    [knot][element][problem], for chains of <= 2 joints whose backward pass runs one thread per problem).
+//    The host boundary (ddpb_get/set_derivatives) always speaks the reference's dense packed layout.
 #pragma once
 #include "rbd.cuh"
 
@@ -19,24 +31,29 @@ enum {
   S_MULT_UPDATES, S_FLAG /* internal: multiplier-update decision of the current iteration */, S_SPARE, NSCALARS = 16
 };
 
-// offsets (doubles) of the 17 blocks inside one slab record for a knot with `ne` equality rows
+// slab order by model size: chains of <= 2 joints (and the pendulum) run their backward pass one thread per problem
+DDPB_HD constexpr bool slab_is_soa(int n) { return n <= 2; }
+
+// offsets (doubles) of the stored blocks inside one slab record of an n-joint model for a knot with `ne` equality
+// rows; `rt` = stored rows per tensor column (n: bottom rows only, or ndx: dense), `ri` = stored x-perturbation slices
+// of f_ux (n or ndx), `n_fuu` = stored doubles of f_uu (0 or dense)
 struct RecLayout {
-  int lx, lu, lxx, lux, luu, f, fx, fu, fxx, fux, fuu, eq, eq_x, eq_u, eq_xx, eq_ux, eq_uu, size;
+  int f, fx, fu, lu, fxx, fux, fuu, eq, eq_x, eq_u, eq_xx, eq_ux, eq_uu, size;
+  int rt, ri, r0;  // tensor rows stored per column, f_ux right-index count, first stored tensor row (n or 0)
 };
-DDPB_HD RecLayout rec_layout(int nd, int nu, int nx, int ne) {
+DDPB_HD RecLayout rec_layout(int n, int ne, int hess_mode) {
+  const int nd = 2 * n, nu = n, nx = 2 * n;
+  const bool dense = hess_mode == HESS_FD_VALUES;
   RecLayout L;
+  L.rt = dense ? nd : n; L.ri = dense ? nd : n; L.r0 = dense ? 0 : n;
   int o = 0;
-  L.lx = o; o += nd;
-  L.lu = o; o += nu;
-  L.lxx = o; o += nd * nd;
-  L.lux = o; o += nu * nd;
-  L.luu = o; o += nu * nu;
   L.f = o; o += nx;
-  L.fx = o; o += nd * nd;
-  L.fu = o; o += nd * nu;
-  L.fxx = o; o += nd * nd * nd;
-  L.fux = o; o += nd * nu * nd;
-  L.fuu = o; o += nd * nu * nu;
+  L.fx = o; o += n * nd;
+  L.fu = o; o += n * nu;
+  L.lu = o; o += nu;                 // n (n + 1) is even: the tensors start on a 16-byte boundary
+  L.fxx = o; o += L.rt * nd * nd;
+  L.fux = o; o += L.rt * nu * L.ri;
+  L.fuu = o; o += dense ? nd * nu * nu : 0;
   L.eq = o; o += ne;
   L.eq_x = o; o += ne * nd;
   L.eq_u = o; o += ne * nu;
@@ -47,18 +64,60 @@ DDPB_HD RecLayout rec_layout(int nd, int nu, int nx, int ne) {
   return L;
 }
 
+// Dense element e (reference element order) of derivative field `field` (0 lx, 1 lu, 2 lxx, 3 lux, 4 luu, 5 f, 6 fx, 7 fu,
+// 8 fxx, 9 fux, 10 fuu, 11 eq, 12 eq_x, 13 eq_u, 14 eq_xx, 15 eq_ux, 16 eq_uu) -> offset inside the stored record, or -1
+// when the entry is structural; *sval is its constant value then.  Used by the host-boundary converters only.
+DDPB_HD int stored_offset(const RecLayout& L, int n, int field, int e, double dt, double c, double* sval) {
+  const int nd = 2 * n, nu = n;
+  *sval = 0.0;
+  switch (field) {
+    case 0: case 2: case 3: return -1;
+    case 1: return L.lu + e;
+    case 4: *sval = (e / nu == e % nu) ? c : 0.0; return -1;
+    case 5: return L.f + e;
+    case 6: {
+      const int k = e % nd, col = e / nd;
+      if (k >= n) return L.fx + (k - n) + n * col;
+      *sval = col < n ? (k == col ? 1.0 : 0.0) : (k == col - n ? dt : 0.0);
+      return -1;
+    }
+    case 7: {
+      const int k = e % nd, col = e / nd;
+      return k >= n ? L.fu + (k - n) + n * col : -1;
+    }
+    case 8: {
+      if (L.rt == nd) return L.fxx + e;
+      const int k = e % nd, ji = e / nd;
+      return k >= n ? L.fxx + (k - n) + n * ji : -1;
+    }
+    case 9: {
+      if (L.rt == nd) return L.fux + e;
+      const int k = e % nd, ji = e / nd, j = ji % nu, i = ji / nu;
+      return (k >= n && i < n) ? L.fux + (k - n) + n * (j + nu * i) : -1;
+    }
+    case 10: return L.rt == nd ? L.fuu + e : -1;
+    case 11: return L.eq + e;
+    case 12: return L.eq_x + e;
+    case 13: return L.eq_u + e;
+    case 14: return L.eq_xx + e;
+    case 15: return L.eq_ux + e;
+    default: return L.eq_uu + e;
+  }
+}
+
 struct BatchDev {
   int B, T, n, nx, nu;         // nx = ndx = 2n, nu = n
   int hess_mode, eq_kind, frame_id, jac_mode;
   int ne_max, ne_total;
-  int max_restarts, pad_;             // 0 = unbounded restarts (reference behaviour)
+  int max_restarts;                   // 0 = unbounded restarts (reference behaviour)
+  int slab_soa;                       // slab order: 0 = record-major [knot][problem][element], 1 = element-major [knot][element][problem]
   int b0, nb;                         // problems [b0, b0 + nb) covered by a launch (sub-batches run on their own streams)
   double dt, c;
   double *xs, *us, *xs_new, *us_new;  // [(T+1)][nx][B], [T][nu][B]
   double* targets;                    // [ne_total][B]
   double *m_origin, *m_val, *m_jac;   // [T][nx][B], [ne_total][B], [ne_total*nd][B]
   double *fb_origin, *fb_k, *fb_K;    // [T][nx][B], [T][nu][B], [T][nu*nd][B]
-  double* slab;                       // records, knot t of problem b at slab_off[t]*B + b*rec_size(t)
+  double* slab;                       // records of knot t start at slab_off[t]*B (see rec_view)
   double* scal;                       // [NSCALARS][B]
   const int* ne;                      // [T]
   const int* eq_off;                  // [T+1]
@@ -66,8 +125,19 @@ struct BatchDev {
   unsigned long long* dbg;            // optional [16] per-phase cycle counters (development; nullptr = off)
 };
 
+// record-major slabs only: the contiguous record of (knot t, problem b)
 DDPB_HD double* slab_rec(const BatchDev& bd, int t, int b, int rec_size) {
   return bd.slab + (size_t)bd.slab_off[t] * bd.B + (size_t)b * rec_size;
+}
+// either slab order: element e of the record of (knot t, problem b) is v[e]
+struct RecView {
+  double* p;
+  size_t stride;
+  DDPB_HD double& operator[](int e) const { return p[(size_t)e * stride]; }
+};
+DDPB_HD RecView rec_view(const BatchDev& bd, int t, int b, int rec_size) {
+  if (bd.slab_soa) return RecView{bd.slab + (size_t)bd.slab_off[t] * bd.B + b, (size_t)bd.B};
+  return RecView{bd.slab + (size_t)bd.slab_off[t] * bd.B + (size_t)b * rec_size, 1};
 }
 
 // ---- execution context: the same CTA body runs on the device (threads of one block) and, for the

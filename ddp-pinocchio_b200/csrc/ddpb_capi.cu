@@ -68,11 +68,13 @@ __global__ void transpose_kernel(double* __restrict__ dst, const double* __restr
 __global__ void copy_kernel(double* dst, const double* src, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
-// packed host sequence of one derivative field <-> slab records.  per_row: doubles per equality row
-// (eq fields, ragged) or 0 for fields with a fixed per-knot size `per_knot`.
+// packed host sequence of one derivative field (the reference's dense layout) <-> stored slab records.  per_row:
+// doubles per equality row (eq fields, ragged) or 0 for fields with a fixed per-knot size `per_knot`.  Entries the slab
+// does not store (batch.cuh: constants of the reference's cost / Euler scheme) are produced from their constants on
+// the way out and CHECKED on the way in: *mismatch counts the dense entries that differ from their structural value.
 __global__ void slab_field_kernel(const __grid_constant__ BatchDev bd, double* packed, size_t field_total, int field, int per_knot,
-                                  int per_row, int to_slab) {
-  const int nd = bd.nx, nu = bd.nu, nx = bd.nx;
+                                  int per_row, int to_slab, unsigned long long* mismatch) {
+  const int n = bd.n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < field_total * bd.B; i += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / field_total);
     const size_t pos = i % field_total;
@@ -87,10 +89,17 @@ __global__ void slab_field_kernel(const __grid_constant__ BatchDev bd, double* p
       }
       t = lo; e = (int)(pos - (size_t)bd.eq_off[t] * per_row);
     }
-    const RecLayout L = rec_layout(nd, nu, nx, bd.ne[t]);
-    const int offs[17] = {L.lx, L.lu, L.lxx, L.lux, L.luu, L.f, L.fx, L.fu, L.fxx, L.fux, L.fuu, L.eq, L.eq_x, L.eq_u, L.eq_xx, L.eq_ux, L.eq_uu};
-    double* r = slab_rec(bd, t, b, L.size) + offs[field] + e;
-    if (to_slab) *r = packed[i]; else packed[i] = *r;
+    const RecLayout L = rec_layout(n, bd.ne[t], bd.hess_mode);
+    double sval;
+    const int off = stored_offset(L, n, field, e, bd.dt, bd.c, &sval);
+    if (off >= 0) {
+      const RecView r = rec_view(bd, t, b, L.size);
+      if (to_slab) r[off] = packed[i]; else packed[i] = r[off];
+    } else if (to_slab) {
+      if (!(packed[i] == sval)) atomicAdd(mismatch, 1ull);
+    } else {
+      packed[i] = sval;
+    }
   }
 }
 
@@ -299,37 +308,9 @@ static int download_T(ddpb_batch* h, double* host, const double* dev, size_t C) 
   return DDPB_OK;
 }
 
-extern "C" {
-
-const char* ddpb_last_error(void) { return g_err.c_str(); }
-
-int ddpb_model_create(const ddpb_model_desc* d, ddpb_model** out) {
-  if (!d || !out) return fail(DDPB_ERR_INVALID, "null argument");
-  ddpb_model* m = new ddpb_model();
-  std::string err;
-  const int rc = model_from_desc(d, m->dev, err);
-  if (rc) { delete m; return fail(rc, err); }
-  m->nq = m->dev.n;
-  *out = m;
-  return DDPB_OK;
-}
-void ddpb_model_destroy(ddpb_model* m) { delete m; }
-
-int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot, const ddpb_params* p, int device, ddpb_batch** out) {
-  if (!m || !p || !out || B < 1 || T < 1) return fail(DDPB_ERR_INVALID, "bad arguments");
-  if (p->hess_mode != DDPB_HESS_FD_JACOBIANS && p->hess_mode != DDPB_HESS_FD_VALUES) return fail(DDPB_ERR_INVALID, "bad hess_mode");
-  if (p->eq_kind < 0 || p->eq_kind > 2) return fail(DDPB_ERR_INVALID, "bad eq_kind");
+// everything of ddpb_batch_create that can fail after the handle exists; the caller destroys the handle on failure
+static int batch_init(ddpb_batch* h, const ddpb_model* m, int B, int T, const int* ne_per_knot, const ddpb_params* p, int device, const cudaDeviceProp& prop) {
   const int n = m->nq;
-  if (p->eq_kind == DDPB_EQ_SPATIAL && (m->dev.kind == DDPB_MODEL_PENDULUM || p->frame_id < 0 || p->frame_id >= m->dev.nframes))
-    return fail(DDPB_ERR_INVALID, "frame index must be in bounds");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(DDPB_ERR_CUDA, "no CUDA device available (there is no CPU fallback)"); }
-  if (device < 0 || device >= ndev) return fail(DDPB_ERR_INVALID, "device index out of range");
-  CU(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return fail(DDPB_ERR_CUDA, "this library is built for sm_100a (B200) only");
-  ddpb_batch* h = new ddpb_batch();
   h->model = m->dev;
   h->device = device;
   h->mt = m->dev.kind == DDPB_MODEL_PENDULUM ? 0 : n;
@@ -341,15 +322,16 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   bd.hess_mode = p->hess_mode; bd.eq_kind = p->eq_kind; bd.frame_id = p->frame_id; bd.jac_mode = p->frame_jac_mode;
   bd.dt = p->dt; bd.c = p->c;
   bd.max_restarts = p->max_backward_restarts < 0 ? 0 : p->max_backward_restarts;
+  bd.slab_soa = slab_is_soa(n) ? 1 : 0;
   h->ne.assign(T, 0); h->eq_off.assign(T + 1, 0); h->slab_off.assign(T + 1, 0);
   const int row_cap = p->eq_kind == DDPB_EQ_SPATIAL ? 3 : n;
   for (int t = 0; t < T; ++t) {
     const int ne = (p->eq_kind == DDPB_EQ_NONE || !ne_per_knot) ? 0 : ne_per_knot[t];
-    if (ne < 0 || ne > row_cap || (p->eq_kind == DDPB_EQ_SPATIAL && ne != 0 && ne != 3)) { delete h; return fail(DDPB_ERR_INVALID, "bad equality row count"); }
+    if (ne < 0 || ne > row_cap || (p->eq_kind == DDPB_EQ_SPATIAL && ne != 0 && ne != 3)) return fail(DDPB_ERR_INVALID, "bad equality row count");
     h->ne[t] = ne;
     h->eq_off[t + 1] = h->eq_off[t] + ne;
     bd.ne_max = std::max(bd.ne_max, ne);
-    h->slab_off[t + 1] = h->slab_off[t] + rec_layout(2 * n, n, 2 * n, ne).size;
+    h->slab_off[t + 1] = h->slab_off[t] + rec_layout(n, ne, p->hess_mode).size;
   }
   bd.ne_total = h->eq_off[T];
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -362,7 +344,7 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   A(bd.xs, (T + 1) * nx * B); A(bd.us, T * nu * B); A(bd.xs_new, (T + 1) * nx * B); A(bd.us_new, T * nu * B);
   A(bd.targets, net * B); A(bd.m_origin, T * nx * B); A(bd.m_val, net * B); A(bd.m_jac, net * nd * B);
   A(bd.fb_origin, T * nx * B); A(bd.fb_k, T * nu * B); A(bd.fb_K, T * nu * nd * B);
-  A(bd.slab, (size_t)h->slab_off[T] * B); A(bd.scal, (size_t)NSCALARS * B); A(h->costs_old, (size_t)(T + 1) * B);
+  A(bd.slab, (size_t)h->slab_off[T] * B); A(bd.scal, (size_t)NSCALARS * B + 2); A(h->costs_old, (size_t)(T + 1) * B);
   A(d_ne, T); A(d_eo, T + 1); A(d_so, T + 1);
   {
     int slots = 1;
@@ -370,7 +352,7 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
     A(h->ls_xs, (size_t)slots * (T + 1) * nx * B); A(h->ls_us, (size_t)slots * T * nu * B);
   }
 #undef A
-  if (rc) { ddpb_batch_destroy(h); return rc; }
+  if (rc) return rc;
   bd.ne = d_ne; bd.eq_off = d_eo; bd.slab_off = d_so;
   CU(cudaMemcpy(d_ne, h->ne.data(), T * sizeof(int), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(d_eo, h->eq_off.data(), (T + 1) * sizeof(int), cudaMemcpyHostToDevice));
@@ -402,17 +384,54 @@ int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot,
   if (const char* e = getenv("DDPB_LIN_KPB")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->lin_kpb = v; }
   while (h->lin_kpb > 1 && knot_smem_max * h->lin_kpb > (size_t)prop.sharedMemPerBlockOptin) --h->lin_kpb;
   h->lin_smem = knot_smem_max * h->lin_kpb;
-  if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) { ddpb_batch_destroy(h); return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory"); }
+  if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory");
   DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });
-  DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(); });
+  DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(p->hess_mode); });
   // sub-batches of ddpb_solve: enough problems per sub-batch to keep whole warps / CTAs busy
   {
     int nsub = B >= 512 ? 4 : (B >= 128 ? 2 : 1);
     if (const char* e = getenv("DDPB_SUBBATCHES")) { const int v = atoi(e); if (v >= 1 && v <= 32) nsub = v; }
     const int rc2 = ddpb_set_subbatches(h, nsub);
-    if (rc2) { ddpb_batch_destroy(h); return rc2; }
+    if (rc2) return rc2;
   }
   CU(cudaStreamSynchronize(h->stream));
+  return DDPB_OK;
+}
+
+extern "C" {
+
+const char* ddpb_last_error(void) { return g_err.c_str(); }
+
+int ddpb_model_create(const ddpb_model_desc* d, ddpb_model** out) {
+  if (!d || !out) return fail(DDPB_ERR_INVALID, "null argument");
+  ddpb_model* m = new ddpb_model();
+  std::string err;
+  const int rc = model_from_desc(d, m->dev, err);
+  if (rc) { delete m; return fail(rc, err); }
+  m->nq = m->dev.n;
+  *out = m;
+  return DDPB_OK;
+}
+void ddpb_model_destroy(ddpb_model* m) { delete m; }
+
+int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot, const ddpb_params* p, int device, ddpb_batch** out) {
+  if (!m || !p || !out || B < 1 || T < 1) return fail(DDPB_ERR_INVALID, "bad arguments");
+  if (p->hess_mode != DDPB_HESS_FD_JACOBIANS && p->hess_mode != DDPB_HESS_FD_VALUES) return fail(DDPB_ERR_INVALID, "bad hess_mode");
+  if (p->eq_kind < 0 || p->eq_kind > 2) return fail(DDPB_ERR_INVALID, "bad eq_kind");
+  const int n = m->nq;
+  if (p->eq_kind == DDPB_EQ_SPATIAL && (m->dev.kind == DDPB_MODEL_PENDULUM || p->frame_id < 0 || p->frame_id >= m->dev.nframes))
+    return fail(DDPB_ERR_INVALID, "frame index must be in bounds");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(DDPB_ERR_CUDA, "no CUDA device available (there is no CPU fallback)"); }
+  if (device < 0 || device >= ndev) return fail(DDPB_ERR_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(DDPB_ERR_CUDA, "this library is built for sm_100a (B200) only");
+  // every failure past this point goes through one cleanup path (batch_init never frees, the handle owns all it got)
+  ddpb_batch* h = new ddpb_batch();
+  const int rc = batch_init(h, m, B, T, ne_per_knot, p, device, prop);
+  if (rc != DDPB_OK) { ddpb_batch_destroy(h); return rc; }
   *out = h;
   return DDPB_OK;
 }
@@ -614,6 +633,8 @@ static int derivs_xfer(ddpb_batch* h, const ddpb_derivs* d, int to_slab) {
                       d->eq_val, d->eq_x, d->eq_u, d->eq_xx, d->eq_ux, d->eq_uu};
   const int per_knot[11] = {nd, nu, nd * nd, nu * nd, nu * nu, nx, nd * nd, nd * nu, nd * nd * nd, nd * nu * nd, nd * nu * nu};
   const int per_row[6] = {1, nd, nu, nd * nd, nu * nd, nu * nu};
+  unsigned long long* mism = (unsigned long long*)(h->bd.scal + (size_t)NSCALARS * bd.B);  // one spare word behind the scalars
+  if (to_slab) CU(cudaMemsetAsync(mism, 0, sizeof(unsigned long long), h->stream));
   for (int f = 0; f < 17; ++f) {
     if (!ptrs[f]) continue;
     const size_t total = f < 11 ? (size_t)T * per_knot[f] : (size_t)bd.ne_total * per_row[f - 11];
@@ -623,11 +644,19 @@ static int derivs_xfer(ddpb_batch* h, const ddpb_derivs* d, int to_slab) {
     if (rc) return rc;
     if (to_slab) CU(cudaMemcpyAsync(h->stage, ptrs[f], bytes, cudaMemcpyHostToDevice, h->stream));
     slab_field_kernel<<<(unsigned)std::min<size_t>((total * bd.B + 255) / 256, 8192), 256, 0, h->stream>>>(
-        bd, h->stage, total, f, f < 11 ? per_knot[f] : 0, f < 11 ? 0 : per_row[f - 11], to_slab);
+        bd, h->stage, total, f, f < 11 ? per_knot[f] : 0, f < 11 ? 0 : per_row[f - 11], to_slab, mism);
     rc = check_launch(h, "slab_field");
     if (rc) return rc;
     if (!to_slab) CU(cudaMemcpyAsync(ptrs[f], h->stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+  }
+  if (to_slab) {
+    unsigned long long bad = 0;
+    CU(cudaMemcpyAsync(&bad, mism, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (bad)
+      return fail(DDPB_ERR_UNSUPPORTED, "derivatives differ from the structure of the reference's problem_t (l = c/2 |u|^2, Euler scheme on a vector-space "
+                                        "configuration): " + std::to_string(bad) + " entries that the slab keeps as constants");
   }
   if (!to_slab) {
     if (d->lfx) std::memset(d->lfx, 0, (size_t)bd.B * nd * sizeof(double));        // lfx = 0  (problem.hpp:958)
@@ -744,6 +773,26 @@ int ddpb_snapshot_restore(ddpb_batch* h) {
   CU(cudaMemcpyAsync(bd.xs_new, h->snap + off[0], (off[1] - off[0]) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   CU(cudaMemcpyAsync(bd.us_new, h->snap + off[1], (off[2] - off[1]) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   return DDPB_OK;
+}
+// development aid (not declared in ddpb.h): the (phase, start ms, end ms) of every launch group recorded while phase timing
+// was on, relative to the first one; consumes the recorded events.  Returns the number of entries written.
+int ddpb_debug_timeline(ddpb_batch* h, float* out3, int max_entries) {
+  if (!h || !out3) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  int n = 0;
+  for (auto& e : h->events) {
+    if (n < max_entries) {
+      float t0 = 0.f, t1 = 0.f;
+      cudaEventElapsedTime(&t0, h->events[0].a, e.a);
+      cudaEventElapsedTime(&t1, h->events[0].a, e.b);
+      out3[3 * n] = (float)e.phase; out3[3 * n + 1] = t0; out3[3 * n + 2] = t1;
+      ++n;
+    }
+  }
+  for (auto& e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  h->events.clear();
+  return n;
 }
 // development aid (not declared in ddpb.h): per-phase cycle counters of the linearization kernel
 int ddpb_debug_phase_cycles(ddpb_batch* h, int enable, unsigned long long* out16) {

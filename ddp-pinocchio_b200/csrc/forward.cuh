@@ -261,8 +261,8 @@ template <int NJ> DDPB_HD double optimality_obj_problem(const BatchDev& bd, int 
   for (int t = bd.T - 1; t >= 0; --t) {
     const int ne = bd.ne[t];
     const size_t eo = bd.eq_off[t];
-    const RecLayout L = rec_layout(nd, nu, nx, ne);
-    const double* rec = slab_rec(bd, t, b, L.size);
+    const RecLayout L = rec_layout(n, ne, bd.hess_mode);
+    const RecView rec = rec_view(bd, t, b, L.size);
     double pe[MAXE];
     for (int i = 0; i < ne; ++i) {
       // p_eq(pe, x_t): val + jac (x_t - origin)
@@ -281,9 +281,9 @@ template <int NJ> DDPB_HD double optimality_obj_problem(const BatchDev& bd, int 
       a = 0.0;
       for (int k = 0; k < ne; ++k) a += (mu * rec[L.eq + k]) * rec[L.eq_u + i * ne + k];
       v += a;
-      a = 0.0;
+      a = 0.0;  // adj f_u: rows k < n of f_u are structural zeros (batch.cuh)
 #pragma unroll
-      for (int k = 0; k < nd; ++k) a += adj[k] * rec[L.fu + i * nd + k];
+      for (int k = 0; k < n; ++k) a += adj[n + k] * rec[L.fu + i * n + k];
       v += a;
       sq += v * v;
     }
@@ -291,11 +291,11 @@ template <int NJ> DDPB_HD double optimality_obj_problem(const BatchDev& bd, int 
     if (retval < nrm) retval = nrm;
 #pragma unroll
     for (int i = 0; i < nd; ++i) {
-      double a = 0.0;
+      // adj f_x: rows k < n of f_x are the constants [I, dt I] (batch.cuh); l_x = 0
+      double a = i < n ? adj[i] : adj[i - n] * bd.dt;
 #pragma unroll
-      for (int k = 0; k < nd; ++k) a += adj[k] * rec[L.fx + i * nd + k];
+      for (int k = 0; k < n; ++k) a += adj[n + k] * rec[L.fx + i * n + k];
       double v = a;
-      v += rec[L.lx + i];
       a = 0.0;
       for (int k = 0; k < ne; ++k) a += (mu * rec[L.eq + k]) * rec[L.eq_x + i * ne + k];
       v += a;
@@ -318,8 +318,8 @@ template <int NJ> DDPB_HD double optimality_constr_problem(const BatchDev& bd, i
   for (int t = 0; t < bd.T; ++t) {
     const int ne = bd.ne[t];
     if (ne == 0) continue;
-    const RecLayout L = rec_layout(nd, nu, nx, ne);
-    const double* rec = slab_rec(bd, t, b, L.size);
+    const RecLayout L = rec_layout(n, ne, bd.hess_mode);
+    const RecView rec = rec_view(bd, t, b, L.size);
     double s = 0.0;
     for (int k = 0; k < ne; ++k) s += rec[L.eq + k] * rec[L.eq + k];
     const double nrm = sqrt(s);
@@ -378,8 +378,8 @@ template <int NJ> DDPB_HD void al_update_problem(const BatchDev& bd, int b, doub
         const int ne = bd.ne[t];
         if (ne == 0) continue;
         const size_t eo = bd.eq_off[t];
-        const RecLayout L = rec_layout(nd, nu, nx, ne);
-        const double* rec = slab_rec(bd, t, b, L.size);
+        const RecLayout L = rec_layout(n, ne, bd.hess_mode);
+        const RecView rec = rec_view(bd, t, b, L.size);
         for (int i = 0; i < ne; ++i) {
           double a = 0.0;
 #pragma unroll

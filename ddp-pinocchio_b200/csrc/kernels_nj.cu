@@ -3,6 +3,7 @@
 #error "compile with -DDDPB_NJ=<n>"
 #endif
 #include "backward.cuh"
+#include "backward_tpp.cuh"
 #include "forward.cuh"
 #include "launch.cuh"
 #include "linearize.cuh"
@@ -42,13 +43,22 @@ template <int NJ, int MODE> __global__ void __launch_bounds__(MODE == HESS_FD_JA
   if (!any) return;  // every problem of the group is frozen (converged / diverged)
   linearize_group<NJ, MODE>(m, bd, t, b0, nk, kpb, ne_sm, sm, DevExec{});
 }
+#if DDPB_NJ <= 2
+// chains of <= 2 joints: one thread per problem on the element-major slab (backward_tpp.cuh); one warp per CTA so that
+// a 4096-problem batch spreads over 128 SMs and leaves them almost entirely to the kernels of the other sub-batches
+template <int NJ, bool DENSE> __global__ void __launch_bounds__(32) backward_tpp_kernel(const __grid_constant__ BatchDev bd) {
+  extern __shared__ __align__(16) double sm[];
+  backward_tpp_warp<NJ, DENSE>(bd, sm);
+}
+#else
 // one CTA of BwdGeom<NJ>::BT threads per problem; enough CTAs per SM that a whole batch is resident in one wave
-template <int NJ> __global__ void __launch_bounds__(BwdGeom<NJ>::BT, NJ <= 2 ? 28 : (NJ <= 3 ? 16 : (NJ <= 5 ? 8 : 7))) backward_kernel(const __grid_constant__ BatchDev bd) {
+template <int NJ> __global__ void __launch_bounds__(BwdGeom<NJ>::BT, NJ <= 3 ? 16 : (NJ <= 5 ? 8 : 7)) backward_kernel(const __grid_constant__ BatchDev bd) {
   extern __shared__ __align__(16) double sm[];
   const int b = bd.b0 + blockIdx.x;
   if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
   backward_problem<NJ, BwdGeom<NJ>::BT>(bd, b, sm, DevExec{});
 }
+#endif
 #else
 template <int NJ> __global__ void linearize_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, int t0, int t1) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,10 +131,14 @@ template <> size_t Launch<KNJ>::lin_smem_bytes(int hess_mode, int ne_max, int eq
   return 0;
 #endif
 }
-template <> size_t Launch<KNJ>::bwd_smem_bytes() {
-#if DDPB_NJ > 0
+template <> size_t Launch<KNJ>::bwd_smem_bytes(int hess_mode) {
+#if DDPB_NJ > 2
+  (void)hess_mode;
   return (size_t)BwdSmem<KNJ>::size_for(BwdGeom<KNJ>::BT) * sizeof(double);
+#elif DDPB_NJ > 0
+  return (size_t)2 * 32 * sizeof(double) * (hess_mode == HESS_FD_VALUES ? TppRec<KNJ, true>::NST : TppRec<KNJ, false>::NST);
 #else
+  (void)hess_mode;
   return 0;
 #endif
 }
@@ -139,6 +153,10 @@ template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
 #if DDPB_NJ > 0
   cudaError_t e = cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_JACOBIANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
   if (e != cudaSuccess) return e;
+#if DDPB_NJ <= 2
+  e = cudaFuncSetAttribute(backward_tpp_kernel<KNJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(HESS_FD_VALUES));
+  if (e != cudaSuccess) return e;
+#endif
   return cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
 #else
   (void)lin_smem;
@@ -159,9 +177,13 @@ template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, i
 #endif
 }
 template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
-#if DDPB_NJ > 0
+#if DDPB_NJ > 2
   (void)threads;
   backward_kernel<KNJ><<<bd.nb, BwdGeom<KNJ>::BT, smem, s>>>(bd);
+#elif DDPB_NJ > 0
+  (void)threads;
+  if (bd.hess_mode == HESS_FD_VALUES) backward_tpp_kernel<KNJ, true><<<(bd.nb + 31) / 32, 32, smem, s>>>(bd);
+  else backward_tpp_kernel<KNJ, false><<<(bd.nb + 31) / 32, 32, smem, s>>>(bd);
 #else
   (void)bd; (void)threads; (void)smem; (void)s;
 #endif

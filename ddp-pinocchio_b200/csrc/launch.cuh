@@ -10,7 +10,7 @@ namespace ddpb {
 
 template <int NJ> struct Launch {
   static size_t lin_smem_bytes(int hess_mode, int ne_max, int eq_kind);
-  static size_t bwd_smem_bytes();
+  static size_t bwd_smem_bytes(int hess_mode);
   static cudaError_t prepare(size_t lin_smem);
   // knots [t0, t1) (all with the same number of equality rows <= ne_sm), kpb problems per CTA
   static void linearize(const ModelDev& m, const BatchDev& bd, int threads, int kpb, int t0, int t1, int ne_sm, cudaStream_t s);

@@ -423,90 +423,79 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   ex.sync();
   DDPB_PHASE_MARK(bd, 6, pc_);
 
-  // phase 6: assemble the records and stream them out, block by block.  Inside a block the element index runs
-  // fastest over consecutive threads (coalesced stores); block sizes of the dynamics part are compile-time
-  // constants, so the index arithmetic is multiplications by reciprocals, not divisions.
-  const RecLayout L = rec_layout(nd, nu, nx, ne);
-  double* rec0 = slab_rec(bd, t, b0, L.size);
+  // phase 6: assemble the stored part of the records (batch.cuh: the structural entries -- cost blocks except lu, rows
+  // k < n of fx / fu and, with FD-of-Jacobians Hessians, of the tensors, v-slices of f_ux, f_uu -- are never written)
+  // and stream it out block by block.  Record-major slab: the element index runs fastest over consecutive threads;
+  // element-major slab: the knot (= problem) index does.  Either way consecutive threads write consecutive doubles.
+  const RecLayout L = rec_layout(NJ, ne, MODE);
+  constexpr bool SOA = slab_is_soa(NJ);
+  double* const out0 = SOA ? bd.slab + (size_t)bd.slab_off[t] * B + b0 : slab_rec(bd, t, b0, L.size);
+  const size_t es = SOA ? (size_t)B : 1, ks = SOA ? 1 : (size_t)L.size;  // element / knot strides
   const double inv_eps = 1.0 / eps, inv_eps2 = 1.0 / (eps * eps);
   const size_t ps = (size_t)ne_sm * N;  // eqxu stride per point
   constexpr bool fdj = MODE == HESS_FD_JACOBIANS;
-#define FOR_BLOCK(kk, e, SIZE) _Pragma("unroll 4") for (int idx_ = tid, kk = idx_ / (SIZE), e = idx_ - kk * (SIZE); idx_ < nk * (SIZE); idx_ += nthr, kk = idx_ / (SIZE), e = idx_ - kk * (SIZE))
-#define REC(kk, off) rec0[(size_t)(kk) * L.size + (off)]
-  {
-    // cost blocks lx | lu | lxx | lux | luu (adjacent), then f
-    constexpr int CB = nd + nu + nd * nd + nu * nd + nu * nu;
-    FOR_BLOCK(kk, e, CB) {
-      double v = 0.0;
-      if (e >= nd && e < nd + nu) v = bd.c * SM(kk, pl.o_base)[2 * n + (e - nd)];              // lu = c u
-      else if (e >= CB - nu * nu) { const int q = e - (CB - nu * nu); v = (q / nu == q % nu) ? bd.c : 0.0; }  // luu = c I
-      REC(kk, L.lx + e) = v;
+#define REC(kk, off) out0[(size_t)(kk) * ks + (size_t)(off) * es]
+  // fn(kk, e) for every (knot of the group, element of a block of SIZE elements)
+  auto for_block = [&](int SIZE, auto&& fn) {
+#pragma unroll 4
+    for (int idx_ = tid; idx_ < nk * SIZE; idx_ += nthr) {
+      int kk, e;
+      if (SOA) { e = idx_ / nk; kk = idx_ - e * nk; } else { kk = idx_ / SIZE; e = idx_ - kk * SIZE; }
+      fn(kk, e);
     }
-    FOR_BLOCK(kk, e, nx) REC(kk, L.f + e) = SM(kk, pl.o_fval)[e];
-    FOR_BLOCK(kk, e, nd * nd) REC(kk, L.fx + e) = fx_at(kk, 0, e % nd, e / nd);
-    FOR_BLOCK(kk, e, nd * nu) REC(kk, L.fu + e) = fu_at(kk, 0, e % nd, e / nd);
-    if (L.size > L.eq_uu + ne * nu * nu) FOR_BLOCK(kk, e, 1) REC(kk, L.size - 1) = 0.0;  // padding double
+  };
+  {
+    for_block(nx, [&](int kk, int e) { REC(kk, L.f + e) = SM(kk, pl.o_fval)[e]; });
+    for_block(n * nd, [&](int kk, int e) { REC(kk, L.fx + e) = fx_at(kk, 0, n + e % n, e / n); });
+    for_block(n * nu, [&](int kk, int e) { REC(kk, L.fu + e) = fu_at(kk, 0, n + e % n, e / n); });
+    for_block(nu, [&](int kk, int e) { REC(kk, L.lu + e) = bd.c * SM(kk, pl.o_base)[2 * n + e]; });  // lu = c u
+    if (L.size > L.eq_uu + ne * nu * nu) for_block(1, [&](int kk, int) { REC(kk, L.size - 1) = 0.0; });  // padding double
   }
   if (fdj) {
-    // problem.hpp:128-145: T(k,j,idx) = (J'(k,j) - J(k,j)) / eps ; rows k < n are exact constants (zero difference).
-    // bottom rows: fx(k,j) of point p is DQ/DV[(k-n) + j'*n] of that point's record; fu(k,j) is dt * M^-1 of its q-set.
-    // Two-level loops: a thread owns a (row k, column j) pair of the Jacobian and walks the perturbation index i, so
-    // the row / column / offset arithmetic is done once per pair and the inner loop is load - subtract - scale - store
-    // with constant strides (consecutive threads still write consecutive doubles for every i).
-    for (int idx = tid; idx < nk * nd * nd; idx += nthr) {
-      const int kk = idx / (nd * nd), r = idx - kk * (nd * nd);
-      const int k = r % nd, j = r / nd;
-      double* dst = &REC(kk, L.fxx + r);
-      if (k >= n) {
-        const int off = (j < n ? V::DQ + j * NJ : V::DV + (j - n) * NJ) + (k - n);
-        const double* vr = VR(kk, 0) + off;
-        const double base = vr[0];
+    // problem.hpp:128-145: T(k,j,idx) = (J'(k,j) - J(k,j)) / eps ; rows k < n are exact constants (zero difference, not
+    // stored).  Stored rows: fx(k,j) of point p is DQ/DV[(k-n) + j'*n] of that point's record; fu(k,j) is dt * M^-1 of
+    // its q-set.  Two-level loops: a thread owns a (row k, column j) pair of the Jacobian and walks the perturbation
+    // index i, so the row / column / offset arithmetic is done once per pair and the inner loop is load - subtract -
+    // scale - store with constant strides (consecutive threads still write consecutive doubles for every i).
+    for_block(n * nd, [&](int kk, int r) {
+      const int kr = r % n, j = r / n;
+      const int off = (j < n ? V::DQ + j * NJ : V::DV + (j - n) * NJ) + kr;
+      const double* vr = VR(kk, 0) + off;
+      const double base = vr[0];
 #pragma unroll
-        for (int i = 0; i < nd; ++i) dst[(size_t)i * nd * nd] = (vr[(size_t)(1 + i) * V::SIZE] - base) * inv_eps;
-      } else {
+      for (int i = 0; i < nd; ++i) REC(kk, L.fxx + r + i * n * nd) = (vr[(size_t)(1 + i) * V::SIZE] - base) * inv_eps;
+    });
+    // only a q-perturbation changes M^-1; v-perturbed points share the base q-set (exact zeros, not stored), and so
+    // do the u-perturbed ones (f_uu: exact zeros, not stored)
+    for_block(n * nu, [&](int kk, int r) {
+      const int kr = r % n, j = r / n;
+      const double* qr = QR(kk, 0) + Q::MINV + j * NJ + kr;
+      const double base = qr[0] * dt;
 #pragma unroll
-        for (int i = 0; i < nd; ++i) dst[(size_t)i * nd * nd] = 0.0;
-      }
-    }
-    for (int idx = tid; idx < nk * nd * nu; idx += nthr) {
-      const int kk = idx / (nd * nu), r = idx - kk * (nd * nu);
-      const int k = r % nd, j = r / nd;
-      double* dst = &REC(kk, L.fux + r);
-      if (k >= n) {
-        // only a q-perturbation changes M^-1; v-perturbed points share the base q-set (exact zero)
-        const double* qr = QR(kk, 0) + Q::MINV + j * NJ + (k - n);
-        const double base = qr[0] * dt;
-#pragma unroll
-        for (int i = 0; i < n; ++i) dst[(size_t)i * nd * nu] = (qr[(size_t)(1 + i) * QS] * dt - base) * inv_eps;
-#pragma unroll
-        for (int i = n; i < nd; ++i) dst[(size_t)i * nd * nu] = 0.0;
-      } else {
-#pragma unroll
-        for (int i = 0; i < nd; ++i) dst[(size_t)i * nd * nu] = 0.0;
-      }
-    }
-    FOR_BLOCK(kk, e, nd * nu * nu) REC(kk, L.fuu + e) = 0.0;  // u-perturbed points share the base q-set: same M^-1, exact zero
+      for (int i = 0; i < n; ++i) REC(kk, L.fux + r + i * n * nu) = (qr[(size_t)(1 + i) * QS] * dt - base) * inv_eps;
+    });
     if (ne > 0) {
-      FOR_BLOCK(kk, e, ne) REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e];
-      FOR_BLOCK(kk, e, ne * N) REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e];  // eq_x | eq_u adjacent on both sides
-      FOR_BLOCK(kk, e, ne * nd * nd) {
+      for_block(ne, [&](int kk, int e) { REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e]; });
+      for_block(ne * N, [&](int kk, int e) { REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e]; });  // eq_x | eq_u adjacent on both sides
+      for_block(ne * nd * nd, [&](int kk, int e) {
         const int k = e % ne, j = (e / ne) % nd, i = e / (ne * nd);
         const double* x = SM(kk, pl.o_eqxu);
         REC(kk, L.eq_xx + e) = (x[(1 + i) * ps + j * ne + k] - x[j * ne + k]) * inv_eps;
-      }
-      FOR_BLOCK(kk, e, ne * nu * nd) {
+      });
+      for_block(ne * nu * nd, [&](int kk, int e) {
         const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
         const double* x = SM(kk, pl.o_eqxu);
         REC(kk, L.eq_ux + e) = (x[(1 + i) * ps + (nd + j) * ne + k] - x[(nd + j) * ne + k]) * inv_eps;
-      }
-      FOR_BLOCK(kk, e, ne * nu * nu) {
+      });
+      for_block(ne * nu * nu, [&](int kk, int e) {
         const int k = e % ne, j = (e / ne) % nu, i = e / (ne * nu);
         const double* x = SM(kk, pl.o_eqxu);
         REC(kk, L.eq_uu + e) = pl.u_points ? (x[(1 + nd + i) * ps + (nd + j) * ne + k] - x[(nd + j) * ne + k]) * inv_eps : 0.0;
-      }
+      });
     }
   } else {
-    // problem.hpp:192-296 (value-based FD): row k of function `which` (0 = f, 1 = eq), global tangent indices ga, gb
+    // problem.hpp:192-296 (value-based FD): row k of function `which` (0 = f, 1 = eq), global tangent indices ga, gb.
+    // Here every tensor entry is data (rows k < n carry the reference's rounding noise): dense blocks.
     auto diag = [&](double f1, double f0, double col) -> double {
       double df = f1 - f0;
       df -= eps * col;
@@ -544,9 +533,8 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     ex.sync();
     // block of a tensor: rows R (f: nd, eq: ne) of function `which`, left indices a0 .. a0+LA-1, right indices b0 .. b0+LB-1,
     // element (k, a, b) at off + k + R * a + R * LA * b
-    auto fill = [&](int which, int off, int R, int a0, int LA, int b0, int LB) {
-      for (int idx = tid; idx < nk * R * LA; idx += nthr) {
-        const int kk = idx / (R * LA), r = idx - kk * (R * LA);
+    auto fill = [&](int which, int off, int R, int a0, int LA, int b0_, int LB) {
+      for_block(R * LA, [&](int kk, int r) {
         const int k = r % R, ga = a0 + r / R;
         const int row = which ? nd + k : k;
         const double* dg = SM(kk, pl.o_dg) + row;
@@ -554,9 +542,8 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const double* vals = which == 0 ? SM(kk, pl.o_fval) + k : SM(kk, pl.o_eqv) + k;
         const int vs = which == 0 ? nx : ne_sm;
         const double f0 = vals[0], ca = jc[ga * dgs], da = dg[ga * dgs];
-        double* dst = &REC(kk, off + r);
         for (int bl = 0; bl < LB; ++bl) {
-          const int gb = b0 + bl;
+          const int gb = b0_ + bl;
           double v;
           if (gb == ga) {
             v = da;
@@ -566,22 +553,21 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
             const int i = lo ? gb : ga, j = lo ? ga : gb;
             v = offd(vals[(size_t)(1 + N + pair_rank(i, j, N)) * vs], f0, lo ? cb : ca, lo ? ca : cb, lo ? db : da, lo ? da : db);
           }
-          dst[(size_t)bl * R * LA] = v;
+          REC(kk, off + r + bl * R * LA) = v;
         }
-      }
+      });
     };
     fill(0, L.fxx, nd, 0, nd, 0, nd);
     fill(0, L.fux, nd, nd, nu, 0, nd);
     fill(0, L.fuu, nd, nd, nu, nd, nu);
     if (ne > 0) {
-      FOR_BLOCK(kk, e, ne) REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e];
-      FOR_BLOCK(kk, e, ne * N) REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e];
+      for_block(ne, [&](int kk, int e) { REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e]; });
+      for_block(ne * N, [&](int kk, int e) { REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e]; });
       fill(1, L.eq_xx, ne, 0, nd, 0, nd);
       fill(1, L.eq_ux, ne, nd, nu, 0, nd);
       fill(1, L.eq_uu, ne, nd, nu, nd, nu);
     }
   }
-#undef FOR_BLOCK
 #undef REC
   DDPB_PHASE_MARK(bd, 7, pc_);
 #undef SM
@@ -628,22 +614,29 @@ DDPB_HD void linearize_pendulum(const ModelDev& m, const BatchDev& bd, int b, in
   const double x[2] = {bd.xs[((size_t)t * 2 + 0) * B + b], bd.xs[((size_t)t * 2 + 1) * B + b]};
   const double u = bd.us[(size_t)t * B + b];
   const double tgt = ne ? bd.targets[(size_t)bd.eq_off[t] * B + b] : 0.0;
-  const RecLayout L = rec_layout(2, 1, 2, ne);
-  double* rec = slab_rec(bd, t, b, L.size);
-  rec[L.lx] = 0.0; rec[L.lx + 1] = 0.0;
-  rec[L.lu] = bd.c * u;
-  for (int e = 0; e < 4; ++e) rec[L.lxx + e] = 0.0;
-  rec[L.lux] = 0.0; rec[L.lux + 1] = 0.0;
-  rec[L.luu] = bd.c;
+  const RecLayout L = rec_layout(1, ne, bd.hess_mode);
+  const RecView rv = rec_view(bd, t, b, L.size);
+  // dense entry e of field F (reference order); structural entries (batch.cuh) are not stored
+  enum { F_lx, F_lu, F_lxx, F_lux, F_luu, F_f, F_fx, F_fu, F_fxx, F_fux, F_fuu, F_eq, F_eq_x, F_eq_u, F_eq_xx, F_eq_ux, F_eq_uu };
+  auto put = [&](int field, int e, double v) {
+    double sv;
+    const int off = stored_offset(L, 1, field, e, dt, bd.c, &sv);
+    if (off >= 0) rv[off] = v;
+  };
+  put(F_lx, 0, 0.0); put(F_lx, 1, 0.0);
+  put(F_lu, 0, bd.c * u);
+  for (int e = 0; e < 4; ++e) put(F_lxx, e, 0.0);
+  put(F_lux, 0, 0.0); put(F_lux, 1, 0.0);
+  put(F_luu, 0, bd.c);
   double f0[2], fx0[4], fu0[2];
   pend_first(m, dt, x, u, f0, fx0, fu0);
-  rec[L.f] = f0[0]; rec[L.f + 1] = f0[1];
-  for (int e = 0; e < 4; ++e) rec[L.fx + e] = fx0[e];
-  rec[L.fu] = fu0[0]; rec[L.fu + 1] = fu0[1];
+  put(F_f, 0, f0[0]); put(F_f, 1, f0[1]);
+  for (int e = 0; e < 4; ++e) put(F_fx, e, fx0[e]);
+  put(F_fu, 0, fu0[0]); put(F_fu, 1, fu0[1]);
   double e0 = 0.0, ex0[2] = {0.0, 0.0}, eu0 = 0.0;
   if (ne) {
     pend_eq_first(m, dt, x, u, tgt, &e0, ex0, &eu0);
-    rec[L.eq] = e0; rec[L.eq_x] = ex0[0]; rec[L.eq_x + 1] = ex0[1]; rec[L.eq_u] = eu0;
+    put(F_eq, 0, e0); put(F_eq_x, 0, ex0[0]); put(F_eq_x, 1, ex0[1]); put(F_eq_u, 0, eu0);
   }
   if (bd.hess_mode == HESS_FD_JACOBIANS) {
     const double eps = 1.4901161193847656e-08, ie = 1.0 / eps;
@@ -656,16 +649,16 @@ DDPB_HD void linearize_pendulum(const ModelDev& m, const BatchDev& bd, int b, in
       if (ne) pend_eq_first(m, dt, xp, up, tgt, &e1, ex1, &eu1);
       if (i < 2) {
         for (int k = 0; k < 2; ++k) {
-          for (int j = 0; j < 2; ++j) rec[L.fxx + k + j * 2 + i * 4] = (fx1[j * 2 + k] - fx0[j * 2 + k]) * ie;
-          rec[L.fux + k + i * 2] = (fu1[k] - fu0[k]) * ie;
+          for (int j = 0; j < 2; ++j) put(F_fxx, k + j * 2 + i * 4, (fx1[j * 2 + k] - fx0[j * 2 + k]) * ie);
+          put(F_fux, k + i * 2, (fu1[k] - fu0[k]) * ie);
         }
         if (ne) {
-          for (int j = 0; j < 2; ++j) rec[L.eq_xx + j + i * 2] = (ex1[j] - ex0[j]) * ie;
-          rec[L.eq_ux + i] = (eu1 - eu0) * ie;
+          for (int j = 0; j < 2; ++j) put(F_eq_xx, j + i * 2, (ex1[j] - ex0[j]) * ie);
+          put(F_eq_ux, i, (eu1 - eu0) * ie);
         }
       } else {
-        for (int k = 0; k < 2; ++k) rec[L.fuu + k] = (fu1[k] - fu0[k]) * ie;
-        if (ne) rec[L.eq_uu] = (eu1 - eu0) * ie;
+        for (int k = 0; k < 2; ++k) put(F_fuu, k, (fu1[k] - fu0[k]) * ie);
+        if (ne) put(F_eq_uu, 0, (eu1 - eu0) * ie);
       }
     }
   } else {
@@ -694,11 +687,11 @@ DDPB_HD void linearize_pendulum(const ModelDev& m, const BatchDev& bd, int b, in
       }
     }
     for (int k = 0; k < 2; ++k) {
-      rec[L.fxx + k + 0 * 2 + 0 * 4] = dg[0][k];
-      rec[L.fxx + k + 1 * 2 + 1 * 4] = dg[1][k];
-      rec[L.fuu + k] = dg[2][k];
+      put(F_fxx, k + 0 * 2 + 0 * 4, dg[0][k]);
+      put(F_fxx, k + 1 * 2 + 1 * 4, dg[1][k]);
+      put(F_fuu, k, dg[2][k]);
     }
-    if (ne) { rec[L.eq_xx + 0] = edg[0]; rec[L.eq_xx + 3] = edg[1]; rec[L.eq_uu] = edg[2]; }
+    if (ne) { put(F_eq_xx, 0, edg[0]); put(F_eq_xx, 3, edg[1]); put(F_eq_uu, 0, edg[2]); }
     for (int i = 0; i < 3; ++i)
       for (int j = i + 1; j < 3; ++j) {
         double xp[2] = {x[0] + ((i == 0 || j == 0) ? eps : 0.0), x[1] + ((i == 1 || j == 1) ? eps : 0.0)};
@@ -711,8 +704,8 @@ DDPB_HD void linearize_pendulum(const ModelDev& m, const BatchDev& bd, int b, in
           df -= eps * col[j][k];
           df *= 2.0;
           const double v = 0.5 * (df * ie2 - dg[i][k] - dg[j][k]);
-          if (j < 2) { rec[L.fxx + k + j * 2 + i * 4] = v; rec[L.fxx + k + i * 2 + j * 4] = v; }
-          else rec[L.fux + k + i * 2] = v;  // ux(k, u, x_i)
+          if (j < 2) { put(F_fxx, k + j * 2 + i * 4, v); put(F_fxx, k + i * 2 + j * 4, v); }
+          else put(F_fux, k + i * 2, v);  // ux(k, u, x_i)
         }
         if (ne) {
           double df = pend_eq(m, dt, xp, up, tgt) - e0;
@@ -720,8 +713,8 @@ DDPB_HD void linearize_pendulum(const ModelDev& m, const BatchDev& bd, int b, in
           df -= eps * ecol[j];
           df *= 2.0;
           const double v = 0.5 * (df * ie2 - edg[i] - edg[j]);
-          if (j < 2) { rec[L.eq_xx + j + i * 2] = v; rec[L.eq_xx + i + j * 2] = v; }
-          else rec[L.eq_ux + i] = v;
+          if (j < 2) { put(F_eq_xx, j + i * 2, v); put(F_eq_xx, i + j * 2, v); }
+          else put(F_eq_ux, i, v);
         }
       }
   }

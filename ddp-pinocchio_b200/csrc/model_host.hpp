@@ -50,6 +50,7 @@ inline int model_from_desc(const ddpb_model_desc* d, ModelDev& M, std::string& e
     for (int k = 0; k < 3; ++k) M.h[i][k] = ms * c[k];
     M.mass[i] = ms;
   }
+  if (d->n_frames > 0 && (!d->frame_parent || !d->frame_trans)) { err = "null frame array"; return DDPB_ERR_INVALID; }
   M.nframes = d->n_frames;
   for (int f = 0; f < d->n_frames; ++f) {
     if (d->frame_parent[f] < 0 || d->frame_parent[f] >= n) { err = "frame parent out of range"; return DDPB_ERR_INVALID; }

@@ -51,8 +51,8 @@ template <int NJ> __device__ __forceinline__ void mult_update_knot(const BatchDe
   if (ne == 0) return;
   const double mu = bd.scal[(size_t)S_MU * B + b];
   const size_t eo = bd.eq_off[t];
-  const RecLayout L = rec_layout(nd, nu, nx, ne);
-  const double* rec = slab_rec(bd, t, b, L.size);
+  const RecLayout L = rec_layout(n, ne, bd.hess_mode);
+  const RecView rec = rec_view(bd, t, b, L.size);
   for (int i = 0; i < ne; ++i) {
     double a = 0.0;
 #pragma unroll
@@ -81,33 +81,36 @@ template <int NJ> __device__ __forceinline__ double optimality_obj_warp(const Ba
 #pragma unroll
   for (int k = 0; k < nd; ++k) adj[k] = 0.0;  // lfx = 0
   double retval = 0.0;
-  // column of f_x (lanes < nd) or f_u (next nu lanes) and the matching l_x / l_u entry, loaded one knot ahead
-  double cur[nd], nxt[nd], lcur = 0.0, lnxt = 0.0;
+  double atop = 0.0;  // the adjoint component that meets this lane's constant row of f_x: adj[col] or adj[col - n]
+  // stored rows (k >= n, batch.cuh) of column `col` of f_x (lanes < nd) or f_u (next nu lanes) and the matching l_u
+  // entry (l_x = 0), loaded one knot ahead
+  double cur[n], nxt[n], lcur = 0.0, lnxt = 0.0;
   auto load = [&](int t, double* dst, double& l) {
-    const RecLayout L = rec_layout(nd, nu, nx, bd.ne[t]);
-    const double* rec = slab_rec(bd, t, b, L.size);
+    const RecLayout L = rec_layout(n, bd.ne[t], bd.hess_mode);
+    const RecView rec = rec_view(bd, t, b, L.size);
     if (isx || isu) {
-      const double* c = rec + (isx ? L.fx : L.fu) + col * nd;
+      const int c0 = (isx ? L.fx : L.fu) + col * n;
 #pragma unroll
-      for (int k = 0; k < nd; ++k) dst[k] = c[k];
-      l = rec[(isx ? L.lx : L.lu) + col];
+      for (int k = 0; k < n; ++k) dst[k] = rec[c0 + k];
+      l = isx ? 0.0 : rec[L.lu + col];
     }
   };
   load(bd.T - 1, cur, lcur);
   for (int t = bd.T - 1; t >= 0; --t) {
     if (t > 0) load(t - 1, nxt, lnxt);
     const int ne = bd.ne[t];
-    double dotc = 0.0;
+    // adj . column: rows k < n of f_x are the constants [I, dt I], those of f_u zeros
+    double dotc = isx ? (col < n ? atop : atop * bd.dt) : 0.0;
 #pragma unroll
-    for (int k = 0; k < nd; ++k) dotc += adj[k] * cur[k];
+    for (int k = 0; k < n; ++k) dotc += adj[n + k] * cur[k];
     double v;
     if (ne == 0) {
-      // lu = l_u + adj f_u ; adj' = adj f_x + l_x   (the eq terms are empty sums)
-      v = isx ? dotc + lcur : lcur + dotc;
+      // lu = l_u + adj f_u ; adj' = adj f_x   (l_x = 0, the eq terms are empty sums)
+      v = isx ? dotc : lcur + dotc;
     } else {
       const size_t eo = bd.eq_off[t];
-      const RecLayout L = rec_layout(nd, nu, nx, ne);
-      const double* rec = slab_rec(bd, t, b, L.size);
+      const RecLayout L = rec_layout(n, ne, bd.hess_mode);
+      const RecView rec = rec_view(bd, t, b, L.size);
       double pe[MAXE];
       for (int i = 0; i < ne; ++i) {
         double pv = bd.m_val[(eo + i) * B + b], a = 0.0;
@@ -127,7 +130,6 @@ template <int NJ> __device__ __forceinline__ double optimality_obj_warp(const Ba
         v += dotc;
       } else if (isx) {
         v = dotc;
-        v += lcur;
         double a = 0.0;
         for (int k = 0; k < ne; ++k) a += (mu * rec[L.eq + k]) * rec[L.eq_x + col * ne + k];
         v += a;
@@ -149,8 +151,9 @@ template <int NJ> __device__ __forceinline__ double optimality_obj_warp(const Ba
     if (retval < nrm) retval = nrm;
 #pragma unroll
     for (int k = 0; k < nd; ++k) adj[k] = __shfl_sync(FULL, v, k);
+    atop = __shfl_sync(FULL, v, isx ? (col < n ? col : col - n) : 0);
 #pragma unroll
-    for (int k = 0; k < nd; ++k) cur[k] = nxt[k];
+    for (int k = 0; k < n; ++k) cur[k] = nxt[k];
     lcur = lnxt;
   }
   return retval;

@@ -19,15 +19,20 @@ def gather_scalars(local, world, rank, dist=None, max_per_rank=None):
     if world == 1:
         return local
     F, Bl = local.shape
-    m = max_per_rank or Bl
+    # shard_range produces ragged shards (ranks differ by one problem): the pad width must be the same on every
+    # rank, so it is agreed on collectively (max of the per-rank counts) unless the caller passes an upper bound
+    counts = torch.tensor([Bl], dtype=torch.int64, device=local.device)
+    cl = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(cl, counts)
+    sizes = [int(c.item()) for c in cl]
+    m = max(sizes) if max_per_rank is None else int(max_per_rank)
+    if max(sizes) > m:
+        raise ValueError(f"gather_scalars: a shard holds {max(sizes)} problems, more than max_per_rank={m}")
     pad = torch.zeros((F, m), dtype=local.dtype, device=local.device)
     pad[:, :Bl] = local
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
-    counts = torch.tensor([Bl], dtype=torch.int64, device=local.device)
-    cl = [torch.empty_like(counts) for _ in range(world)]
-    dist.all_gather(cl, counts)
-    return torch.cat([o[:, : int(c.item())] for o, c in zip(out, cl)], dim=1)
+    return torch.cat([o[:, :c] for o, c in zip(out, sizes)], dim=1)
 
 
 def all_converged(status_local, dist=None, world=1):

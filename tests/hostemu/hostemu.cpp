@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../ddp-pinocchio_b200/csrc/backward.cuh"
+#include "../../ddp-pinocchio_b200/csrc/backward_tpp.cuh"
 #include "../../ddp-pinocchio_b200/csrc/forward.cuh"
 #include "../../ddp-pinocchio_b200/csrc/linearize.cuh"
 #include "../../ddp-pinocchio_b200/csrc/model_host.hpp"
@@ -54,7 +55,15 @@ template <int NJ> static void linearize_host(const ModelDev& m, const BatchDev& 
   if (bd.hess_mode == HESS_FD_JACOBIANS) linearize_group<NJ, HESS_FD_JACOBIANS>(m, bd, t, b0, nk, kpb, bd.ne[t], sm, DevExec{});
   else linearize_group<NJ, HESS_FD_VALUES>(m, bd, t, b0, nk, kpb, bd.ne[t], sm, DevExec{});
 }
-template <int NJ> static void backward_host(const BatchDev& bd, int b, double* sm) { backward_problem<NJ, 1>(bd, b, sm, DevExec{}); }
+// chains of <= 2 joints run the thread-per-problem body (backward_tpp.cuh) on the element-major slab, longer ones the CTA body
+template <int NJ> static void backward_host(const BatchDev& bd, int b, double* sm) {
+  if (slab_is_soa(NJ)) {
+    if (bd.hess_mode == HESS_FD_VALUES) backward_thread_plain<(NJ <= 2 ? NJ : 1), true>(bd, b);
+    else backward_thread_plain<(NJ <= 2 ? NJ : 1), false>(bd, b);
+  } else {
+    backward_problem<NJ, 1>(bd, b, sm, DevExec{});
+  }
+}
 
 extern "C" {
 
@@ -70,13 +79,14 @@ void* emu_create(const ddpb_model_desc* d, int B, int T, const int* ne_per_knot,
   bd.hess_mode = p->hess_mode; bd.eq_kind = p->eq_kind; bd.frame_id = p->frame_id; bd.jac_mode = p->frame_jac_mode;
   bd.dt = p->dt; bd.c = p->c;
   bd.max_restarts = p->max_backward_restarts < 0 ? 0 : p->max_backward_restarts;
+  bd.slab_soa = slab_is_soa(n) ? 1 : 0;
   h->ne.assign(T, 0); h->eq_off.assign(T + 1, 0); h->slab_off.assign(T + 1, 0);
   for (int t = 0; t < T; ++t) {
     const int ne = (p->eq_kind == DDPB_EQ_NONE || !ne_per_knot) ? 0 : ne_per_knot[t];
     h->ne[t] = ne;
     h->eq_off[t + 1] = h->eq_off[t] + ne;
     bd.ne_max = bd.ne_max > ne ? bd.ne_max : ne;
-    h->slab_off[t + 1] = h->slab_off[t] + rec_layout(2 * n, n, 2 * n, ne).size;
+    h->slab_off[t + 1] = h->slab_off[t] + rec_layout(n, ne, p->hess_mode).size;
   }
   bd.ne_total = h->eq_off[T];
   const size_t nx = bd.nx, nu = bd.nu, nd = bd.nx, net = bd.ne_total;
@@ -197,26 +207,32 @@ void emu_solve(void* hv, const ddpb_solver_params* p) {
     emu_swap(h);
   }
 }
-// packed field [B][total] <-> slab (host version of slab_field_kernel)
-void emu_field(void* hv, double* packed, int field, int to_slab) {
+// packed dense field [B][total] <-> stored slab (host version of slab_field_kernel); returns the number of dense entries
+// that differ from their structural constant (to_slab only)
+int emu_field(void* hv, double* packed, int field, int to_slab) {
   Emu* h = (Emu*)hv;
   const BatchDev& bd = h->bd;
-  const int nd = bd.nx, nu = bd.nu, nx = bd.nx, T = bd.T;
+  const int n = bd.n, nd = bd.nx, nu = bd.nu, nx = bd.nx, T = bd.T;
   const int per_knot[11] = {nd, nu, nd * nd, nu * nd, nu * nu, nx, nd * nd, nd * nu, nd * nd * nd, nd * nu * nd, nd * nu * nu};
   const int per_row[6] = {1, nd, nu, nd * nd, nu * nd, nu * nu};
   const size_t total = field < 11 ? (size_t)T * per_knot[field] : (size_t)bd.ne_total * per_row[field - 11];
+  int bad = 0;
   for (int b = 0; b < bd.B; ++b)
     for (int t = 0; t < T; ++t) {
-      const RecLayout L = rec_layout(nd, nu, nx, bd.ne[t]);
-      const int offs[17] = {L.lx, L.lu, L.lxx, L.lux, L.luu, L.f, L.fx, L.fu, L.fxx, L.fux, L.fuu, L.eq, L.eq_x, L.eq_u, L.eq_xx, L.eq_ux, L.eq_uu};
+      const RecLayout L = rec_layout(n, bd.ne[t], bd.hess_mode);
+      const RecView r = rec_view(bd, t, b, L.size);
       const size_t cnt = field < 11 ? per_knot[field] : (size_t)bd.ne[t] * per_row[field - 11];
       const size_t pos = field < 11 ? (size_t)t * per_knot[field] : (size_t)bd.eq_off[t] * per_row[field - 11];
-      double* r = slab_rec(bd, t, b, L.size) + offs[field];
       for (size_t e = 0; e < cnt; ++e) {
-        if (to_slab) r[e] = packed[(size_t)b * total + pos + e];
-        else packed[(size_t)b * total + pos + e] = r[e];
+        double sval;
+        const int off = stored_offset(L, n, field, (int)e, bd.dt, bd.c, &sval);
+        double& pk = packed[(size_t)b * total + pos + e];
+        if (off >= 0) { if (to_slab) r[off] = pk; else pk = r[off]; }
+        else if (to_slab) { if (!(pk == sval)) ++bad; }
+        else pk = sval;
       }
     }
+  return bad;
 }
 
 }  // extern "C"

@@ -138,7 +138,9 @@ class EmuBatch(capi.BatchBase):
             if f in ("lfx", "lfxx") or a.size == 0:
                 continue
             a = np.ascontiguousarray(a, dtype=float)
-            lib().emu_field(self._h, a.ctypes.data_as(_dp), capi.DERIV_FIELDS.index(f) - 2, 1)
+            bad = lib().emu_field(self._h, a.ctypes.data_as(_dp), capi.DERIV_FIELDS.index(f) - 2, 1)
+            if bad:
+                raise RuntimeError(f"{f}: {bad} entries differ from the structural constants the slab does not store")
 
     def set_scalar(self, name, values):
         self._arr(SCAL, capi.NSCALARS)[S_IDX[name]] = np.broadcast_to(values, (self.B,))

@@ -22,6 +22,8 @@ def _worker(rank, world, port, q):
     assert np.array_equal(g_loc["x0"], g_all["x0"][lo:hi])        # shards of one global batch
     local = torch.tensor(np.stack([np.arange(lo, hi, dtype=float) + 100 * f for f in range(3)]))
     out = D.gather_scalars(local, world, rank, dist, max_per_rank=4)
+    out_default = D.gather_scalars(local, world, rank, dist)      # ragged shards (4 + 3), pad width agreed collectively
+    assert torch.equal(out, out_default)
     ok = D.all_converged(torch.tensor([1.0] * (hi - lo)) if rank == 0 else torch.tensor([0.0] * (hi - lo)), dist, world)
     q.put((rank, out.numpy(), ok))
     dist.destroy_process_group()
