@@ -15,10 +15,9 @@
 //    tensors, FD-of-Jacobians mode: fxx_B[(k-n) + n (j + ndx i)] | fux_B[(k-n) + n (j + nu i)], i < n
 //    tensors, value-based mode    : fxx | fux | fuu dense (their "structural" entries carry the reference's FD
 //                                   rounding noise there, so they are data)
-//    Two orders of the slab: record-major ("AoS", one contiguous record per (knot, problem), [knot][problem][element],
-//    for the CTA-per-problem backward pass which streams records with TMA) and element-major ("SoA",
-//    [knot][element][problem], for chains of <= 2 joints whose backward pass runs one thread per problem).
-//    The host boundary (ddpb_get/set_derivatives) always speaks the reference's dense packed layout.
+//    The slab is record-major: one contiguous record per (knot, problem), ordered [knot][problem][element], which the
+//    backward pass streams with bulk asynchronous copies (TMA / cp.async).  The host boundary (ddpb_get/set_derivatives)
+//    always speaks the reference's dense packed layout.
 #pragma once
 #include "rbd.cuh"
 
@@ -30,9 +29,6 @@ enum {
   S_MU = 0, S_REG, S_W, S_N, S_STEP, S_OPT_OBJ, S_OPT_CONSTR, S_COST, S_MERIT, S_ITERATIONS, S_STATUS, S_ROLLOUTS, S_RESTARTS,
   S_MULT_UPDATES, S_FLAG /* internal: multiplier-update decision of the current iteration */, S_SPARE, NSCALARS = 16
 };
-
-// slab order by model size: chains of <= 2 joints (and the pendulum) run their backward pass one thread per problem
-DDPB_HD constexpr bool slab_is_soa(int n) { return n <= 2; }
 
 // offsets (doubles) of the stored blocks inside one slab record of an n-joint model for a knot with `ne` equality
 // rows; `rt` = stored rows per tensor column (n: bottom rows only, or ndx: dense), `ri` = stored x-perturbation slices
@@ -110,7 +106,7 @@ struct BatchDev {
   int hess_mode, eq_kind, frame_id, jac_mode;
   int ne_max, ne_total;
   int max_restarts;                   // 0 = unbounded restarts (reference behaviour)
-  int slab_soa;                       // slab order: 0 = record-major [knot][problem][element], 1 = element-major [knot][element][problem]
+  int pad_;
   int b0, nb;                         // problems [b0, b0 + nb) covered by a launch (sub-batches run on their own streams)
   double dt, c;
   double *xs, *us, *xs_new, *us_new;  // [(T+1)][nx][B], [T][nu][B]
@@ -125,20 +121,12 @@ struct BatchDev {
   unsigned long long* dbg;            // optional [16] per-phase cycle counters (development; nullptr = off)
 };
 
-// record-major slabs only: the contiguous record of (knot t, problem b)
+// the contiguous record of (knot t, problem b)
 DDPB_HD double* slab_rec(const BatchDev& bd, int t, int b, int rec_size) {
   return bd.slab + (size_t)bd.slab_off[t] * bd.B + (size_t)b * rec_size;
 }
-// either slab order: element e of the record of (knot t, problem b) is v[e]
-struct RecView {
-  double* p;
-  size_t stride;
-  DDPB_HD double& operator[](int e) const { return p[(size_t)e * stride]; }
-};
-DDPB_HD RecView rec_view(const BatchDev& bd, int t, int b, int rec_size) {
-  if (bd.slab_soa) return RecView{bd.slab + (size_t)bd.slab_off[t] * bd.B + b, (size_t)bd.B};
-  return RecView{bd.slab + (size_t)bd.slab_off[t] * bd.B + (size_t)b * rec_size, 1};
-}
+using RecView = double*;
+DDPB_HD RecView rec_view(const BatchDev& bd, int t, int b, int rec_size) { return slab_rec(bd, t, b, rec_size); }
 
 // ---- execution context: the same CTA body runs on the device (threads of one block) and, for the
 // CPU unit tests of tests/hostemu, as a plain sequential loop over the tasks of every phase -------

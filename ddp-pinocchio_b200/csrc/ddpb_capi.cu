@@ -322,7 +322,6 @@ static int batch_init(ddpb_batch* h, const ddpb_model* m, int B, int T, const in
   bd.hess_mode = p->hess_mode; bd.eq_kind = p->eq_kind; bd.frame_id = p->frame_id; bd.jac_mode = p->frame_jac_mode;
   bd.dt = p->dt; bd.c = p->c;
   bd.max_restarts = p->max_backward_restarts < 0 ? 0 : p->max_backward_restarts;
-  bd.slab_soa = slab_is_soa(n) ? 1 : 0;
   h->ne.assign(T, 0); h->eq_off.assign(T + 1, 0); h->slab_off.assign(T + 1, 0);
   const int row_cap = p->eq_kind == DDPB_EQ_SPATIAL ? 3 : n;
   for (int t = 0; t < T; ++t) {

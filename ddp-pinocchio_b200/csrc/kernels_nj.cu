@@ -3,7 +3,7 @@
 #error "compile with -DDDPB_NJ=<n>"
 #endif
 #include "backward.cuh"
-#include "backward_tpp.cuh"
+#include "backward_lg.cuh"
 #include "forward.cuh"
 #include "launch.cuh"
 #include "linearize.cuh"
@@ -44,11 +44,11 @@ template <int NJ, int MODE> __global__ void __launch_bounds__(MODE == HESS_FD_JA
   linearize_group<NJ, MODE>(m, bd, t, b0, nk, kpb, ne_sm, sm, DevExec{});
 }
 #if DDPB_NJ <= 2
-// chains of <= 2 joints: one thread per problem on the element-major slab (backward_tpp.cuh); one warp per CTA so that
-// a 4096-problem batch spreads over 128 SMs and leaves them almost entirely to the kernels of the other sub-batches
-template <int NJ, bool DENSE> __global__ void __launch_bounds__(32) backward_tpp_kernel(const __grid_constant__ BatchDev bd) {
+// chains of <= 2 joints: one lane group of ndx^2 lanes per problem, registers and shuffles only (backward_lg.cuh)
+constexpr int LG_WARPS = 4;  // warps per CTA (independent of each other)
+template <int NJ, bool DENSE> __global__ void __launch_bounds__(32 * LG_WARPS) backward_lg_kernel(const __grid_constant__ BatchDev bd) {
   extern __shared__ __align__(16) double sm[];
-  backward_tpp_warp<NJ, DENSE>(bd, sm);
+  backward_lg_warp<NJ, DENSE>(bd, sm + (size_t)(threadIdx.x >> 5) * LgRec<NJ, DENSE>::smem_per_warp);
 }
 #else
 // one CTA of BwdGeom<NJ>::BT threads per problem; enough CTAs per SM that a whole batch is resident in one wave
@@ -136,7 +136,7 @@ template <> size_t Launch<KNJ>::bwd_smem_bytes(int hess_mode) {
   (void)hess_mode;
   return (size_t)BwdSmem<KNJ>::size_for(BwdGeom<KNJ>::BT) * sizeof(double);
 #elif DDPB_NJ > 0
-  return (size_t)2 * 32 * sizeof(double) * (hess_mode == HESS_FD_VALUES ? TppRec<KNJ, true>::NST : TppRec<KNJ, false>::NST);
+  return (size_t)LG_WARPS * sizeof(double) * (hess_mode == HESS_FD_VALUES ? LgRec<KNJ, true>::smem_per_warp : LgRec<KNJ, false>::smem_per_warp);
 #else
   (void)hess_mode;
   return 0;
@@ -154,8 +154,6 @@ template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
   cudaError_t e = cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_JACOBIANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
   if (e != cudaSuccess) return e;
 #if DDPB_NJ <= 2
-  e = cudaFuncSetAttribute(backward_tpp_kernel<KNJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(HESS_FD_VALUES));
-  if (e != cudaSuccess) return e;
 #endif
   return cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
 #else
@@ -182,8 +180,13 @@ template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t s
   backward_kernel<KNJ><<<bd.nb, BwdGeom<KNJ>::BT, smem, s>>>(bd);
 #elif DDPB_NJ > 0
   (void)threads;
-  if (bd.hess_mode == HESS_FD_VALUES) backward_tpp_kernel<KNJ, true><<<(bd.nb + 31) / 32, 32, smem, s>>>(bd);
-  else backward_tpp_kernel<KNJ, false><<<(bd.nb + 31) / 32, 32, smem, s>>>(bd);
+  if (bd.hess_mode == HESS_FD_VALUES) {
+    constexpr int ppc = LG_WARPS * LgRec<KNJ, true>::GPW;  // problems per CTA
+    backward_lg_kernel<KNJ, true><<<(bd.nb + ppc - 1) / ppc, 32 * LG_WARPS, smem, s>>>(bd);
+  } else {
+    constexpr int ppc = LG_WARPS * LgRec<KNJ, false>::GPW;
+    backward_lg_kernel<KNJ, false><<<(bd.nb + ppc - 1) / ppc, 32 * LG_WARPS, smem, s>>>(bd);
+  }
 #else
   (void)bd; (void)threads; (void)smem; (void)s;
 #endif

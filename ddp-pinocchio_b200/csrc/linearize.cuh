@@ -425,22 +425,20 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
 
   // phase 6: assemble the stored part of the records (batch.cuh: the structural entries -- cost blocks except lu, rows
   // k < n of fx / fu and, with FD-of-Jacobians Hessians, of the tensors, v-slices of f_ux, f_uu -- are never written)
-  // and stream it out block by block.  Record-major slab: the element index runs fastest over consecutive threads;
-  // element-major slab: the knot (= problem) index does.  Either way consecutive threads write consecutive doubles.
+  // and stream it out block by block: inside a block the element index runs fastest over consecutive threads, so
+  // consecutive threads write consecutive doubles.
   const RecLayout L = rec_layout(NJ, ne, MODE);
-  constexpr bool SOA = slab_is_soa(NJ);
-  double* const out0 = SOA ? bd.slab + (size_t)bd.slab_off[t] * B + b0 : slab_rec(bd, t, b0, L.size);
-  const size_t es = SOA ? (size_t)B : 1, ks = SOA ? 1 : (size_t)L.size;  // element / knot strides
+  double* const out0 = slab_rec(bd, t, b0, L.size);
+  const size_t ks = (size_t)L.size;  // knot stride
   const double inv_eps = 1.0 / eps, inv_eps2 = 1.0 / (eps * eps);
   const size_t ps = (size_t)ne_sm * N;  // eqxu stride per point
   constexpr bool fdj = MODE == HESS_FD_JACOBIANS;
-#define REC(kk, off) out0[(size_t)(kk) * ks + (size_t)(off) * es]
+#define REC(kk, off) out0[(size_t)(kk) * ks + (size_t)(off)]
   // fn(kk, e) for every (knot of the group, element of a block of SIZE elements)
   auto for_block = [&](int SIZE, auto&& fn) {
 #pragma unroll 4
     for (int idx_ = tid; idx_ < nk * SIZE; idx_ += nthr) {
-      int kk, e;
-      if (SOA) { e = idx_ / nk; kk = idx_ - e * nk; } else { kk = idx_ / SIZE; e = idx_ - kk * SIZE; }
+      const int kk = idx_ / SIZE, e = idx_ - kk * SIZE;
       fn(kk, e);
     }
   };

@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../ddp-pinocchio_b200/csrc/backward.cuh"
-#include "../../ddp-pinocchio_b200/csrc/backward_tpp.cuh"
+#include "../../ddp-pinocchio_b200/csrc/backward_lg.cuh"
 #include "../../ddp-pinocchio_b200/csrc/forward.cuh"
 #include "../../ddp-pinocchio_b200/csrc/linearize.cuh"
 #include "../../ddp-pinocchio_b200/csrc/model_host.hpp"
@@ -55,11 +55,11 @@ template <int NJ> static void linearize_host(const ModelDev& m, const BatchDev& 
   if (bd.hess_mode == HESS_FD_JACOBIANS) linearize_group<NJ, HESS_FD_JACOBIANS>(m, bd, t, b0, nk, kpb, bd.ne[t], sm, DevExec{});
   else linearize_group<NJ, HESS_FD_VALUES>(m, bd, t, b0, nk, kpb, bd.ne[t], sm, DevExec{});
 }
-// chains of <= 2 joints run the thread-per-problem body (backward_tpp.cuh) on the element-major slab, longer ones the CTA body
+// chains of <= 2 joints run the lane-group body (backward_lg.cuh), longer ones the CTA body -- as on the device
 template <int NJ> static void backward_host(const BatchDev& bd, int b, double* sm) {
-  if (slab_is_soa(NJ)) {
-    if (bd.hess_mode == HESS_FD_VALUES) backward_thread_plain<(NJ <= 2 ? NJ : 1), true>(bd, b);
-    else backward_thread_plain<(NJ <= 2 ? NJ : 1), false>(bd, b);
+  if (NJ <= 2) {
+    if (bd.hess_mode == HESS_FD_VALUES) backward_lg_plain<(NJ <= 2 ? NJ : 1), true>(bd, b);
+    else backward_lg_plain<(NJ <= 2 ? NJ : 1), false>(bd, b);
   } else {
     backward_problem<NJ, 1>(bd, b, sm, DevExec{});
   }
@@ -79,7 +79,6 @@ void* emu_create(const ddpb_model_desc* d, int B, int T, const int* ne_per_knot,
   bd.hess_mode = p->hess_mode; bd.eq_kind = p->eq_kind; bd.frame_id = p->frame_id; bd.jac_mode = p->frame_jac_mode;
   bd.dt = p->dt; bd.c = p->c;
   bd.max_restarts = p->max_backward_restarts < 0 ? 0 : p->max_backward_restarts;
-  bd.slab_soa = slab_is_soa(n) ? 1 : 0;
   h->ne.assign(T, 0); h->eq_off.assign(T + 1, 0); h->slab_off.assign(T + 1, 0);
   for (int t = 0; t < T; ++t) {
     const int ne = (p->eq_kind == DDPB_EQ_NONE || !ne_per_knot) ? 0 : ne_per_knot[t];
@@ -220,7 +219,7 @@ int emu_field(void* hv, double* packed, int field, int to_slab) {
   for (int b = 0; b < bd.B; ++b)
     for (int t = 0; t < T; ++t) {
       const RecLayout L = rec_layout(n, bd.ne[t], bd.hess_mode);
-      const RecView r = rec_view(bd, t, b, L.size);
+      double* r = slab_rec(bd, t, b, L.size);
       const size_t cnt = field < 11 ? per_knot[field] : (size_t)bd.ne[t] * per_row[field - 11];
       const size_t pos = field < 11 ? (size_t)t * per_knot[field] : (size_t)bd.eq_off[t] * per_row[field - 11];
       for (size_t e = 0; e < cnt; ++e) {
