@@ -148,6 +148,7 @@ struct ddpb_batch {
   float phase_ms[4] = {0, 0, 0, 0};
   size_t lin_smem = 0;
   int lin_threads = 128, bwd_threads = 128, lin_kpb = 1;
+  bool lin_pt = true;  // use the thread-per-point linearization where it exists (DDPB_LIN_PT=0: development switch)
   // ddpb_solve runs the batch as `nsub` sub-batches, each on its own stream: the latency-bound sweeps (backward pass,
   // rollouts) of one sub-batch overlap the throughput-bound linearization of another, and a problem that needs
   // several backward restarts only delays its own sub-batch
@@ -227,7 +228,10 @@ static int launch_linearize(const LaunchCtx& c) {
   while (t0 < T) {
     int t1 = t0 + 1;
     while (t1 < T && h->ne[t1] == h->ne[t0]) ++t1;
-    DISPATCH(h->mt, L::linearize(h->model, c.bd, h->lin_threads, h->lin_kpb, t0, t1, h->ne[t0], c.s));
+    // knots without equality rows of a short chain go to the thread-per-point kernel where one exists
+    bool done = false;
+    if (h->ne[t0] == 0 && h->lin_pt) DISPATCH(h->mt, done = L::linearize_pt(h->model, c.bd, t0, t1, c.s));
+    if (!done) DISPATCH(h->mt, L::linearize(h->model, c.bd, h->lin_threads, h->lin_kpb, t0, t1, h->ne[t0], c.s));
     int rc = check_launch(h, "linearize");
     if (rc) return rc;
     t0 = t1;
@@ -372,6 +376,7 @@ static int batch_init(ddpb_batch* h, const ddpb_model* m, int B, int T, const in
   h->lin_threads = fdv ? (n <= 2 ? 32 : 128) : (n >= 5 ? 256 : 128);
   h->bwd_threads = 32;  // informational: the backward kernel fixes its own CTA size (BwdGeom in backward.cuh)
   // development knobs (launch geometry sweeps); not part of the interface
+  if (const char* e = getenv("DDPB_LIN_PT")) h->lin_pt = atoi(e) != 0;
   if (const char* e = getenv("DDPB_LIN_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0) h->lin_threads = v; }
 
   // problems per CTA of the linearization: the serial sub-phases of a knot occupy a handful of lanes, so a CTA owns as

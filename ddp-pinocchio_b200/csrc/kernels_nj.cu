@@ -7,6 +7,7 @@
 #include "forward.cuh"
 #include "launch.cuh"
 #include "linearize.cuh"
+#include "linearize_pt.cuh"
 #include "outer_warp.cuh"
 
 namespace ddpb {
@@ -44,6 +45,12 @@ template <int NJ, int MODE> __global__ void __launch_bounds__(MODE == HESS_FD_JA
   linearize_group<NJ, MODE>(m, bd, t, b0, nk, kpb, ne_sm, sm, DevExec{});
 }
 #if DDPB_NJ <= 2
+// one thread per evaluation point (linearize_pt.cuh): 4 independent warps per CTA, 255 registers per thread
+constexpr int PT_WARPS = 4;
+template <int NJ> __global__ void __launch_bounds__(32 * PT_WARPS, 2) linearize_pt_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, int t0, int nt) {
+  __shared__ __align__(16) double stage[PT_WARPS][PtGeom<NJ>::KPW * PtGeom<NJ>::SIZE];
+  linearize_pt_warp<NJ>(m, bd, t0, nt, stage[threadIdx.x >> 5]);
+}
 // chains of <= 2 joints: one lane group of ndx^2 lanes per problem, registers and shuffles only (backward_lg.cuh)
 constexpr int LG_WARPS = 4;  // warps per CTA (independent of each other)
 template <int NJ, bool DENSE> __global__ void __launch_bounds__(32 * LG_WARPS) backward_lg_kernel(const __grid_constant__ BatchDev bd) {
@@ -172,6 +179,18 @@ template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, i
   (void)threads; (void)kpb; (void)ne_sm;
   const size_t n = (size_t)bd.nb * (t1 - t0);
   linearize_kernel<KNJ><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(m, bd, t0, t1);
+#endif
+}
+template <> bool Launch<KNJ>::linearize_pt(const ModelDev& m, const BatchDev& bd, int t0, int t1, cudaStream_t s) {
+#if DDPB_NJ > 0 && DDPB_NJ <= 2
+  if (bd.hess_mode != HESS_FD_JACOBIANS) return false;
+  const long long knots = (long long)(t1 - t0) * bd.nb;
+  const long long warps = (knots + PtGeom<KNJ>::KPW - 1) / PtGeom<KNJ>::KPW;
+  linearize_pt_kernel<KNJ><<<(unsigned)((warps + PT_WARPS - 1) / PT_WARPS), 32 * PT_WARPS, 0, s>>>(m, bd, t0, t1 - t0);
+  return true;
+#else
+  (void)m; (void)bd; (void)t0; (void)t1; (void)s;
+  return false;
 #endif
 }
 template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {

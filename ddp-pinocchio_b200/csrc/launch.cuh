@@ -14,6 +14,9 @@ template <int NJ> struct Launch {
   static cudaError_t prepare(size_t lin_smem);
   // knots [t0, t1) (all with the same number of equality rows <= ne_sm), kpb problems per CTA
   static void linearize(const ModelDev& m, const BatchDev& bd, int threads, int kpb, int t0, int t1, int ne_sm, cudaStream_t s);
+  // chains of <= 2 joints, FD-of-Jacobians Hessians, knots [t0, t1) without equality rows: one thread per evaluation point
+  // (linearize_pt.cuh); false when this model size / mode has no such kernel
+  static bool linearize_pt(const ModelDev& m, const BatchDev& bd, int t0, int t1, cudaStream_t s);
   static void backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s);
   // xs_c / us_c: scratch trajectories of the concurrent line-search trials, linesearch_slots() x the trajectory size
   // cost_seq_aug of the current trajectory (independent of the backward pass), then the concurrent line-search trials

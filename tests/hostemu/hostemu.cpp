@@ -12,6 +12,7 @@
 #include "../../ddp-pinocchio_b200/csrc/backward_lg.cuh"
 #include "../../ddp-pinocchio_b200/csrc/forward.cuh"
 #include "../../ddp-pinocchio_b200/csrc/linearize.cuh"
+#include "../../ddp-pinocchio_b200/csrc/linearize_pt.cuh"
 #include "../../ddp-pinocchio_b200/csrc/model_host.hpp"
 
 using namespace ddpb;
@@ -123,6 +124,11 @@ void emu_linearize(void* hv) {
   EMU_NJ(h->nj, {
     const int kpb = 3;  // exercise the several-knots-per-CTA path, including a ragged last group
     for (int t = 0; t < bd.T; ++t) {
+      if (NJ <= 2 && bd.hess_mode == HESS_FD_JACOBIANS && bd.ne[t] == 0) {   // as the launcher does (ddpb_capi.cu launch_linearize)
+        for (int b = 0; b < bd.B; ++b)
+          if (bd.scal[(size_t)S_STATUS * bd.B + b] == 0.0) linearize_pt_knot_plain<(NJ <= 2 ? NJ : 1)>(h->model, bd, t, b);
+        continue;
+      }
       LinPlan<NJ> pl;
       pl.init(bd.hess_mode, bd.ne[t], bd.ne[t], bd.eq_kind);   // shared memory sized for this knot's row count, as the launcher does
       std::vector<double> sm((size_t)pl.total * kpb);
