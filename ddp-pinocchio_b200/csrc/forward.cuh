@@ -111,6 +111,21 @@ template <int NJ> DDPB_HD void rollout_problem(const ModelDev& m, const BatchDev
   }
 }
 
+// one term of cost_seq_aug of the current trajectory: costs[t][b] (t == T: the terminal cost lf = 0)
+template <int NJ> DDPB_HD void cost_term_knot(const ModelDev& m, const BatchDev& bd, int b, int t, double* costs, double mu, const Scratch& sc) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
+  const int B = bd.B;
+  if (t >= bd.T) { costs[(size_t)bd.T * B + b] = 0.0; return; }
+  double x[nx], u[nu], xn[nx];
+#pragma unroll
+  for (int k = 0; k < nx; ++k) x[k] = bd.xs[((size_t)t * nx + k) * B + b];
+#pragma unroll
+  for (int k = 0; k < nu; ++k) u[k] = bd.us[((size_t)t * nu + k) * B + b];
+  // the reference re-evaluates f(x_t,u_t) inside eval_eq_to; only needed where the knot has rows
+  if (bd.ne[t] > 0) DynOps<NJ>::eval(m, bd.dt, x, u, xn, sc);
+  costs[(size_t)t * B + b] = merit_term<NJ>(m, bd, b, t, x, u, xn, mu);
+}
+
 // cost_seq_aug of the current trajectory into costs[(T+1)][B]; returns the plain cost sum_t l
 template <int NJ> DDPB_HD double cost_seq_problem(const ModelDev& m, const BatchDev& bd, int b, double* costs, double mu, const Scratch& sc) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;

@@ -76,16 +76,20 @@ template <int NJ> __global__ void linearize_kernel(const __grid_constant__ Model
 }
 #endif
 
-// line search: cost_seq_aug of the current trajectory (thread per problem), then LS_NC concurrent trials per problem
+// line search: cost_seq_aug of the current trajectory (thread per problem), then LsGeom::NC concurrent trials per problem
 // per-thread scratch of the fused forward dynamics in dynamic shared memory: element e of thread i at dyn_scr[e * blockDim.x + i]
 extern __shared__ __align__(16) double dyn_scr[];
 __device__ __forceinline__ Scratch thread_scratch() { return Scratch{dyn_scr + threadIdx.x, (int)blockDim.x}; }
+// cost_seq_aug of the current trajectory (ddp.hpp:699-735): the terms of different knots are independent, so one thread
+// per (knot, problem) instead of a T-step loop per problem -- problem index fastest => coalesced SoA accesses
 template <int NJ> __global__ void cost_old_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, double* costs_old) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = bd.b0 + i;
-  if (i >= bd.nb || bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
-  cost_seq_problem<NJ>(m, bd, b, costs_old, bd.scal[(size_t)S_MU * bd.B + b], thread_scratch());
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)bd.nb * (bd.T + 1)) return;
+  const int b = bd.b0 + (int)(i % bd.nb), t = (int)(i / bd.nb);
+  if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
+  cost_term_knot<NJ>(m, bd, b, t, costs_old, bd.scal[(size_t)S_MU * bd.B + b], thread_scratch());
 }
-template <int NJ> __global__ void __launch_bounds__(32 * LS_NC) forward_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
+template <int NJ> __global__ void __launch_bounds__(32 * LsGeom<NJ>::NC) forward_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
                                                                                const double* costs_old, double* xs_c, double* us_c) {
   linesearch_block<NJ>(m, bd, costs_old, xs_c, us_c, thread_scratch());
 }
@@ -151,7 +155,7 @@ template <> size_t Launch<KNJ>::bwd_smem_bytes(int hess_mode) {
 }
 template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
   {
-    cudaError_t e = cudaFuncSetAttribute(forward_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(32 * LS_NC));
+    cudaError_t e = cudaFuncSetAttribute(forward_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(32 * LsGeom<KNJ>::NC));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(cost_old_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(cost_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rollout_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
@@ -211,12 +215,13 @@ template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t s
 #endif
 }
 template <> void Launch<KNJ>::cost_old(const ModelDev& m, const BatchDev& bd, double* costs_old, cudaStream_t s) {
-  cost_old_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd, costs_old);
+  const size_t nkb = (size_t)bd.nb * (bd.T + 1);
+  cost_old_kernel<KNJ><<<(unsigned)((nkb + TPP - 1) / TPP), TPP, scr_bytes(TPP), s>>>(m, bd, costs_old);
 }
 template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, cudaStream_t s) {
-  forward_kernel<KNJ><<<(bd.nb + 31) / 32, 32 * LS_NC, scr_bytes(32 * LS_NC), s>>>(m, bd, costs_old, xs_c, us_c);
+  forward_kernel<KNJ><<<(bd.nb + 31) / 32, 32 * LsGeom<KNJ>::NC, scr_bytes(32 * LsGeom<KNJ>::NC), s>>>(m, bd, costs_old, xs_c, us_c);
 }
-template <> int Launch<KNJ>::linesearch_slots() { return LS_NC; }
+template <> int Launch<KNJ>::linesearch_slots() { return LsGeom<KNJ>::NC; }
 template <> void Launch<KNJ>::rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s) {
   rollout_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd);
 }

@@ -198,12 +198,15 @@ template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev&
 // rolls out into its own scratch trajectory; the smallest accepted trial index wins exactly as in the sequential scan
 // (34 trials at most, last one kept on give-up, ddp_fwd.ipp:35-37), and the block copies the winner into the
 // new-trajectory storage.  The `rollouts` scalar keeps counting what the sequential algorithm would have run.
-constexpr int LS_NC = 4;
+// Trials per round: 8 for models of <= 2 joints (a 4096-problem batch is then 1024 warps, ~2 per SM sub-partition; almost
+// every launch has some problem that needs one of the trials 4..7, which used to cost the whole block a second round),
+// 4 for the arms (their per-thread dynamics scratch fills shared memory).
+template <int NJ> struct LsGeom { static constexpr int NC = Dim<NJ>::n <= 2 ? 8 : 4; };
 constexpr int LS_MAX_TRIALS = 34;  // 2^-33 >= 1e-10 > 2^-34
 
 template <int NJ>
 __device__ __forceinline__ void linesearch_block(const ModelDev& m, const BatchDev& bd, const double* costs_old, double* xs_c, double* us_c, const Scratch& sc) {
-  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, LS_NC = LsGeom<NJ>::NC;
   const int B = bd.B, T = bd.T;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = bd.b0 + blockIdx.x * 32 + lane;

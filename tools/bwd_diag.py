@@ -30,7 +30,11 @@ for arg in sys.argv[1:] or ["c2", "c3"]:
         t_clean = bt.phase_times()["backward"]
         assert (bt.get_scalars()["restarts"] == r1).all()
         bt.compute_derivatives(); t_lin = bt.phase_times()["linearize"]
-        bt.forward_pass(); t_fwd = bt.phase_times()["forward"]
+        ro0 = bt.get_scalars()["rollouts"].copy()
+        step = bt.forward_pass(); t_fwd = bt.phase_times()["forward"]
+        act = bt.get_scalars()["status"] == 0
+        trials = (bt.get_scalars()["rollouts"] - ro0)[act]
+        print("   line search: trials needed per problem, histogram 1,2,3,4,5-8,9-16,17-34:", np.histogram(trials, bins=[1, 2, 3, 4, 5, 9, 17, 35])[0], "max", trials.max())
         bt.enable_phase_timing(False)
         print(f"{w.name} B={w.B} after {iters} iterations: backward {t_real:.3f} ms with restarts (total {rr.sum():.0f}, max/problem {rr.max():.0f}, "
               f"problems {int((rr > 0).sum())}, guarded {int((st == 2).sum())}), clean {t_clean:.3f} ms = {t_clean * 1e3 / w.T:.2f} us/knot; "
