@@ -33,7 +33,7 @@ template <int NJ> struct BwdSmem {
   // stored head of the slab record without f, copied verbatim: fx_B[n x nd] | fu_B[n x nu] | lu[nu]  (batch.cuh rec_layout)
   static constexpr int h_fx = 0, h_fu = h_fx + n * nd, h_lu = h_fu + n * nu, NHEAD = h_lu + nu;  // NHEAD is even
   static constexpr int even(int x) { return (x + 1) & ~1; }
-  static constexpr int RS = NJ <= 6 ? 32 : 16;  // tensor elements per staging round and warp
+  static constexpr int RS = NJ <= 6 ? 32 : 16;  // dense tensors: elements per staging round and warp
   static constexpr int head = 0, head2 = even(head + NHEAD), VxxR = even(head2 + NHEAD), Vx = VxxR + nd * nd, VF = even(Vx + nd), VU = VF + nd * nd,
                        Qx = even(VU + nd * nu), Qu = Qx + nd, Qxx = even(Qu + nu), Qux = Qxx + nd * nd, Quu = Qux + nu * nd,
                        Wf = even(Quu + nu * nu),  // V_x-contraction of fxx | fux | fuu, task-list order
@@ -45,7 +45,19 @@ template <int NJ> struct BwdSmem {
                        stage = even(mbar + 2),  // device: NW warp-private staging buffers of RS * nd doubles
                        SIZE = stage;
   static constexpr int c_zero = cst, c_c = cst + 1, c_one = cst + 2, c_dt = cst + 3;
-  static constexpr int size_for(int threads) { return SIZE + (threads >= 32 ? (threads / 32) * RS * nd : 0); }
+  // tensor geometry of a mode for NW warps: run length RL, element count NEL, elements per warp EW (even: every warp's
+  // share starts 16-byte aligned), elements per staging round RSM.  The compact tensors of the FD-of-Jacobians mode are
+  // staged in ONE round (the whole share of a warp is fetched by TMA during the previous knot).
+  template <bool DENSE, int NW> struct Ten {
+    static constexpr int RL = DENSE ? nd : n, NEL = DENSE ? NTEN : nd * nd + nu * n;
+    static constexpr int EW = (((NEL + NW - 1) / NW) + 1) & ~1;
+    static constexpr int RSM = DENSE ? RS : EW;
+    static constexpr int STG = RSM * RL;  // staging doubles per warp
+  };
+  template <int NW> static constexpr int stage_doubles(bool dense) { return dense ? Ten<true, NW>::STG : Ten<false, NW>::STG; }
+  static constexpr int size_for(int threads, bool dense) {
+    return SIZE + (threads >= 128 ? 4 * stage_doubles<4>(dense) : threads >= 64 ? 2 * stage_doubles<2>(dense) : threads >= 32 ? stage_doubles<1>(dense) : 0);
+  }
   // 16-byte inner products need even run lengths and even offsets: the stored columns have n rows
   static constexpr bool head_aligned = (n % 2) == 0;
 };
@@ -124,42 +136,9 @@ DDPB_HD void cp_async_wait_all() {
 #endif
 }
 
-// Cholesky of the lower triangle of A (nu x nu, column-major in shared memory) in place + 1/diag; returns false on a
-// non-positive pivot.  Device: executed by the first warp, lane i owns row i; host: the same arithmetic serially.
-template <int NU> DDPB_HD bool chol_warp(double* A, double* dinv, int lane) {
-#if defined(__CUDA_ARCH__)
-  const unsigned FULL = 0xffffffffu;
-  double a[NU];
-  const int row = lane < NU ? lane : NU - 1;
-#pragma unroll
-  for (int j = 0; j < NU; ++j) a[j] = A[j * NU + row];
-  bool ok = true;
-  double di = 0.0;
-#pragma unroll
-  for (int k = 0; k < NU; ++k) {
-    double x = a[k];
-#pragma unroll
-    for (int j = 0; j < NU; ++j)
-      if (j < k) x -= a[j] * a[j];
-    const double piv = __shfl_sync(FULL, x, k);
-    if (piv <= 0.0) { ok = false; break; }
-    const double linv = rsqrt(piv);  // column scaling by 1/sqrt(pivot): one special-function latency per column
-    double s = a[k];
-#pragma unroll
-    for (int j = 0; j < NU; ++j)
-      if (j < k) s -= a[j] * __shfl_sync(FULL, a[j], k);
-    a[k] = lane == k ? piv * linv : s * linv;
-    if (lane == k) di = linv;
-  }
-  if (ok && lane < NU) {
-#pragma unroll
-    for (int j = 0; j < NU; ++j)
-      if (j <= lane) A[j * NU + lane] = a[j];
-    dinv[lane] = di;
-  }
-  return ok;
-#else
-  (void)lane;
+// Cholesky of the lower triangle of A (nu x nu, column-major) in place + 1/diag; returns false on a non-positive pivot
+// (Eigen::LLT semantics).  CPU emulation of phase D of backward_problem; the device version works on registers there.
+template <int NU> inline bool chol_host(double* A, double* dinv) {
   for (int k = 0; k < NU; ++k) {
     double x = A[k * NU + k];
     for (int j = 0; j < k; ++j) x -= A[j * NU + k] * A[j * NU + k];
@@ -174,7 +153,6 @@ template <int NU> DDPB_HD bool chol_warp(double* A, double* dinv, int lane) {
     }
   }
   return true;
-#endif
 }
 
 template <int V> struct IntC { static constexpr int value = V; };
@@ -206,7 +184,7 @@ template <int RL, bool ALIGNED> DDPB_HD double contract_run(const double* vx, co
 
 // BT = compile-time thread count of the executor (BwdGeom<NJ>::BT on the device, 1 in the CPU emulation).
 // Record-major slabs only (chains of >= 3 joints on the device; backward_tpp.cuh covers the element-major ones).
-template <int NJ, int BT, class Ex>
+template <int NJ, int BT, bool DENSE, class Ex>
 DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& ex) {
   constexpr int n = NJ, nd = 2 * NJ, nu = NJ, nx = 2 * NJ;
   using S = BwdSmem<NJ>;
@@ -216,8 +194,9 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
   const int tid = ex.tid();
   // stored tensors (batch.cuh): FD-of-Jacobians mode keeps rows k >= n of f_xx | f_ux(:, :, i < n) only -- n doubles per
   // (j, i) pair, contracted with V_x[n..] -- value-based mode keeps f_xx | f_ux | f_uu dense
-  const bool dense = bd.hess_mode == HESS_FD_VALUES;
-  const int NEL = dense ? NTEN : nd * nd + nu * n;  // tensor elements (k-runs) of a record, contiguous from L.fxx
+  // (DENSE: a compile-time copy of bd.hess_mode == HESS_FD_VALUES -- one kernel per mode, neither pays for the other's registers)
+  constexpr bool dense = DENSE;
+  constexpr int NEL = dense ? NTEN : nd * nd + nu * n;  // tensor elements (k-runs) of a record, contiguous from L.fxx
   // a one-warp group needs no CTA barrier: warp-level synchronisation orders its shared-memory traffic
   auto bsync = [&]() { if (BT == 32) ex.sync_warp(); else ex.sync(); };
   double mu = bd.scal[(size_t)S_MU * B + b];
@@ -313,10 +292,12 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
     // (warp-private staging buffer) -- is fetched while knot t+1 is being processed
     int hcur = 0;  // which head buffer holds the knot being processed
 #if defined(__CUDA_ARCH__)
-    constexpr int RS = S::RS, NW = BT / 32;
-    const int EW = (((NEL + NW - 1) / NW) + 1) & ~1;  // elements per warp, even: every warp's share starts 16-byte aligned
+    constexpr int NW = BT >= 32 ? BT / 32 : 1;
+    using TD = typename S::template Ten<true, NW>;
+    using TC = typename S::template Ten<false, NW>;
+    constexpr int EW = dense ? TD::EW : TC::EW, RS = dense ? TD::RSM : TC::RSM, STG = dense ? TD::STG : TC::STG;
     const int warp = tid >> 5, lane = tid & 31;
-    double* stg = sm + S::stage + warp * RS * nd;
+    double* stg = sm + S::stage + warp * STG;
     const int e_beg = warp * EW < NEL ? warp * EW : NEL, e_end = (warp + 1) * EW < NEL ? (warp + 1) * EW : NEL;
 #endif
     // fetch what knot tp needs first into the buffers that are idle while the current knot is processed: the head of
@@ -330,7 +311,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       const double* recp = slab_rec(bd, tp, b, Lp.size);
       double* hdst = sm + (hnext ? S::head2 : S::head);
 #if defined(__CUDA_ARCH__)
-      const int RL = Lp.rt;
+      constexpr int RL = dense ? nd : n;
 #if DDPB_BWD_TMA
       if (tid == 0) {
         unsigned bytes = S::NHEAD * 8;
@@ -347,7 +328,7 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         for (int wq = 0; wq < NW; ++wq) {
           const int eb = wq * EW, ee = (wq + 1) * EW < NEL ? (wq + 1) * EW : NEL;
           const int nr = ee - eb < RS ? ee - eb : RS;
-          if (nr > 0) tma_bulk_g2s(sm + S::stage + wq * RS * nd, recp + Lp.fxx + (size_t)eb * RL, (unsigned)(((nr * RL + 1) & ~1) * 8), sm + S::mbar);
+          if (nr > 0) tma_bulk_g2s(sm + S::stage + wq * STG, recp + Lp.fxx + (size_t)eb * RL, (unsigned)(((nr * RL + 1) & ~1) * 8), sm + S::mbar);
         }
       }
 #else
@@ -388,8 +369,11 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       if (tid < nx) xorg = bd.xs[((size_t)t * nx + tid) * B + b];
       {
         // W(e) = sum_k V_x[r0 + k] T_e[k] for every stored tensor element e (a run of RL doubles at L.fxx + e RL)
-        auto contract = [&](auto rl_c) {
+        auto contract = [&](auto rl_c, auto rs_c, auto ew_c) {
           constexpr int RL = decltype(rl_c)::value;
+          constexpr int RS = decltype(rs_c)::value;              // elements per round (shadows the runtime value)
+          constexpr bool MULTI = RS < decltype(ew_c)::value;     // more than one round per warp and knot
+          (void)RS; (void)MULTI;
           const double* vx = sm + S::Vx + (RL == nd ? 0 : n);
 #if defined(__CUDA_ARCH__)
           // Each warp owns a contiguous range of the element list (= a contiguous piece of the adjacent tensor blocks) and
@@ -410,16 +394,16 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
               if (c < nch) buf[i] = src[c];
             }
           };
-          if (e_beg + RS < e_end) load_round(e_beg + RS);
+          if (MULTI && e_beg + RS < e_end) load_round(e_beg + RS);
           DDPB_PHASE_MARK(bd, 13, pc_);
           staged_wait();
           tma_pending = false;
           DDPB_PHASE_MARK(bd, 14, pc_);
           for (int e0 = e_beg; e0 < e_end; e0 += RS) {
             const int ne_round = e_end - e0 < RS ? e_end - e0 : RS;
-            if (lane < ne_round) sm[S::Wf + e0 + lane] = contract_run<RL, RAL>(vx, stg + lane * RL);
+            for (int l = lane; l < ne_round; l += 32) sm[S::Wf + e0 + l] = contract_run<RL, RAL>(vx, stg + l * RL);  // a round may hold more than 32 elements
             __syncwarp();
-            if (e0 + RS < e_end) {
+            if (MULTI && e0 + RS < e_end) {
               const int nn = e_end - (e0 + RS) < RS ? e_end - (e0 + RS) : RS;
               const int nch = (nn * RL + 1) / 2;
 #pragma unroll
@@ -435,7 +419,11 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
           for (int e = 0; e < NEL; ++e) sm[S::Wf + e] = contract_run<RL, false>(vx, rec + L.fxx + (size_t)e * RL);
 #endif
         };
-        if (dense) contract(IntC<nd>{}); else contract(IntC<n>{});
+#if defined(__CUDA_ARCH__)
+        contract(IntC<(dense ? nd : n)>{}, IntC<RS>{}, IntC<EW>{});
+#else
+        contract(IntC<(dense ? nd : n)>{}, IntC<0>{}, IntC<0>{});
+#endif
         if (ne > 0) {
           for (int e = tid; e < ne; e += BT) {
             sm[S::eqv + e] = rec[L.eq + e];
@@ -550,50 +538,114 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       }
       bsync();
       DDPB_PHASE_MARK(bd, 10, pc_);
-      // ---- phase D (first warp): Cholesky of Q_uu + reg I, then k = -(LL^T)^-1 Q_u, K = -(LL^T)^-1 Q_ux, one
-      // right-hand side per lane ------------------------------------------------------------------------------------
+      // ---- phase D (first warp): Cholesky of Q_uu + reg I, then k = -(LL^T)^-1 Q_u, K = -(LL^T)^-1 Q_ux ---------------------
+#if defined(__CUDA_ARCH__)
+      // One lane per column of the augmented matrix [Q_uu + reg I | -Q_ux | -Q_u] (nu + nd + 1 <= 32 columns), its nu
+      // entries in registers.  Right-looking factorisation U^T U (U = L^T): at step k the pivot lane broadcasts its diagonal,
+      // every lane scales its row-k entry by 1/sqrt(pivot) and subtracts U(k, i) U(k, c) from its entries i > k -- the
+      // right-hand-side lanes thereby do the forward substitution in the same sweep (same order of subtractions as
+      // Eigen::LLT's left-looking loop and a row-oriented solve; fails on a pivot <= 0 like Eigen::LLT).  The back
+      // substitution is column-oriented on the right-hand-side lanes with L broadcast once.  ~12 dependent steps of one
+      // multiply-add each instead of ~70 shared-memory round trips (this phase was a third of the knot, ncu).
+#ifdef DDPB_BWD_SKIP_D  // development: what does this phase cost? (results are wrong)
+      if (tid < nu * nd) sm[S::KK + tid] = 0.0;
+      if (tid < nu) sm[S::kk + tid] = 0.0;
+      if (tid == 0) sm[S::flags] = 1.0;
+      if (false) {
+#else
       if (tid < 32) {
-        const bool ok = chol_warp<nu>(sm + S::L, sm + S::dinv, tid);
+#endif
+        const unsigned FULL = 0xffffffffu;
+        const int ln = tid;
+        constexpr int NCOL = nu + nd + 1;
+        static_assert(NCOL <= 32, "one lane per column of the augmented matrix");
+        double a[nu], dinv_[nu];
+        {
+          // Eigen::LLT reads the LOWER triangle (Q_uu is not symmetric to the last bit: V_xx is not symmetrised):
+          // lane c < nu takes row c of the matrix, U(k, c) = L(c, k)
+          const double* src = ln < nu ? sm + S::L + ln : (ln < nu + nd ? sm + S::Qux + (ln - nu) * nu : sm + S::Qu);
+          const int stride = ln < nu ? nu : 1;
+          const double sgn = ln < nu ? 1.0 : -1.0;
+#pragma unroll
+          for (int i = 0; i < nu; ++i) a[i] = ln < NCOL ? sgn * src[i * stride] : 0.0;
+        }
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < nu; ++k) {
+          const double piv = __shfl_sync(FULL, a[k], k);
+          if (piv <= 0.0) { ok = false; break; }
+          const double linv = rsqrt(piv);  // column scaling by 1/sqrt(pivot): one special-function latency per step
+          dinv_[k] = linv;
+          a[k] = ln == k ? piv * linv : a[k] * linv;
+#pragma unroll
+          for (int i = 0; i < nu; ++i)
+            if (i > k) {
+              const double uki = __shfl_sync(FULL, a[k], i);  // U(k, i), final once row k is scaled
+              a[i] -= uki * a[k];
+            }
+        }
         if (tid == 0) sm[S::flags] = ok ? 1.0 : 0.0;
         if (ok) {
-          ex.sync_warp();
-          FOR_ELEMS(c, nd + 1) {
-            if (c < 32 || BT == 1) {
-              const double* A = sm + S::L;
-              const double* di = sm + S::dinv;
-              double rhs[nu];
+          // x_k = y_k / L(k, k), y_i -= L(k, i) x_k  (k = nu-1 .. 0); L(k, i) = U(i, k) is lane k's a[i], fetched where it
+          // is used (the factor lanes no longer change; holding all of L would cost 2 nu (nu - 1) / 2 registers)
 #pragma unroll
-              for (int i = 0; i < nu; ++i) rhs[i] = -(c == nd ? sm[S::Qu + i] : sm[S::Qux + c * nu + i]);
+          for (int k = nu - 1; k >= 0; --k) {
+            a[k] *= dinv_[k];
 #pragma unroll
-              for (int i = 0; i < nu; ++i) {
-                double s = rhs[i];
-#pragma unroll
-                for (int j = 0; j < nu; ++j)
-                  if (j < i) s -= A[j * nu + i] * rhs[j];
-                rhs[i] = s * di[i];
+            for (int i = 0; i < nu; ++i)
+              if (i < k) {
+                const double lki = __shfl_sync(FULL, a[i], k);
+                if (ln >= nu) a[i] -= lki * a[k];
               }
+          }
+          if (ln >= nu && ln < nu + nd) {
+            const int c = ln - nu;
 #pragma unroll
-              for (int i = nu - 1; i >= 0; --i) {
-                double s = rhs[i];
+            for (int i = 0; i < nu; ++i) {
+              sm[S::KK + c * nu + i] = a[i];
+              bd.fb_K[((size_t)t * nu * nd + c * nu + i) * B + b] = a[i];
+            }
+          } else if (ln == nu + nd) {
 #pragma unroll
-                for (int j = 0; j < nu; ++j)
-                  if (j > i) s -= A[i * nu + j] * rhs[j];
-                rhs[i] = s * di[i];
-              }
-#pragma unroll
-              for (int i = 0; i < nu; ++i) {
-                if (c == nd) {
-                  sm[S::kk + i] = rhs[i];
-                  bd.fb_k[((size_t)t * nu + i) * B + b] = rhs[i];
-                } else {
-                  sm[S::KK + c * nu + i] = rhs[i];
-                  bd.fb_K[((size_t)t * nu * nd + c * nu + i) * B + b] = rhs[i];
-                }
+            for (int i = 0; i < nu; ++i) {
+              sm[S::kk + i] = a[i];
+              bd.fb_k[((size_t)t * nu + i) * B + b] = a[i];
+            }
+          }
+        }
+      }
+#else
+      {
+        const bool ok = chol_host<nu>(sm + S::L, sm + S::dinv);
+        sm[S::flags] = ok ? 1.0 : 0.0;
+        if (ok) {
+          for (int c = 0; c <= nd; ++c) {
+            const double* A = sm + S::L;
+            const double* di = sm + S::dinv;
+            double rhs[nu];
+            for (int i = 0; i < nu; ++i) rhs[i] = -(c == nd ? sm[S::Qu + i] : sm[S::Qux + c * nu + i]);
+            for (int i = 0; i < nu; ++i) {
+              double sacc = rhs[i];
+              for (int j = 0; j < i; ++j) sacc -= A[j * nu + i] * rhs[j];
+              rhs[i] = sacc * di[i];
+            }
+            for (int k = nu - 1; k >= 0; --k) {   // column-oriented, as on the device
+              rhs[k] *= di[k];
+              for (int i = 0; i < k; ++i) rhs[i] -= A[i * nu + k] * rhs[k];
+            }
+            for (int i = 0; i < nu; ++i) {
+              if (c == nd) {
+                sm[S::kk + i] = rhs[i];
+                bd.fb_k[((size_t)t * nu + i) * B + b] = rhs[i];
+              } else {
+                sm[S::KK + c * nu + i] = rhs[i];
+                bd.fb_K[((size_t)t * nu * nd + c * nu + i) * B + b] = rhs[i];
               }
             }
           }
         }
       }
+#endif
       if (tid < nx) bd.fb_origin[((size_t)t * nx + tid) * B + b] = xorg;
       bsync();
       DDPB_PHASE_MARK(bd, 11, pc_);

@@ -59,11 +59,11 @@ template <int NJ, bool DENSE> __global__ void __launch_bounds__(32 * LG_WARPS) b
 }
 #else
 // one CTA of BwdGeom<NJ>::BT threads per problem; enough CTAs per SM that a whole batch is resident in one wave
-template <int NJ> __global__ void __launch_bounds__(BwdGeom<NJ>::BT, NJ <= 3 ? 16 : (NJ <= 5 ? 8 : 7)) backward_kernel(const __grid_constant__ BatchDev bd) {
+template <int NJ, bool DENSE> __global__ void __launch_bounds__(BwdGeom<NJ>::BT, NJ <= 3 ? 16 : (NJ <= 5 ? 8 : 7)) backward_kernel(const __grid_constant__ BatchDev bd) {
   extern __shared__ __align__(16) double sm[];
   const int b = bd.b0 + blockIdx.x;
   if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
-  backward_problem<NJ, BwdGeom<NJ>::BT>(bd, b, sm, DevExec{});
+  backward_problem<NJ, BwdGeom<NJ>::BT, DENSE>(bd, b, sm, DevExec{});
 }
 #endif
 #else
@@ -144,8 +144,7 @@ template <> size_t Launch<KNJ>::lin_smem_bytes(int hess_mode, int ne_max, int eq
 }
 template <> size_t Launch<KNJ>::bwd_smem_bytes(int hess_mode) {
 #if DDPB_NJ > 2
-  (void)hess_mode;
-  return (size_t)BwdSmem<KNJ>::size_for(BwdGeom<KNJ>::BT) * sizeof(double);
+  return (size_t)BwdSmem<KNJ>::size_for(BwdGeom<KNJ>::BT, hess_mode == HESS_FD_VALUES) * sizeof(double);
 #elif DDPB_NJ > 0
   return (size_t)LG_WARPS * sizeof(double) * (hess_mode == HESS_FD_VALUES ? LgRec<KNJ, true>::smem_per_warp : LgRec<KNJ, false>::smem_per_warp);
 #else
@@ -200,7 +199,8 @@ template <> bool Launch<KNJ>::linearize_pt(const ModelDev& m, const BatchDev& bd
 template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
 #if DDPB_NJ > 2
   (void)threads;
-  backward_kernel<KNJ><<<bd.nb, BwdGeom<KNJ>::BT, smem, s>>>(bd);
+  if (bd.hess_mode == HESS_FD_VALUES) backward_kernel<KNJ, true><<<bd.nb, BwdGeom<KNJ>::BT, smem, s>>>(bd);
+  else backward_kernel<KNJ, false><<<bd.nb, BwdGeom<KNJ>::BT, smem, s>>>(bd);
 #elif DDPB_NJ > 0
   (void)threads;
   if (bd.hess_mode == HESS_FD_VALUES) {

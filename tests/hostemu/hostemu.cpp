@@ -62,7 +62,8 @@ template <int NJ> static void backward_host(const BatchDev& bd, int b, double* s
     if (bd.hess_mode == HESS_FD_VALUES) backward_lg_plain<(NJ <= 2 ? NJ : 1), true>(bd, b);
     else backward_lg_plain<(NJ <= 2 ? NJ : 1), false>(bd, b);
   } else {
-    backward_problem<NJ, 1>(bd, b, sm, DevExec{});
+    if (bd.hess_mode == HESS_FD_VALUES) backward_problem<NJ, 1, true>(bd, b, sm, DevExec{});
+    else backward_problem<NJ, 1, false>(bd, b, sm, DevExec{});
   }
 }
 
