@@ -138,6 +138,8 @@ struct ddpb_batch {
   std::vector<void*> allocs;
   double* costs_old = nullptr;
   double *ls_xs = nullptr, *ls_us = nullptr;  // scratch trajectories of the concurrent line-search trials
+  double* ls_res = nullptr;                   // [34][3][B] (sum, merit, plain) of every trial
+  int* ls_win = nullptr;                      // [B] line-search state per problem
   double* stage = nullptr;
   size_t stage_bytes = 0;
   double* h_stage = nullptr;  // pinned bounce buffer for small scalar traffic
@@ -255,7 +257,8 @@ static int launch_forward(const LaunchCtx& c, bool with_cost_old = true) {
   ddpb_batch* h = c.h;
   if (with_cost_old) { int rc = launch_cost_old(c); if (rc) return rc; }
   PhaseScope ps(h, 2, c.s);
-  DISPATCH(h->mt, L::forward(h->model, c.bd, h->costs_old, h->ls_xs, h->ls_us, c.s));
+  DISPATCH(h->mt, L::forward(h->model, c.bd, h->costs_old, h->ls_xs, h->ls_us, h->ls_res, h->ls_win, c.s));
+  h->launches += 3;  // two waves of trials, each with its selection kernel
   return check_launch(h, "forward");
 }
 static int launch_al_update(const LaunchCtx& c, double thr) {
@@ -353,6 +356,7 @@ static int batch_init(ddpb_batch* h, const ddpb_model* m, int B, int T, const in
     int slots = 1;
     DISPATCH(h->mt, { slots = L::linesearch_slots(); });
     A(h->ls_xs, (size_t)slots * (T + 1) * nx * B); A(h->ls_us, (size_t)slots * T * nu * B);
+    A(h->ls_res, (size_t)34 * 3 * B); A(h->ls_win, (size_t)B);
   }
 #undef A
   if (rc) return rc;

@@ -76,7 +76,7 @@ template <int NJ> __global__ void linearize_kernel(const __grid_constant__ Model
 }
 #endif
 
-// line search: cost_seq_aug of the current trajectory (thread per problem), then LsGeom::NC concurrent trials per problem
+// line search: cost_seq_aug of the current trajectory, then all trials at once (outer_warp.cuh)
 // per-thread scratch of the fused forward dynamics in dynamic shared memory: element e of thread i at dyn_scr[e * blockDim.x + i]
 extern __shared__ __align__(16) double dyn_scr[];
 __device__ __forceinline__ Scratch thread_scratch() { return Scratch{dyn_scr + threadIdx.x, (int)blockDim.x}; }
@@ -89,9 +89,14 @@ template <int NJ> __global__ void cost_old_kernel(const __grid_constant__ ModelD
   if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
   cost_term_knot<NJ>(m, bd, b, t, costs_old, bd.scal[(size_t)S_MU * bd.B + b], thread_scratch());
 }
-template <int NJ> __global__ void __launch_bounds__(32 * LsGeom<NJ>::NC) forward_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
-                                                                               const double* costs_old, double* xs_c, double* us_c) {
-  linesearch_block<NJ>(m, bd, costs_old, xs_c, us_c, thread_scratch());
+template <int NJ> __global__ void __launch_bounds__(32 * LsGeom<NJ>::WPB) ls_trials_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
+                                                                                         const double* costs_old, double* xs_c, double* us_c, double* res,
+                                                                                         const int* win, int c0, int c1) {
+  ls_trials_block<NJ>(m, bd, costs_old, xs_c, us_c, res, win, c0, c1, thread_scratch());
+}
+template <int NJ> __global__ void ls_select_kernel(const __grid_constant__ BatchDev bd, const double* xs_c, const double* us_c, const double* res, int* win,
+                                                   int c0, int c1, int last) {
+  ls_select_warp<NJ>(bd, xs_c, us_c, res, win, c0, c1, last != 0);
 }
 template <int NJ> __global__ void rollout_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,7 +159,7 @@ template <> size_t Launch<KNJ>::bwd_smem_bytes(int hess_mode) {
 }
 template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
   {
-    cudaError_t e = cudaFuncSetAttribute(forward_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(32 * LsGeom<KNJ>::NC));
+    cudaError_t e = cudaFuncSetAttribute(ls_trials_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(32 * LsGeom<KNJ>::WPB));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(cost_old_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(cost_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rollout_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
@@ -218,10 +223,17 @@ template <> void Launch<KNJ>::cost_old(const ModelDev& m, const BatchDev& bd, do
   const size_t nkb = (size_t)bd.nb * (bd.T + 1);
   cost_old_kernel<KNJ><<<(unsigned)((nkb + TPP - 1) / TPP), TPP, scr_bytes(TPP), s>>>(m, bd, costs_old);
 }
-template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, cudaStream_t s) {
-  forward_kernel<KNJ><<<(bd.nb + 31) / 32, 32 * LsGeom<KNJ>::NC, scr_bytes(32 * LsGeom<KNJ>::NC), s>>>(m, bd, costs_old, xs_c, us_c);
+template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, double* ls_res, int* ls_win, cudaStream_t s) {
+  using G = LsGeom<KNJ>;
+  const unsigned pb = (unsigned)((bd.nb + 31) / 32), sb = (unsigned)(((size_t)bd.nb * 32 + 127) / 128);
+  const int waves[3] = {0, G::NC1, LS_MAX_TRIALS};
+  for (int wv = 0; wv < 2; ++wv) {
+    const int c0 = waves[wv], c1 = waves[wv + 1];
+    ls_trials_kernel<KNJ><<<dim3(pb, (unsigned)((c1 - c0 + G::WPB - 1) / G::WPB)), 32 * G::WPB, scr_bytes(32 * G::WPB), s>>>(m, bd, costs_old, xs_c, us_c, ls_res, ls_win, c0, c1);
+    ls_select_kernel<KNJ><<<sb, 128, 0, s>>>(bd, xs_c, us_c, ls_res, ls_win, c0, c1, wv == 1);
+  }
 }
-template <> int Launch<KNJ>::linesearch_slots() { return LsGeom<KNJ>::NC; }
+template <> int Launch<KNJ>::linesearch_slots() { return ls_slots<KNJ>(); }
 template <> void Launch<KNJ>::rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s) {
   rollout_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd);
 }

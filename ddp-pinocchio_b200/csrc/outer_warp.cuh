@@ -7,6 +7,7 @@
 //                          f_x / f_u columns are read straight from the slab record (contiguous 8*ndx-byte runs) one
 //                          knot ahead, the new adjoint is exchanged with shuffles
 //   mult_update_knot     : multiplier update (ddp.hpp:686-687) -- independent per (knot, problem)
+//   ls_trials / ls_select: the backtracking line search (ddp_fwd.ipp:10-67) with all its trials at once
 #pragma once
 #if defined(__CUDACC__)
 #include "forward.cuh"
@@ -193,81 +194,87 @@ template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev&
 
 // ---- line search with concurrent trials ---------------------------------------------------------------------
 // The reference tries step = 1, 1/2, 1/4, ... one rollout after the other and takes the first step whose merit does not
-// increase (ddp_fwd.ipp:29-60).  The trials are independent, so a block evaluates LS_NC of them at once: block =
-// LS_NC warps, warp w = trial slot w of 32 consecutive problems (lane = problem => coalesced SoA accesses).  Every trial
-// rolls out into its own scratch trajectory; the smallest accepted trial index wins exactly as in the sequential scan
-// (34 trials at most, last one kept on give-up, ddp_fwd.ipp:35-37), and the block copies the winner into the
-// new-trajectory storage.  The `rollouts` scalar keeps counting what the sequential algorithm would have run.
-// Trials per round: 8 for models of <= 2 joints (a 4096-problem batch is then 1024 warps, ~2 per SM sub-partition; almost
-// every launch has some problem that needs one of the trials 4..7, which used to cost the whole block a second round),
-// 4 for the arms (their per-thread dynamics scratch fills shared memory).
-template <int NJ> struct LsGeom { static constexpr int NC = Dim<NJ>::n <= 2 ? 8 : 4; };
+// increase (ddp_fwd.ipp:29-60).  A rollout is a latency chain of T dynamics evaluations, so a problem that needs the c-th
+// halving used to cost its whole launch c rollouts -- and some problem of a large batch always does.  The trials are
+// independent, so they run AT ONCE, spread over the grid: trial c of problem b is one thread (warp = trial c of 32
+// consecutive problems => coalesced SoA accesses), every trial rolls out into its own scratch trajectory (trial 0 straight
+// into the new-trajectory storage: the usual case, the full step, copies nothing), and a selection kernel then takes the
+// smallest accepted trial index exactly as the sequential scan would (34 trials at most, the last one kept on give-up,
+// ddp_fwd.ipp:35-37) and copies the winner.  Two waves: trials [0, NC1) for everybody, trials [NC1, 34) for the problems
+// still unresolved (almost always none: those threads exit at once).  The `rollouts` scalar keeps counting what the
+// sequential algorithm would have run.
+//   NC1: 8 for models of <= 2 joints (a 4096-problem batch is then ~2 warps per SM sub-partition: the FP64 pipe is the
+//   limit, more speculative trials would cost time), 16 for the arms (their batches leave most of the machine idle).
+template <int NJ> struct LsGeom {
+  static constexpr int NC1 = Dim<NJ>::n <= 2 ? 8 : 16;
+  static constexpr int WPB = 4;  // trial warps per block
+};
 constexpr int LS_MAX_TRIALS = 34;  // 2^-33 >= 1e-10 > 2^-34
+// scratch slots: trial c of wave 0 uses slot c (slot 0 is the new-trajectory storage itself), trial c of wave 1 slot c - NC1
+template <int NJ> constexpr int ls_slots() { return LsGeom<NJ>::NC1 > LS_MAX_TRIALS - LsGeom<NJ>::NC1 ? LsGeom<NJ>::NC1 : LS_MAX_TRIALS - LsGeom<NJ>::NC1; }
 
+// per-problem line-search state in `win` [B] ints: -1 unresolved, >= 0 resolved.  res: [LS_MAX_TRIALS][3][B] (sum, merit, plain)
 template <int NJ>
-__device__ __forceinline__ void linesearch_block(const ModelDev& m, const BatchDev& bd, const double* costs_old, double* xs_c, double* us_c, const Scratch& sc) {
-  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, LS_NC = LsGeom<NJ>::NC;
+__device__ __forceinline__ void ls_trials_block(const ModelDev& m, const BatchDev& bd, const double* costs_old, double* xs_c, double* us_c, double* res,
+                                                const int* win, int c0, int c1, const Scratch& sc) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
   const int B = bd.B, T = bd.T;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = bd.b0 + blockIdx.x * 32 + lane;
-  const bool valid = b < bd.b0 + bd.nb;
+  const int c = c0 + blockIdx.y * LsGeom<NJ>::WPB + w;
+  if (b >= bd.b0 + bd.nb || c >= c1) return;
+  if (bd.scal[(size_t)S_STATUS * B + b] != 0.0 || (c0 > 0 && win[b] != -1)) return;  // frozen, or resolved by the first wave
   const size_t xs_slot = (size_t)(T + 1) * nx * B, us_slot = (size_t)T * nu * B;
-  __shared__ double s_sum[LS_NC][32], s_merit[LS_NC][32], s_plain[LS_NC][32];
-  __shared__ int s_win[32];
-  const bool frozen = valid && bd.scal[(size_t)S_STATUS * B + b] != 0.0;
-  const double mu = valid ? bd.scal[(size_t)S_MU * B + b] : 0.0;
-  if (w == 0) s_win[lane] = (valid && !frozen) ? -1 : -2;  // -1 unresolved, -2 nothing to do
-  __syncthreads();
-  int win = -1;
-  for (int r = 0; r * LS_NC < LS_MAX_TRIALS; ++r) {
-    const int c = r * LS_NC + w;
-    const bool run = valid && !frozen && s_win[lane] == -1 && c < LS_MAX_TRIALS;
-    double sum = 1.0, merit = 0.0, plain = 0.0;
-    // trial slot 0 rolls out straight into the new-trajectory storage: when the first trial of a round wins (the
-    // usual case: the full step) nothing has to be copied
-    double* xo = w == 0 ? bd.xs_new : xs_c + w * xs_slot;
-    double* uo = w == 0 ? bd.us_new : us_c + w * us_slot;
-    if (run) rollout_candidate<NJ>(m, bd, b, ldexp(1.0, -c), mu, costs_old, xo, uo, &sum, &merit, &plain, sc, w == 0);
-    s_sum[w][lane] = run ? sum : 1.0;
-    s_merit[w][lane] = merit; s_plain[w][lane] = plain;
-    __syncthreads();
-    if (w == 0 && valid && !frozen && s_win[lane] == -1) {
-      int found = -1;
-      for (int k = 0; k < LS_NC; ++k)
-        if (found < 0 && r * LS_NC + k < LS_MAX_TRIALS && s_sum[k][lane] <= 0.0) found = k;
-      const bool last_round = (r + 1) * LS_NC >= LS_MAX_TRIALS;
-      if (found < 0 && last_round) found = (LS_MAX_TRIALS - 1) - r * LS_NC;  // give up: keep the last trial
-      if (found >= 0) {
-        const int cstar = r * LS_NC + found;
-        const bool accepted = s_sum[found][lane] <= 0.0;
-        bd.scal[(size_t)S_STEP * B + b] = accepted ? ldexp(1.0, -cstar) : ldexp(1.0, -LS_MAX_TRIALS);
-        bd.scal[(size_t)S_ROLLOUTS * B + b] += (double)(accepted ? cstar + 1 : LS_MAX_TRIALS);
-        bd.scal[(size_t)S_MERIT * B + b] = s_merit[found][lane];
-        bd.scal[(size_t)S_COST * B + b] = s_plain[found][lane];
-        s_win[lane] = 1000 + found;  // resolved in this round: slot `found`
-      }
+  const int slot = c - c0;
+  double* xo = c == 0 ? bd.xs_new : xs_c + slot * xs_slot;
+  double* uo = c == 0 ? bd.us_new : us_c + slot * us_slot;
+  double sum, merit, plain;
+  rollout_candidate<NJ>(m, bd, b, ldexp(1.0, -c), bd.scal[(size_t)S_MU * B + b], costs_old, xo, uo, &sum, &merit, &plain, sc, c == 0);
+  res[((size_t)c * 3 + 0) * B + b] = sum;
+  res[((size_t)c * 3 + 1) * B + b] = merit;
+  res[((size_t)c * 3 + 2) * B + b] = plain;
+}
+
+// one warp per problem: the smallest accepted trial of [c0, c1) wins; last wave: give up on the last trial.  The winner's
+// scratch trajectory is copied into the new-trajectory storage by the warp (element index strided by the batch size).
+template <int NJ>
+__device__ __forceinline__ void ls_select_warp(const BatchDev& bd, const double* xs_c, const double* us_c, const double* res, int* win, int c0, int c1, bool last) {
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
+  const int B = bd.B, T = bd.T;
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), b = bd.b0 + i;
+  if (i >= bd.nb) return;
+  const size_t xs_slot = (size_t)(T + 1) * nx * B, us_slot = (size_t)T * nu * B;
+  if (bd.scal[(size_t)S_STATUS * B + b] != 0.0) {
+    if (c0 == 0) {  // keep a frozen problem's trajectory through the pointer swap
+      for (int e = lane; e < (T + 1) * nx; e += 32) bd.xs_new[(size_t)e * B + b] = bd.xs[(size_t)e * B + b];
+      for (int e = lane; e < T * nu; e += 32) bd.us_new[(size_t)e * B + b] = bd.us[(size_t)e * B + b];
+      if (lane == 0) win[b] = 0;
     }
-    __syncthreads();
-    // problems resolved in this round: copy the winning scratch trajectory now (a later round would overwrite the slot)
-    if (valid && s_win[lane] > 1000) {
-      const int slot = s_win[lane] - 1000;
-      const double* xw = xs_c + slot * xs_slot;
-      const double* uw = us_c + slot * us_slot;
-#pragma unroll 8
-      for (int e = nx + w; e < (T + 1) * nx; e += LS_NC) bd.xs_new[(size_t)e * B + b] = xw[(size_t)e * B + b];
-#pragma unroll 8
-      for (int e = w; e < T * nu; e += LS_NC) bd.us_new[(size_t)e * B + b] = uw[(size_t)e * B + b];
-    }
-    __syncthreads();
-    if (w == 0 && valid && s_win[lane] >= 1000) s_win[lane] = 0;  // done
-    win = 0;
-    for (int k = 0; k < 32; ++k) win |= (s_win[k] == -1);
-    __syncthreads();
-    if (!win) break;
+    return;
   }
-  if (frozen) {  // keep a frozen problem's trajectory through the pointer swap
-    for (int e = w; e < (T + 1) * nx; e += LS_NC) bd.xs_new[(size_t)e * B + b] = bd.xs[(size_t)e * B + b];
-    for (int e = w; e < T * nu; e += LS_NC) bd.us_new[(size_t)e * B + b] = bd.us[(size_t)e * B + b];
+  if (c0 > 0 && win[b] != -1) return;
+  int found = -1;
+  for (int c = c0; c < c1; ++c)
+    if (found < 0 && res[((size_t)c * 3 + 0) * B + b] <= 0.0) found = c;
+  const bool accepted = found >= 0;
+  if (!accepted && last) found = LS_MAX_TRIALS - 1;  // give up: keep the last trial
+  if (found < 0) {
+    if (lane == 0) win[b] = -1;
+    return;
+  }
+  if (found != 0) {
+    const double* xw = xs_c + (size_t)(found - c0) * xs_slot;
+    const double* uw = us_c + (size_t)(found - c0) * us_slot;
+    for (int e = nx + lane; e < (T + 1) * nx; e += 32) bd.xs_new[(size_t)e * B + b] = xw[(size_t)e * B + b];
+    for (int e = lane; e < T * nu; e += 32) bd.us_new[(size_t)e * B + b] = uw[(size_t)e * B + b];
+  }
+  if (lane == 0) {
+    bd.scal[(size_t)S_STEP * B + b] = accepted ? ldexp(1.0, -found) : ldexp(1.0, -LS_MAX_TRIALS);
+    bd.scal[(size_t)S_ROLLOUTS * B + b] += (double)(accepted ? found + 1 : LS_MAX_TRIALS);
+    bd.scal[(size_t)S_MERIT * B + b] = res[((size_t)found * 3 + 1) * B + b];
+    bd.scal[(size_t)S_COST * B + b] = res[((size_t)found * 3 + 2) * B + b];
+    win[b] = found;
   }
 }
 
