@@ -3,8 +3,9 @@
 
 One "step" = one complete fixed-iteration DDP solve (ddp_solver_t::solve, ddp.hpp:744-842, `iterations`
 iterations + the reference's warm-up pass) of the whole synthetic batch from its initial trajectory.
-  value : knots linearized/s = B_total * T * iterations * steps / time, inputs already resident in HBM
-          (a device-side snapshot is restored at the start of every step), CUDA events on the launching stream;
+  value : knots linearized/s = (sum over problems of the iterations carried through) * T * steps / time -- a problem the
+          guard froze (status 2) or that converged early stops counting -- inputs already resident in HBM (a device-side
+          snapshot is restored at the start of every step), CUDA events on the launching stream;
   e2e   : the same metric through the C ABI with HOST (pinned) inputs: x0 / controls / targets / multiplier
           seeds go host->device, the initial rollout runs, the solve runs, and per-problem scalars plus the
           final trajectory come back device->host, every step.
@@ -33,13 +34,28 @@ METRIC = "DDP iterations/sec (batch x horizon knots linearized/sec)"
 
 
 def algorithmic_bytes_per_knot(w):
-    """bytes one linearization must write / one backward step must read, per knot."""
+    """BASELINE.md section 3 / SURVEY.md 8(d): bytes one linearization must write / one backward step must read, per knot,
+    counted on the reference's dense derivative_storage_t."""
     nd, nu, nx = w.ndx, w.nu, w.nx
     ne = w.ne_per_knot().astype(np.int64)
     slab = (nd + nu + nd * nd + nu * nd + nu * nu) + (nx + nd * nd + nd * nu + nd ** 3 + nd * nd * nu + nd * nu * nu) + \
         ne * (1 + nd + nu + nd * nd + nu * nd + nu * nu)
     lin = 8.0 * (slab + nx + nu)
     bwd = 8.0 * (slab + 2 * nx + ne + ne * nd + nu + nu * nd)
+    return float(lin.mean()), float(bwd.mean())
+
+
+def stored_bytes_per_knot(w):
+    """The same two figures for the records the kernels actually move (csrc/batch.cuh: the constants of the reference's
+    cost / Euler scheme and, with FD-of-Jacobians Hessians, the structurally zero tensor entries are not stored)."""
+    n, nd, nu, nx = w.n, w.ndx, w.nu, w.nx
+    ne = w.ne_per_knot().astype(np.int64)
+    dense = w.hess_mode == synthetic.HESS_FD_VALUES
+    tens = (nd ** 3 + nd * nu * nd + nd * nu * nu) if dense else (n * nd * nd + n * nu * n)
+    rec = nx + n * nd + n * nu + nu + tens + ne * (1 + nd + nu + nd * nd + nu * nd + nu * nu)
+    rec = (rec + 1) // 2 * 2
+    lin = 8.0 * (rec + nx + nu)
+    bwd = 8.0 * (rec - nx + 2 * nx + ne + ne * nd + nu + nu * nd)   # the backward pass does not read f
     return float(lin.mean()), float(bwd.mean())
 
 
@@ -102,13 +118,14 @@ class ClockSampler:
 
 
 def kernel_counts(workload_name):
-    """Per-kernel figures taken from ncu captures of this workload (profiles/r01_kernel_counts.json): executed FP64
+    """Per-kernel figures taken from ncu captures of this workload (profiles/r02_kernel_counts.json): executed FP64
     flops per knot and DRAM bytes per knot (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its knots)."""
-    p = os.path.join(ROOT, "profiles", "r01_kernel_counts.json")
-    if not os.path.exists(p):
-        return {}
-    with open(p) as f:
-        return json.load(f).get(workload_name, {})
+    for name in ("r02_kernel_counts.json",):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                return json.load(f).get(workload_name, {})
+    return {}
 
 
 def calibrate_cpu_sample(ol, w, nthreads, target_s):
@@ -131,15 +148,17 @@ def run_reference(args, w, rank):
     for _ in range(args.warmup):
         ol.solve_batch(w, g, min(nprob, nthreads), nthreads, 1, w.mu)
     t = 0.0
-    ro = rs = 0
+    ro = rs = its_done = div = 0
     for _ in range(args.steps):
         sec, info = ol.solve_batch(w, g, nprob, nthreads, w.iterations, w.mu)
-        t += sec; ro += info["rollouts"]; rs += info["restarts"]
-    val = nprob * w.T * w.iterations * args.steps / t
+        t += sec; ro += info["rollouts"]; rs += info["restarts"]; its_done += info["iterations"]; div = info["diverged"]
+    val = its_done * w.T / t   # knots of the iterations carried through (a problem frozen by the guard stops counting)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "knots/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "ddp_iterations_per_sec": nprob * w.iterations * args.steps / t,
-            "config": {"workload": w.name, "problems": nprob, "horizon": w.T, "iterations_per_step": w.iterations},
+            "dtype": "f64", "data": "synthetic", "ddp_iterations_per_sec": its_done / t,
+            "config": {"workload": w.name, "problems": nprob, "horizon": w.T, "iterations_per_step": w.iterations,
+                       "counting": "problem-iterations carried through x horizon (frozen problems stop counting)"},
+            "status": {"problems": nprob, "guarded": int(div)},
             "cpu_baseline": {"value": val, "unit": "knots/s", "cores": nthreads, "kind": "port",
                              "sample": f"{nprob} of {w.B} problems x {w.T} knots x {w.iterations} iterations per step, OpenMP over problems"},
             "e2e": {"value": val, "unit": "knots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -288,18 +307,26 @@ def main():
         tt = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=scal_t.device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(tt[0]), float(tt[1])
+    # problem-iterations carried through in one solve (identical every step: same inputs), summed over the ranks
+    its_done = float(sc["iterations"].sum())
+    st_hist = [int((sc["status"] == k).sum()) for k in (0, 1, 2)]
+    if world > 1:
+        tt = torch.tensor([its_done] + st_hist, dtype=torch.float64, device=scal_t.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        its_done = float(tt[0]); st_hist = [int(v) for v in tt[1:].tolist()]
     if rank == 0:
-        knots_per_step = world * B * T * its
+        knots_per_step = its_done * T
         value = knots_per_step * args.steps / (ms * 1e-3)
         e2e_val = knots_per_step * args.steps / (e2e_ms * 1e-3)
         hbm_peak, peak_src = read_peaks()
         lin_b, bwd_b = algorithmic_bytes_per_knot(w)
+        lin_sb, bwd_sb = stored_bytes_per_knot(w)
         n_lin = n_bwd = (its + 1) * ksteps  # launches in the kernel-timing leg (incl. the warm-up pass of every solve)
         kc = kernel_counts(w.name)
         kern = {
-            "linearize": {"ms_avg": phases["linearize"] / n_lin, "alg_bytes": lin_b * B * T},
-            "backward": {"ms_avg": phases["backward"] / n_bwd, "alg_bytes": bwd_b * B * T},
-            "forward": {"ms_avg": phases["forward"] / n_bwd, "alg_bytes": None},
+            "linearize": {"ms_avg": phases["linearize"] / n_lin, "alg_bytes": lin_b * B * T, "stored_bytes": lin_sb * B * T},
+            "backward": {"ms_avg": phases["backward"] / n_bwd, "alg_bytes": bwd_b * B * T, "stored_bytes": bwd_sb * B * T},
+            "forward": {"ms_avg": phases["forward"] / n_bwd, "alg_bytes": None, "stored_bytes": None},
         }
         dom = max(("linearize", "backward", "forward"), key=lambda k: phases[k])
         share = {k: phases[k] / max(sum(phases.values()), 1e-9) for k in phases}
@@ -311,7 +338,8 @@ def main():
         kout = {}
         for k, v in kern.items():
             kout[k] = {"ms_avg": v["ms_avg"], "share_of_step": share[k],
-                       "hbm_gbs": (v["alg_bytes"] / (v["ms_avg"] * 1e-3) / 1e9) if v["alg_bytes"] else None}
+                       "hbm_gbs": (v["alg_bytes"] / (v["ms_avg"] * 1e-3) / 1e9) if v["alg_bytes"] else None,
+                       "hbm_gbs_stored_records": (v["stored_bytes"] / (v["ms_avg"] * 1e-3) / 1e9) if v["stored_bytes"] else None}
             fl = kc.get(k, {}).get("fp64_flops_per_knot")
             if fl:
                 kout[k]["fp64_tflops"] = fl * B * T / (v["ms_avg"] * 1e-3) / 1e12
@@ -319,10 +347,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "knots/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "ddp_iterations_per_sec": world * B * its * args.steps / (ms * 1e-3),
+            "data": "synthetic", "ddp_iterations_per_sec": its_done * args.steps / (ms * 1e-3),
             "config": {"workload": w.name, "problems_per_gpu": B, "horizon": T, "iterations_per_step": its, "nx": w.nx, "nu": w.nu,
                        "hess_mode": "fd_of_jacobians" if w.hess_mode == 0 else "fd_of_values", "mu": w.mu,
-                       "l2": "working set (derivative slabs %.2f GB per GPU) is larger than L2" % (lin_b * B * T / 1e9),
+                       "l2": "working set (derivative slabs %.2f GB per GPU) is larger than L2" % (lin_sb * B * T / 1e9),
+                       "counting": "problem-iterations carried through x horizon (frozen problems stop counting)",
                        "parallelism": f"dp{world} (independent problem shards, NCCL gathers per-problem scalars only)"},
             "e2e": {"value": e2e_val, "unit": "knots/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": e2e_ms / args.steps, "timer": "wall clock between synchronisations"},
@@ -330,13 +359,19 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": rname, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": (traffic * B * T) if traffic else None, "peak_source": peak_src,
-                         "note": "algorithmic bytes per launch (BASELINE.md s3: 8*(slab+nx+nu) per knot written by the linearization, "
-                                 "8*(slab+2nx+nu+nu*ndx+eq) read by the backward pass) / mean CUDA-event launch duration; traffic = ncu "
-                                 "dram bytes per knot (profiles/r01_kernel_counts.json) x knots per launch"},
+                         "achieved_stored_records": rk["stored_bytes"] / (rk["ms_avg"] * 1e-3) / 1e9,
+                         "note": "algorithmic bytes per launch (BASELINE.md s3 / SURVEY 8d, counted on the reference's dense "
+                                 "derivative_storage_t: 8*(slab+nx+nu) per knot written by the linearization, 8*(slab+2nx+nu+nu*ndx+eq) read "
+                                 "by the backward pass) / mean CUDA-event launch duration; the kernels move only the state-dependent "
+                                 "entries (csrc/batch.cuh), so traffic (ncu dram bytes per knot, profiles/r02_kernel_counts.json, x knots "
+                                 "per launch) is BELOW the algorithmic bytes and achieved_stored_records is the rate on the bytes "
+                                 "actually stored"},
             "kernels": kout,
             "kernel_timing": {"steps": ksteps, "ms_per_step_one_stream": ms_one_stream,
                               "note": "launch durations measured with the solver on one stream (no overlap between sub-batches)"},
             "fp64_peak_tflops_measured": fp64_peak,
+            "status": {"problems": world * B, "active": st_hist[0], "converged": st_hist[1], "guarded": st_hist[2],
+                       "problem_iterations_per_solve": its_done},
             "rollouts_per_iteration": float(sc["rollouts"].mean() / its), "backward_restarts_per_problem": float(sc["restarts"].mean()),
             "opt_constr_median": float(np.median(sc["opt_constr"])),
         }
@@ -346,7 +381,7 @@ def main():
             nprob = args.cpu_sample or calibrate_cpu_sample(ol, w, nthreads, 10.0)
             gs = w.generate(B=nprob)
             sec, info = ol.solve_batch(w, gs, nprob, nthreads, its, w.mu)
-            line["cpu_baseline"] = {"value": nprob * T * its / sec, "unit": "knots/s", "cores": nthreads, "kind": "port",
+            line["cpu_baseline"] = {"value": info["iterations"] * T / sec, "unit": "knots/s", "cores": nthreads, "kind": "port",
                                     "sample": f"{nprob} of {B} problems x {T} knots x {its} iterations, OpenMP over problems, {sec:.1f} s"}
         print(json.dumps(line), flush=True)
     bt.close()

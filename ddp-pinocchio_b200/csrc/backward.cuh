@@ -155,6 +155,16 @@ template <int NU> inline bool chol_host(double* A, double* dinv) {
   return true;
 }
 
+// origin = x_t of the feedback sequence (ddp_bwd.ipp:136) for the problems a backward pass is about to process: one
+// element per thread before the pass (a plain copy: keeping it out of the recursion removes a global load -> store from
+// every knot's dependent path).  i in [0, T * nx * nb).
+DDPB_HD void fb_origin_knot(const BatchDev& bd, size_t i) {
+  const size_t e = i / bd.nb;
+  const int b = bd.b0 + (int)(i - e * bd.nb);
+  if (bd.scal[(size_t)S_STATUS * bd.B + b] != 0.0) return;
+  bd.fb_origin[e * bd.B + b] = bd.xs[e * bd.B + b];
+}
+
 template <int V> struct IntC { static constexpr int value = V; };
 
 // sum_k vx[k] * f3[k] over a run of RL doubles with two interleaved partial sums (even / odd k); 16-byte loads on the
@@ -365,8 +375,6 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
       const double* rec = slab_rec(bd, t, b, L.size);
       // ---- phase A: head of the record (prefetched) ; tensors -> V_x contraction ----------------------------------------
       const double* hd = sm + (hcur ? S::head2 : S::head);
-      double xorg = 0.0;
-      if (tid < nx) xorg = bd.xs[((size_t)t * nx + tid) * B + b];
       {
         // W(e) = sum_k V_x[r0 + k] T_e[k] for every stored tensor element e (a run of RL doubles at L.fxx + e RL)
         auto contract = [&](auto rl_c, auto rs_c, auto ew_c) {
@@ -646,7 +654,6 @@ DDPB_HD void backward_problem(const BatchDev& bd, int b, double* sm, const Ex& e
         }
       }
 #endif
-      if (tid < nx) bd.fb_origin[((size_t)t * nx + tid) * B + b] = xorg;
       bsync();
       DDPB_PHASE_MARK(bd, 11, pc_);
       if (sm[S::flags] == 0.0) {

@@ -76,7 +76,7 @@ DDPB_HD bool lg_knot(const BatchDev& bd, int b, int t, bool live, const Rd& R, d
 
   // ---- block 1: VF = V_xx f_x, VU = V_xx f_u, tensor contractions with V_x, Q_x, Q_u ------------------------------------
   // rows k < n of f_x are [I, dt I], those of f_u zero (batch.cuh)
-  double VF[LG_NL], VU[LG_NL], W[LG_NL], WU[LG_NL], WUU[LG_NL], QX[LG_NL], FR[LG_NL][n], GRr[LG_NL][n], XS[LG_NL];
+  double VF[LG_NL], VU[LG_NL], W[LG_NL], WU[LG_NL], WUU[LG_NL], QX[LG_NL], FR[LG_NL][n], GRr[LG_NL][n];
   LG_FOR(g) {
     const int r = g % nd, c = g / nd;
     double vrow[n], xk[RT], xn[n];
@@ -111,8 +111,6 @@ DDPB_HD bool lg_knot(const BatchDev& bd, int b, int t, bool live, const Rd& R, d
     LV(W) = a0 + a1;
     LV(WU) = (c < RI) ? (b0 + b1) : 0.0;   // tensor term of Q_ux(r, c): slices c >= RI are structural zeros
     LV(WUU) = c0 + c1;
-    // origin = x_t (ddp_bwd.ipp:136): loaded here so that its store in block 3 never waits for memory
-    LV(XS) = (live && g < nx) ? bd.xs[((size_t)t * nx + (g < nx ? g : 0)) * B + b] : 0.0;
     // Q_x(r) (used from the lanes c = 0) and Q_u(r), r < nu (used from the lanes c = nu)
     double qx = r < n ? xtop : dt * xtop;
     double qu = 0.0;
@@ -244,7 +242,8 @@ DDPB_HD bool lg_knot(const BatchDev& bd, int b, int t, bool live, const Rd& R, d
 #pragma unroll
     for (int i = 0; i < nu; ++i) { LV(KC)[i] = rhsK[i]; LV(KK)[i] = rhsk[i]; }
     if (okl && live) {
-      // lane (r < nu, c) owns K(r, c), lane (r < nu, c = 0) also k(r); lanes g < nx the origin x_t (ddp_bwd.ipp:134-136)
+      // lane (r < nu, c) owns K(r, c), lane (r < nu, c = 0) also k(r)  (ddp_bwd.ipp:134-135; the origin x_t of :136 is
+      // written by fb_origin_knot before the pass, see backward.cuh)
       double kv = rhsK[0], kkv = rhsk[0];
 #pragma unroll
       for (int i = 1; i < nu; ++i)
@@ -253,7 +252,6 @@ DDPB_HD bool lg_knot(const BatchDev& bd, int b, int t, bool live, const Rd& R, d
         bd.fb_K[((size_t)t * nu * nd + c * nu + r) * B + b] = kv;
         if (c == 0) bd.fb_k[((size_t)t * nu + r) * B + b] = kkv;
       }
-      if (g < nx) bd.fb_origin[((size_t)t * nx + g) * B + b] = LV(XS);
     }
   }
   // (no early return on failure: the other group of the warp still needs this group's lanes at the shuffles below)

@@ -44,6 +44,10 @@ template <int NJ, int MODE> __global__ void __launch_bounds__(MODE == HESS_FD_JA
   if (!any) return;  // every problem of the group is frozen (converged / diverged)
   linearize_group<NJ, MODE>(m, bd, t, b0, nk, kpb, ne_sm, sm, DevExec{});
 }
+template <int NJ> __global__ void fb_origin_kernel(const __grid_constant__ BatchDev bd) {  // (template: one copy per translation unit)
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)bd.T * bd.nx * bd.nb) fb_origin_knot(bd, i);
+}
 #if DDPB_NJ <= 2
 // one thread per evaluation point (linearize_pt.cuh): 4 independent warps per CTA, 255 registers per thread
 constexpr int PT_WARPS = 4;
@@ -202,6 +206,12 @@ template <> bool Launch<KNJ>::linearize_pt(const ModelDev& m, const BatchDev& bd
 #endif
 }
 template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
+#if DDPB_NJ > 0
+  {
+    const size_t ne_ = (size_t)bd.T * bd.nx * bd.nb;
+    fb_origin_kernel<KNJ><<<(unsigned)((ne_ + 255) / 256), 256, 0, s>>>(bd);
+  }
+#endif
 #if DDPB_NJ > 2
   (void)threads;
   if (bd.hess_mode == HESS_FD_VALUES) backward_kernel<KNJ, true><<<bd.nb, BwdGeom<KNJ>::BT, smem, s>>>(bd);

@@ -136,12 +136,22 @@ template <int NJ> __device__ __forceinline__ void linearize_pt_warp(const ModelD
   constexpr int nx = 2 * NJ, nu = NJ, n = NJ, nd = 2 * NJ;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long total = (long long)nt * bd.nb;
+  // 32-bit knot ids (a launch covers at most T x B < 2^31 knots); the warp's first knot is split into (knot, problem)
+  // once, the others follow by increments -- no division per thread or per stored chunk
+  const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned total = (unsigned)nt * (unsigned)bd.nb, nb = (unsigned)bd.nb;
   const int kk = lane / G::P, p = lane - kk * G::P;
-  const long long kid = warp_global * G::KPW + kk;
+  const unsigned kid_first = warp_global * G::KPW;
+  const unsigned tt_first = kid_first / nb, bi_first = kid_first - tt_first * nb;
+  auto split = [&](int k, int& tq, int& bq) {  // knot kid_first + k, k < KPW <= nb + ... : at most a few wraps
+    unsigned tt = tt_first, bi = bi_first + (unsigned)k;
+    while (bi >= nb) { bi -= nb; ++tt; }
+    tq = t0 + (int)tt; bq = bd.b0 + (int)bi;
+  };
+  const unsigned kid = kid_first + (unsigned)kk;
   const bool inrange = kk < G::KPW && kid < total;
-  const int t = t0 + (int)(inrange ? kid / bd.nb : 0), b = bd.b0 + (int)(inrange ? kid % bd.nb : 0);
+  int t = t0, b = bd.b0;
+  if (inrange) split(kk, t, b);
   const int B = bd.B;
   const bool act = inrange && bd.scal[(size_t)S_STATUS * B + b] == 0.0;  // frozen problems keep their records
   PtOut<NJ> o;
@@ -173,10 +183,10 @@ template <int NJ> __device__ __forceinline__ void linearize_pt_warp(const ModelD
   // the warp's records, 16 bytes per lane and store: consecutive lanes -> consecutive chunks of a record
   constexpr int CH = G::SIZE / 2;
   for (int idx = lane; idx < G::KPW * CH; idx += 32) {
-    const int k2 = idx / CH, c = idx - k2 * CH;
-    const long long kid2 = warp_global * G::KPW + k2;
-    if (kid2 >= total) break;
-    const int t2 = t0 + (int)(kid2 / bd.nb), b2 = bd.b0 + (int)(kid2 % bd.nb);
+    const int k2 = idx / CH, c = idx - k2 * CH;   // CH is a compile-time constant
+    if (kid_first + (unsigned)k2 >= total) break;
+    int t2, b2;
+    split(k2, t2, b2);
     if (bd.scal[(size_t)S_STATUS * B + b2] != 0.0) continue;
     reinterpret_cast<double2*>(slab_rec(bd, t2, b2, G::SIZE))[c] = reinterpret_cast<const double2*>(stage + k2 * G::SIZE)[c];
   }

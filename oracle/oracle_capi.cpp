@@ -376,11 +376,12 @@ extern "C" void orc_solve(void* h, int prec, int max_iter, double thr, double mu
 // xs0: [nprob][(T+1) nx], us0: [nprob][T nu], targets: [nprob][sum ne], mjac0: [nprob][sum ne * ndx]
 extern "C" double orc_solve_batch(const orc_model_desc* m, const orc_problem_desc* d, int nprob, int nthreads, int max_iter, double thr, double mu,
                        double reg, double w, double n, const double* xs0, const double* us0, const double* targets, const double* mjac0,
-                       double* xs_out, double* us_out, int* rollouts_total, int* restarts_total) {
-  int ro = 0, rs = 0;
+                       double* xs_out, double* us_out, int* rollouts_total, int* restarts_total, long long* iterations_total, int* diverged_total) {
+  int ro = 0, rs = 0, dv = 0;
+  long long it = 0;
   auto t0 = std::chrono::steady_clock::now();
 #ifdef _OPENMP
-#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1) reduction(+ : ro, rs)
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1) reduction(+ : ro, rs, dv, it)
 #endif
   for (int b = 0; b < nprob; ++b) {
     Problem<double> p;
@@ -396,10 +397,15 @@ extern "C" double orc_solve_batch(const orc_model_desc* m, const orc_problem_des
     if (xs_out) out(xs_out + (size_t)b * (T + 1) * nx, R.xs);
     if (us_out) out(us_out + (size_t)b * T * nu, R.us);
     for (auto& l : R.log) { ro += l.rollouts; rs += l.restarts; }
+    // iterations carried through: a problem frozen by the guard (status 2) does not complete the iteration it stopped in
+    it += (long long)R.log.size() - (R.status == 2 && !R.log.empty() ? 1 : 0);
+    dv += R.status == 2;
   }
   auto t1 = std::chrono::steady_clock::now();
   if (rollouts_total) *rollouts_total = ro;
   if (restarts_total) *restarts_total = rs;
+  if (iterations_total) *iterations_total = it;
+  if (diverged_total) *diverged_total = dv;
   return std::chrono::duration<double>(t1 - t0).count();
 }
 

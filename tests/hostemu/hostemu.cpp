@@ -78,6 +78,7 @@ void* emu_create(const ddpb_model_desc* d, int B, int T, const int* ne_per_knot,
   BatchDev& bd = h->bd;
   std::memset(&bd, 0, sizeof(bd));
   bd.B = B; bd.T = T; bd.n = n; bd.nx = 2 * n; bd.nu = n;
+  bd.b0 = 0; bd.nb = B;
   bd.hess_mode = p->hess_mode; bd.eq_kind = p->eq_kind; bd.frame_id = p->frame_id; bd.jac_mode = p->frame_jac_mode;
   bd.dt = p->dt; bd.c = p->c;
   bd.max_restarts = p->max_backward_restarts < 0 ? 0 : p->max_backward_restarts;
@@ -145,6 +146,7 @@ void emu_linearize(void* hv) {
 void emu_backward(void* hv) {
   Emu* h = (Emu*)hv;
   const BatchDev& bd = h->bd;
+  for (size_t i = 0; i < (size_t)bd.T * bd.nx * bd.B; ++i) fb_origin_knot(bd, i);   // bd.b0 = 0, bd.nb = B in the emulation
   EMU_NJ(h->nj, {
     std::vector<double> sm(BwdSmem<NJ>::SIZE);
     for (int b = 0; b < bd.B; ++b)

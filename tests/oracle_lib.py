@@ -252,8 +252,8 @@ def solve_batch(w, data, nprob, nthreads, max_iter, mu, reg=0.0, thr=0.0, want_t
         tg = np.zeros(1); mj = np.zeros(1)
     xs_out = np.zeros_like(xs0) if want_traj else None
     us_out = np.zeros_like(us0) if want_traj else None
-    ro, rs = C.c_int(), C.c_int()
+    ro, rs, dv, it = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
     sec = lib().orc_solve_batch(C.byref(md), C.byref(pd), nprob, nthreads, max_iter, C.c_double(thr), C.c_double(mu), C.c_double(reg),
                                 C.c_double(1.0 / mu), C.c_double(1.0 / mu ** 0.1), _d(xs0), _d(us0), _d(tg), _d(mj),
-                                _d(xs_out) if want_traj else None, _d(us_out) if want_traj else None, C.byref(ro), C.byref(rs))
-    return sec, dict(rollouts=ro.value, restarts=rs.value, xs=xs_out, us=us_out)
+                                _d(xs_out) if want_traj else None, _d(us_out) if want_traj else None, C.byref(ro), C.byref(rs), C.byref(it), C.byref(dv))
+    return sec, dict(rollouts=ro.value, restarts=rs.value, iterations=it.value, diverged=dv.value, xs=xs_out, us=us_out)
