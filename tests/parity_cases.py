@@ -272,6 +272,53 @@ def check_forward(make, w):
     bt.close()
 
 
+def check_structure_is_enforced(make, w, exc):
+    """The slab keeps the constants of the reference's cost / Euler scheme implicit: derivatives that do not have that
+    structure (e.g. a dense random f_x) are refused by set_derivatives instead of being silently truncated."""
+    g, bt, us, orcs, rng = setup(make, w)
+    xs, _ = bt.get_trajectory()
+    ds = [orcs[b].compute_derivatives(xs[b], us[b]) for b in range(w.B)]
+    d = {f: np.stack([ds[b][f] for b in range(w.B)]) for f in ol.DERIV_FIELDS}
+    bt.set_derivatives(d)                                  # the oracle's derivatives have the structure
+    bad = dict(d); bad["fx"] = d["fx"] + 1e-3              # rows k < n of f_x are no longer [I, dt I]
+    import pytest
+    with pytest.raises(exc):
+        bt.set_derivatives(bad)
+    bad = dict(d); bad["luu"] = d["luu"] * 2.0             # l_uu != c I
+    with pytest.raises(exc):
+        bt.set_derivatives(bad)
+    bt.close()
+
+
+def check_forward_many_halvings(make, w, scale=3e3):
+    """Line search with gains scaled so that the full step is rejected many times: the accepted step index (and the
+    trajectory it produces) equals the oracle's sequential halving, including problems resolved by the second wave of
+    concurrent trials and give-ups after 34 trials."""
+    g, bt, us, orcs, rng = setup(make, w)
+    xs, _ = bt.get_trajectory()
+    mval = rng.uniform(-1, 1, (w.B, bt.ne_total))
+    bt.set_multipliers(mval, g["mult_jac"])
+    ds = [orcs[b].compute_derivatives(xs[b], us[b]) for b in range(w.B)]
+    bt.set_derivatives({f: np.stack([ds[b][f] for b in range(w.B)]) for f in ol.DERIV_FIELDS})
+    mu_e, _ = bt.backward_pass(w.mu, 0.0)
+    _, k, K = bt.get_feedback()
+    sc = np.ones(w.B); sc[::2] = scale; sc[1::3] = scale ** 2    # different problems need different numbers of halvings
+    bt.set_feedback(k * sc[:, None, None], K)
+    bt.set_scalar("mu", mu_e); bt.set_scalar("status", 0.0); bt.set_scalar("rollouts", 0.0)
+    step = bt.forward_pass()
+    xn, un = bt.get_new_trajectory()
+    ro = bt.get_scalars()["rollouts"]
+    mo, mv, mj = bt.get_multipliers()
+    seen = set()
+    for b in range(w.B):
+        xo, uo, so, rollouts = orcs[b].forward_pass(xs[b], us[b], mo[b], mv[b], mj[b], k[b] * sc[b], K[b], mu_e[b])
+        assert step[b] == so and int(ro[b]) == int(rollouts), (b, step[b], so, ro[b], rollouts)
+        assert relerr(xn[b], xo) < TOL_ROLLOUT and relerr(un[b], uo) < TOL_ROLLOUT
+        seen.add(int(rollouts))
+    bt.close()
+    return seen
+
+
 def check_solve(make, w, iters):
     """End to end: same control flow as the double oracle and trajectories as close to the __float128 oracle
     as the double oracle's own (the FD Hessians make 1e-8 unreachable for ANY two double implementations,

@@ -51,3 +51,14 @@ def test_solve(name, T, iters):
         assert s["dev_vs_quad"] <= 50 * s["double_vs_quad"] + 1e-8, s
         assert s["dev_vs_double"] <= 50 * s["double_vs_quad"] + 1e-8, s
     assert sum(s["same_flow"] for s in stats) >= len(stats) - 1, stats
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_slab_structure_is_enforced(name):
+    pc.check_structure_is_enforced(make, pc.S.workload(name, B=2, T=5), RuntimeError)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_forward_many_halvings(name):
+    seen = pc.check_forward_many_halvings(make, pc.S.workload(name, B=7, T=8))
+    assert max(seen) > 4      # some problem needed more than four trials

@@ -184,3 +184,61 @@ def test_repeated_solves_replay_identically():
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_slab_structure_is_enforced(name):
+    from ddp_pinocchio_b200 import capi
+    pc.check_structure_is_enforced(make, pc.S.workload(name, B=2, T=5), capi.DdpbError)
+
+
+@pytest.mark.parametrize("name,B", [("c2", 70), ("c3", 40), ("c5", 9)])
+def test_forward_many_halvings(name, B):
+    """All line-search trials run at once in two waves (8 or 16 trials, then the rest up to 34): the accepted step must be
+    the one the reference's sequential halving finds, whichever wave resolves the problem."""
+    seen = pc.check_forward_many_halvings(make, pc.S.workload(name, B=B, T=8))
+    assert max(seen) > 16 and min(seen) == 1, seen      # both waves exercised, and the full step somewhere
+
+
+def test_guarded_exit_while_other_kernels_run():
+    """A problem whose Cholesky keeps failing at a knot t > 0 leaves the backward kernel through the guarded exit while
+    the copy staged for knot t-1 is still in flight; the kernel must drain it before its shared memory is handed to
+    another kernel.  Two batches on their own streams, driven from two host threads: batch A's backward pass hits the
+    guard on every problem (doctored f_xx: the value function turns indefinite three knots into the pass) in a loop,
+    batch B linearizes concurrently; B's records must equal the ones it produces alone, every time."""
+    import threading
+    import torch
+    wa = pc.S.workload("c3", B=256, T=12)
+    ga, bta, usa, orcs, rng = pc.setup(make, wa)
+    bta.set_stream(torch.cuda.Stream().cuda_stream)
+    bta.set_multipliers(rng.uniform(-1, 1, (wa.B, bta.ne_total)), ga["mult_jac"])
+    bta.compute_derivatives()
+    D = bta.get_derivatives()
+    D["fxx"] = D["fxx"] - 1e12 * (np.abs(D["fxx"]) > 0)      # only state-dependent entries change: the structure is kept
+    bta.set_derivatives(D)
+    wb = pc.S.workload("c3", B=512, T=20)
+    gb, btb, usb, _, _ = pc.setup(make, wb)
+    btb.set_stream(torch.cuda.Stream().cuda_stream)
+    btb.compute_derivatives()
+    ref = btb.get_derivatives(["fx", "fxx", "f_val"])
+    stop = threading.Event()
+    seen_guard = []
+
+    def hammer():
+        while not stop.is_set():
+            bta.set_scalar("status", 0.0)
+            bta.backward_pass(1e4, 0.0)
+            seen_guard.append(int((bta.get_scalars()["status"] == 2).sum()))
+
+    th = threading.Thread(target=hammer)
+    th.start()
+    try:
+        for _ in range(25):
+            btb.compute_derivatives()
+            cur = btb.get_derivatives(["fx", "fxx", "f_val"])
+            for f in ref:
+                assert np.array_equal(cur[f], ref[f]), f
+    finally:
+        stop.set(); th.join()
+    assert seen_guard and max(seen_guard) > wa.B // 2, seen_guard[:5]     # the guarded exit was really taken
+    bta.close(); btb.close()
