@@ -63,9 +63,11 @@ DDPB_HD bool lg_knot(const BatchDev& bd, int b, int t, bool live, const Rd& R, d
   const int B = bd.B;
   const double dt = bd.dt;
   const int ne = live ? bd.ne[t] : 0;
-  const RecLayout L = rec_layout(n, ne, bd.hess_mode);
-  const RecView GR = rec_view(bd, live ? t : 0, b, L.size);  // equality blocks (ne > 0 only), read where they are used
-  const size_t eo = live ? bd.eq_off[t] : 0;
+  // equality blocks (ne > 0 only: their offsets are not even computed otherwise), read from global memory where they are used
+  RecLayout L;
+  const double* GR = nullptr;
+  size_t eo = 0;
+  if (ne > 0) { L = rec_layout(n, ne, bd.hess_mode); GR = slab_rec(bd, t, b, L.size); eo = bd.eq_off[t]; }
   auto eqv = [&](int k) -> double { return GR[L.eq + k]; };
   auto eqx = [&](int k, int c) -> double { return GR[L.eq_x + c * ne + k]; };
   auto equ = [&](int k, int c) -> double { return GR[L.eq_u + c * ne + k]; };
@@ -350,8 +352,7 @@ template <int NJ, bool DENSE> __device__ __forceinline__ void backward_lg_warp(c
   // stage the record of knot tk of this group's problem into ring slot tk % NS: chunks lgx, lgx + LG, ...
   auto fetch = [&](int tk) {
     if (tk < 0 || !st.active) return;
-    const RecLayout Lk = rec_layout(NJ, bd.ne[tk], bd.hess_mode);
-    const double* src = slab_rec(bd, tk, b, Lk.size) + O::o_fx;
+    const double* src = slab_rec_t(bd, tk, b) + O::o_fx;
     double* dst = ring + (size_t)(tk % NS) * STAGE;
 #pragma unroll
     for (int c = 0; c < (NCH + LG - 1) / LG; ++c) {

@@ -125,6 +125,12 @@ struct BatchDev {
 DDPB_HD double* slab_rec(const BatchDev& bd, int t, int b, int rec_size) {
   return bd.slab + (size_t)bd.slab_off[t] * bd.B + (size_t)b * rec_size;
 }
+// the same without knowing the knot's row count: the record size of knot t is the step of the prefix table (two cached
+// loads instead of evaluating rec_layout -- the offsets of the state-dependent blocks do not depend on the row count)
+DDPB_HD double* slab_rec_t(const BatchDev& bd, int t, int b) {
+  const long long o0 = bd.slab_off[t], o1 = bd.slab_off[t + 1];
+  return bd.slab + (size_t)o0 * bd.B + (size_t)b * (size_t)(o1 - o0);
+}
 using RecView = double*;
 DDPB_HD RecView rec_view(const BatchDev& bd, int t, int b, int rec_size) { return slab_rec(bd, t, b, rec_size); }
 

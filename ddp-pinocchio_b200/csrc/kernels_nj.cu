@@ -125,15 +125,16 @@ template <int NJ> __global__ void mult_update_kernel(const __grid_constant__ Bat
   mult_update_knot<NJ>(bd, bd.b0 + (int)(i % bd.nb), (int)(i / bd.nb));
 }
 template <int NJ> __global__ void al_decide_kernel(const __grid_constant__ BatchDev bd, double thr, int phase) {
-  const int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (i >= bd.nb) return;
-  al_decide_warp<NJ>(bd, bd.b0 + i, thr, phase);
+  const int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / AdjGeom<NJ>::G);
+  const bool live = i < bd.nb;
+  al_decide_warp<NJ>(bd, bd.b0 + (live ? i : 0), live, thr, phase);
 }
 template <int NJ> __global__ void optimality_kernel(const __grid_constant__ BatchDev bd) {
-  const int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), b = bd.b0 + i;
-  if (i >= bd.nb) return;
+  const int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / AdjGeom<NJ>::G);
+  const bool live = i < bd.nb;
+  const int b = bd.b0 + (live ? i : 0);
   const double oo = optimality_obj_warp<NJ>(bd, b, bd.scal[(size_t)S_MU * bd.B + b]);
-  if ((threadIdx.x & 31) != 0) return;
+  if ((threadIdx.x & (AdjGeom<NJ>::G - 1)) != 0 || !live) return;
   bd.scal[(size_t)S_OPT_OBJ * bd.B + b] = oo;
   bd.scal[(size_t)S_OPT_CONSTR * bd.B + b] = optimality_constr_problem<NJ>(bd, b);
 }
@@ -252,14 +253,14 @@ template <> void Launch<KNJ>::cost(const ModelDev& m, const BatchDev& bd, double
 }
 template <> void Launch<KNJ>::al_update(const BatchDev& bd, double thr, cudaStream_t s) {
   const size_t nkb = (size_t)bd.nb * bd.T;
-  const unsigned wblocks = (unsigned)(((size_t)bd.nb * 32 + 127) / 128);
+  const unsigned wblocks = (unsigned)(((size_t)bd.nb * AdjGeom<KNJ>::G + 127) / 128);
   origin_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 0);
   mult_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 1);
 }
 template <> void Launch<KNJ>::optimality(const BatchDev& bd, cudaStream_t s) {
-  optimality_kernel<KNJ><<<(unsigned)(((size_t)bd.nb * 32 + 127) / 128), 128, 0, s>>>(bd);
+  optimality_kernel<KNJ><<<(unsigned)(((size_t)bd.nb * AdjGeom<KNJ>::G + 127) / 128), 128, 0, s>>>(bd);
 }
 
 }  // namespace ddpb

@@ -69,12 +69,18 @@ template <int NJ> __device__ __forceinline__ void mult_update_knot(const BatchDe
     }
 }
 
-// one warp: opt_obj of problem b (all lanes return the same value)
+// lanes per problem of the adjoint sweeps: the smallest power of two holding one lane per adjoint / control component
+// (8 for the 2R chain: four problems per warp, a quarter of the warp instructions of one warp per problem)
+template <int NJ> struct AdjGeom {
+  static constexpr int need = 3 * Dim<NJ>::n;
+  static constexpr int G = need <= 4 ? 4 : (need <= 8 ? 8 : (need <= 16 ? 16 : 32));
+};
+// one lane group: opt_obj of problem b (all lanes of the group return the same value); shuffles are group-relative
 template <int NJ> __device__ __forceinline__ double optimality_obj_warp(const BatchDev& bd, int b, double mu) {
-  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n;
+  constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n, G = AdjGeom<NJ>::G;
   static_assert(nd + nu <= 32, "one lane per adjoint / control component");
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & (G - 1);
   const int B = bd.B;
   const bool isx = lane < nd, isu = lane >= nd && lane < nd + nu;
   const int col = isx ? lane : lane - nd;
@@ -86,18 +92,28 @@ template <int NJ> __device__ __forceinline__ double optimality_obj_warp(const Ba
   // stored rows (k >= n, batch.cuh) of column `col` of f_x (lanes < nd) or f_u (next nu lanes) and the matching l_u
   // entry (l_x = 0), loaded one knot ahead
   double cur[n], nxt[n], lcur = 0.0, lnxt = 0.0;
+  // offsets of the head blocks (batch.cuh rec_layout: independent of the knot's equality rows)
+  constexpr int o_fx = nx, o_fu = o_fx + n * nd, o_lu = o_fu + n * nu;
   auto load = [&](int t, double* dst, double& l) {
-    const RecLayout L = rec_layout(n, bd.ne[t], bd.hess_mode);
-    const RecView rec = rec_view(bd, t, b, L.size);
     if (isx || isu) {
-      const int c0 = (isx ? L.fx : L.fu) + col * n;
+      const double* rec = slab_rec_t(bd, t, b);
+      const int c0 = (isx ? o_fx : o_fu) + col * n;
 #pragma unroll
       for (int k = 0; k < n; ++k) dst[k] = rec[c0 + k];
-      l = isx ? 0.0 : rec[L.lu + col];
+      l = isx ? 0.0 : rec[o_lu + col];
     }
   };
+  // the sweep is a latency chain of T steps fed by ~150 bytes of the slab each: the column it needs is in registers one
+  // knot ahead, and the record PF knots ahead is pulled into L2 so that this register load never waits for HBM
+  constexpr int PF = 6;
+  auto prefetch = [&](int t) {
+    if (t < 0 || !(isx || isu)) return;
+    l2_prefetch(slab_rec_t(bd, t, b) + (isx ? o_fx : o_fu) + col * n);
+  };
+  for (int k = 2; k <= PF; ++k) prefetch(bd.T - k);
   load(bd.T - 1, cur, lcur);
   for (int t = bd.T - 1; t >= 0; --t) {
+    prefetch(t - 1 - PF);
     if (t > 0) load(t - 1, nxt, lnxt);
     const int ne = bd.ne[t];
     // adj . column: rows k < n of f_x are the constants [I, dt I], those of f_u zeros
@@ -147,12 +163,12 @@ template <int NJ> __device__ __forceinline__ double optimality_obj_warp(const Ba
     // |lu|^2 in the reference's order (i = 0 .. nu-1), then the new adjoint to every lane
     double sq = 0.0;
 #pragma unroll
-    for (int i = 0; i < nu; ++i) { const double li = __shfl_sync(FULL, v, nd + i); sq += li * li; }
+    for (int i = 0; i < nu; ++i) { const double li = __shfl_sync(FULL, v, nd + i, G); sq += li * li; }
     const double nrm = sqrt(sq);
     if (retval < nrm) retval = nrm;
 #pragma unroll
-    for (int k = 0; k < nd; ++k) adj[k] = __shfl_sync(FULL, v, k);
-    atop = __shfl_sync(FULL, v, isx ? (col < n ? col : col - n) : 0);
+    for (int k = 0; k < nd; ++k) adj[k] = __shfl_sync(FULL, v, k, G);
+    atop = __shfl_sync(FULL, v, isx ? (col < n ? col : col - n) : 0, G);
 #pragma unroll
     for (int k = 0; k < n; ++k) cur[k] = nxt[k];
     lcur = lnxt;
@@ -163,14 +179,18 @@ template <int NJ> __device__ __forceinline__ double optimality_obj_warp(const Ba
 // optimality measures + the decision of update_derivatives / solve's switch (ddp.hpp:660-695, 786-802) for one problem
 // per warp.  phase 0: first sweep and decision (S_FLAG: 1 = multipliers will be updated); phase 1: after the
 // multiplier update, second sweep for the flagged problems (n = opt_obj / mu^0.1, w /= mu).
-template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev& bd, int b, double thr, int phase) {
+// (b, live): the group's problem; groups past the end of the sub-batch still take part in the warp's shuffles
+template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev& bd, int b, bool live, double thr, int phase) {
   const int B = bd.B;
-  const int lane = threadIdx.x & 31;
-  if (bd.scal[(size_t)S_STATUS * B + b] != 0.0) return;
+  const int lane = threadIdx.x & (AdjGeom<NJ>::G - 1);
+  const bool act = live && bd.scal[(size_t)S_STATUS * B + b] == 0.0;
+  const bool flagged = act && (phase == 0 || bd.scal[(size_t)S_FLAG * B + b] == 1.0);
+  // a whole warp without work leaves together; otherwise every lane runs the sweep (idle groups on problem b, harmlessly)
+  if (!__any_sync(0xffffffffu, flagged)) return;
   double mu = bd.scal[(size_t)S_MU * B + b];
   if (phase == 0) {
     const double opt_obj = optimality_obj_warp<NJ>(bd, b, mu);
-    if (lane != 0) return;
+    if (lane != 0 || !act) return;
     const double opt_constr = optimality_constr_problem<NJ>(bd, b);
     bd.scal[(size_t)S_OPT_OBJ * B + b] = opt_obj;
     bd.scal[(size_t)S_OPT_CONSTR * B + b] = opt_constr;
@@ -183,9 +203,8 @@ template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev&
     }
     bd.scal[(size_t)S_FLAG * B + b] = flag;
   } else {
-    if (bd.scal[(size_t)S_FLAG * B + b] != 1.0) return;
     const double oo = optimality_obj_warp<NJ>(bd, b, mu);
-    if (lane != 0) return;
+    if (lane != 0 || !flagged) return;
     bd.scal[(size_t)S_N * B + b] = oo / pow(mu, 0.1);
     bd.scal[(size_t)S_W * B + b] = bd.scal[(size_t)S_W * B + b] / mu;
     bd.scal[(size_t)S_MULT_UPDATES * B + b] += 1.0;
