@@ -22,7 +22,8 @@ EXPORTS = ["ddpb_model_create", "ddpb_model_destroy", "ddpb_batch_create", "ddpb
            "ddpb_get_scalars", "ddpb_scalars_device_ptr", "ddpb_compute_derivatives", "ddpb_backward_pass", "ddpb_forward_pass",
            "ddpb_cost_seq_aug", "ddpb_optimality", "ddpb_solve", "ddpb_solve_async", "ddpb_batch_dims", "ddpb_launch_count",
            "ddpb_phase_times", "ddpb_enable_phase_timing", "ddpb_snapshot_save", "ddpb_snapshot_restore",
-           "ddpb_measure_fp64_peak", "ddpb_set_subbatches"]
+           "ddpb_measure_fp64_peak", "ddpb_set_subbatches", "ddpb_model_create_from_urdf", "ddpb_model_dims", "ddpb_model_get",
+           "ddpb_model_frame_name"]
 
 
 class DdpbError(RuntimeError):
@@ -100,6 +101,30 @@ def model_desc_c(m, keep):
         md.n_frames = m.n_frames
         md.frame_parent = _i(arrs["frame_parent"]); md.frame_rot = _d(arrs["frame_rot"]); md.frame_trans = _d(arrs["frame_trans"])
     return md
+
+
+def model_from_urdf(text):
+    """URDF text -> models.ModelDesc through the library's own converter (ddpb_model_create_from_urdf: the replacement of
+    pinocchio::urdf::buildModel, pinocchio_model.ipp:98-113); the arrays come back from the C ABI, nothing is parsed here."""
+    from . import models
+    L = lib()
+    L.ddpb_model_frame_name.restype = C.c_char_p
+    data = text.encode() if isinstance(text, str) else bytes(text)
+    h = C.c_void_p()
+    _check(L.ddpb_model_create_from_urdf(data, C.c_ulonglong(len(data)), C.byref(h)))
+    try:
+        dims = (C.c_int * 2)()
+        _check(L.ddpb_model_dims(h, dims))
+        n, f = dims[0], dims[1]
+        R = np.zeros((n, 3, 3)); p = np.zeros((n, 3)); ax = np.zeros((n, 3)); m = np.zeros(n); c = np.zeros((n, 3)); I = np.zeros((n, 6))
+        fpar = np.zeros(f, dtype=np.int32); fp = np.zeros((f, 3))
+        _check(L.ddpb_model_get(h, _d(R), _d(p), _d(ax), _d(m), _d(c), _d(I), _i(fpar), _d(fp)))
+        names = [L.ddpb_model_frame_name(h, i).decode() for i in range(f)]
+    finally:
+        L.ddpb_model_destroy(h)
+    return models.ModelDesc(name="urdf", kind=models.KIND_REVOLUTE_CHAIN, n_joints=n, parent=np.arange(-1, n - 1, dtype=np.int32),
+                            placement_rot=R, placement_trans=p, axis=ax, mass=m, com=c, inertia=I, frame_parent=fpar,
+                            frame_rot=np.tile(np.eye(3), (f, 1, 1)), frame_trans=fp, frame_names=names)
 
 
 class BatchBase:

@@ -14,6 +14,7 @@
 #include "forward.cuh"
 #include "launch.cuh"
 #include "model_host.hpp"
+#include "urdf_host.hpp"
 
 using namespace ddpb;
 
@@ -117,6 +118,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct ddpb_model {
   ModelDev dev;
   int nq;
+  urdf::Model src;  // the description the model was built from (arrays as in ddpb_model_desc; names for URDF models)
 };
 
 struct PhaseEv { cudaEvent_t a, b; int phase; };
@@ -417,8 +419,50 @@ int ddpb_model_create(const ddpb_model_desc* d, ddpb_model** out) {
   const int rc = model_from_desc(d, m->dev, err);
   if (rc) { delete m; return fail(rc, err); }
   m->nq = m->dev.n;
+  if (d->kind == DDPB_MODEL_REVOLUTE_CHAIN) {
+    const int n = d->n_joints, f = d->n_frames;
+    urdf::Model& s = m->src;
+    s.parent.assign(d->parent, d->parent + n);
+    s.placement_rot.assign(d->placement_rot, d->placement_rot + 9 * n); s.placement_trans.assign(d->placement_trans, d->placement_trans + 3 * n);
+    s.axis.assign(d->axis, d->axis + 3 * n); s.mass.assign(d->mass, d->mass + n); s.com.assign(d->com, d->com + 3 * n);
+    s.inertia.assign(d->inertia, d->inertia + 6 * n);
+    if (f > 0) { s.frame_parent.assign(d->frame_parent, d->frame_parent + f); s.frame_trans.assign(d->frame_trans, d->frame_trans + 3 * f); }
+  }
   *out = m;
   return DDPB_OK;
+}
+int ddpb_model_create_from_urdf(const char* xml, unsigned long long length, ddpb_model** out) {
+  if (!xml || !out) return fail(DDPB_ERR_INVALID, "null argument");
+  urdf::Model src;
+  std::string err;
+  int rc = urdf::model_from_urdf(xml, (size_t)length, src, err);
+  if (rc) return fail(rc, "URDF: " + err);
+  const ddpb_model_desc d = src.desc();
+  ddpb_model* m = new ddpb_model();
+  rc = model_from_desc(&d, m->dev, err);
+  if (rc) { delete m; return fail(rc, "URDF: " + err); }
+  m->nq = m->dev.n;
+  m->src = std::move(src);
+  *out = m;
+  return DDPB_OK;
+}
+int ddpb_model_dims(const ddpb_model* m, int* dims2) {
+  if (!m || !dims2) return fail(DDPB_ERR_INVALID, "null argument");
+  dims2[0] = m->dev.n; dims2[1] = m->dev.nframes;
+  return DDPB_OK;
+}
+int ddpb_model_get(const ddpb_model* m, double* placement_rot, double* placement_trans, double* axis, double* mass, double* com,
+                   double* inertia, int* frame_parent, double* frame_trans) {
+  if (!m) return fail(DDPB_ERR_INVALID, "null model");
+  const urdf::Model& s = m->src;
+  auto put = [](auto* dst, const auto& v) { if (dst) std::copy(v.begin(), v.end(), dst); };
+  put(placement_rot, s.placement_rot); put(placement_trans, s.placement_trans); put(axis, s.axis); put(mass, s.mass); put(com, s.com);
+  put(inertia, s.inertia); put(frame_parent, s.frame_parent); put(frame_trans, s.frame_trans);
+  return DDPB_OK;
+}
+const char* ddpb_model_frame_name(const ddpb_model* m, int frame) {
+  if (!m || frame < 0 || frame >= (int)m->src.frame_names.size()) return "";
+  return m->src.frame_names[frame].c_str();
 }
 void ddpb_model_destroy(ddpb_model* m) { delete m; }
 

@@ -10,8 +10,11 @@
 // Error convention: the reference terminates on precondition violations (DDP_ASSERT -> std::terminate,
 // src/lib.cpp:107-110); here a failing C-ABI call throws ddpb::error carrying ddpb_last_error().
 #pragma once
+#include <fstream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
+#include <cstdlib>
 #include <utility>
 #include <vector>
 
@@ -50,6 +53,26 @@ struct model_t {
     nq = d.kind == DDPB_MODEL_PENDULUM ? 1 : d.n_joints;
     frames = d.n_frames;
   }
+  // model_t{urdf_path} (pinocchio_model.ipp:155: pinocchio::urdf::buildModel with a fixed base; a leading '~' is the home
+  // directory as in builder_from_urdf_t, :98-113).  Serial chains of revolute / continuous joints, fixed joints merged.
+  explicit model_t(const std::string& urdf_path) {
+    std::string path = urdf_path;
+    if (!path.empty() && path[0] == '~') { const char* home = std::getenv("HOME"); path = std::string(home ? home : "") + path.substr(1); }
+    std::ifstream in(path, std::ios::binary);
+    if (!in) throw error(DDPB_ERR_INVALID, ("cannot open " + path).c_str());
+    std::ostringstream ss;
+    ss << in.rdbuf();
+    *this = from_urdf_text(ss.str());
+  }
+  static model_t from_urdf_text(const std::string& xml) {
+    model_t m;
+    check(ddpb_model_create_from_urdf(xml.data(), xml.size(), &m.h));
+    int dims[2];
+    check(ddpb_model_dims(m.h, dims));
+    m.nq = dims[0]; m.frames = dims[1];
+    return m;
+  }
+  const char* frame_name(index_t i) const { return ddpb_model_frame_name(h, (int)i); }  // pinocchio_model.hpp frame_name(i)
   // pendulum_model_t{mass, length} (pendulum_model.hpp:29)
   static model_t pendulum(double mass, double length) {
     ddpb_model_desc d{};
@@ -57,8 +80,17 @@ struct model_t {
     return model_t(d);
   }
   model_t(model_t&& o) noexcept : h(o.h), nq(o.nq), frames(o.frames) { o.h = nullptr; }
+  model_t& operator=(model_t&& o) noexcept {
+    if (this != &o) { ddpb_model_destroy(h); h = o.h; nq = o.nq; frames = o.frames; o.h = nullptr; }
+    return *this;
+  }
   model_t(const model_t&) = delete;
   model_t& operator=(const model_t&) = delete;
+
+ private:
+  model_t() = default;
+
+ public:
   ~model_t() { ddpb_model_destroy(h); }
   index_t configuration_dim() const { return nq; }
   index_t tangent_dim() const { return nq; }

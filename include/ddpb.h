@@ -107,6 +107,16 @@ enum ddpb_scalar_field {
 
 /* ---- lifetime -------------------------------------------------------------------------- */
 int ddpb_model_create(const ddpb_model_desc* desc, ddpb_model** out);
+/* model_t{urdf_path} -> pinocchio::urdf::buildModel(path, model) with a fixed base (pinocchio_model.ipp:98-113, :155): the same
+ * from URDF TEXT (the caller reads the file).  Revolute / continuous joints in a serial chain; fixed joints are merged into
+ * the body of their supporting joint and their child links become operational frames (every link is a BODY frame, in
+ * traversal order); anything else returns DDPB_ERR_UNSUPPORTED, malformed text DDPB_ERR_INVALID. */
+int ddpb_model_create_from_urdf(const char* urdf_xml, unsigned long long length, ddpb_model** out);
+/* what a model holds (adapters, tests): dims2 = {joints, frames}; any output array may be NULL.  Layouts as in ddpb_model_desc. */
+int ddpb_model_dims(const ddpb_model* m, int* dims2);
+int ddpb_model_get(const ddpb_model* m, double* placement_rot, double* placement_trans, double* axis, double* mass, double* com,
+                   double* inertia, int* frame_parent, double* frame_trans);
+const char* ddpb_model_frame_name(const ddpb_model* m, int frame); /* "" when the model was built from arrays */
 void ddpb_model_destroy(ddpb_model* m);
 /* ne_per_knot[t] (t in [0,T)) = equality rows at knot t, i.e. rows of the doubly advanced
  * constraint that acts on x_{t+2} (indexing::shift_time_idx_t, indexer.hpp:291-318); the same for

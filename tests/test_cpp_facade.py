@@ -31,3 +31,20 @@ def test_reference_style_pendulum_main(tmp_path, pkg):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "problem 0: q_T = 3.1" in r.stdout
+
+
+def test_model_from_urdf_path(tmp_path, pkg):
+    """model_t{urdf_path} (pinocchio_model.ipp:155) through the facade: host code only, runs without a GPU."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_urdf import UR5
+    exe = str(tmp_path / "urdf_model")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-I", os.path.join(PKG, "include"), os.path.join(ROOT, "tests", "cpp", "urdf_model.cpp"),
+                           "-L", PKG, "-lddpb", f"-Wl,-rpath,{PKG}", "-o", exe])
+    path = tmp_path / "ur5_like.urdf"
+    path.write_text(UR5)
+    r = subprocess.run([exe, str(path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "nq 6 nv 6 frames 8" in r.stdout and "frame 7 tool0" in r.stdout and "moved nq 6" in r.stdout
+    r = subprocess.run([exe, str(tmp_path / "missing.urdf")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stdout
