@@ -114,10 +114,10 @@ template <int NJ> __global__ void cost_kernel(const __grid_constant__ ModelDev m
   bd.scal[(size_t)S_COST * bd.B + b] = plain;
 }
 // outer-loop sweeps (outer_warp.cuh): per-(knot, problem) kernels and one-warp-per-problem adjoint recursion
-template <int NJ> __global__ void origin_update_kernel(const __grid_constant__ BatchDev bd) {
+template <int NJ> __global__ void origin_update_kernel(const __grid_constant__ BatchDev bd, int fb_all) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)bd.nb * bd.T) return;
-  origin_update_knot<NJ>(bd, bd.b0 + (int)(i % bd.nb), (int)(i / bd.nb));
+  origin_update_knot<NJ>(bd, bd.b0 + (int)(i % bd.nb), (int)(i / bd.nb), fb_all != 0);
 }
 template <int NJ> __global__ void mult_update_kernel(const __grid_constant__ BatchDev bd) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,7 +254,7 @@ template <> void Launch<KNJ>::cost(const ModelDev& m, const BatchDev& bd, double
 template <> void Launch<KNJ>::al_update(const BatchDev& bd, double thr, cudaStream_t s) {
   const size_t nkb = (size_t)bd.nb * bd.T;
   const unsigned wblocks = (unsigned)(((size_t)bd.nb * AdjGeom<KNJ>::G + 127) / 128);
-  origin_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
+  origin_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd, thr > 0.0 ? 1 : 0);
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 0);
   mult_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 1);

@@ -14,11 +14,21 @@
 
 namespace ddpb {
 
-template <int NJ> __device__ __forceinline__ void origin_update_knot(const BatchDev& bd, int b, int t) {
+// fb_all = false: the feedback sequence is re-centred only at knots with equality rows.  Its re-centred k is read once,
+// by the multiplier update at such knots (ddp.hpp:686-687); at every other knot k, K and the origin are overwritten by
+// the backward pass of the same iteration before anything reads them, so the reference's update there (8 n^2 + 6 n doubles
+// of traffic per knot) is dead -- unless a problem can stop on the optimality threshold in this iteration and hand its
+// feedback back as the result of solve (ddp.hpp:744-748), which needs threshold > 0: the host passes fb_all = true then.
+template <int NJ> __device__ __forceinline__ void origin_update_knot(const BatchDev& bd, int b, int t, bool fb_all) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n, nd = 2 * n;
   const int B = bd.B;
   if (bd.scal[(size_t)S_STATUS * B + b] != 0.0) return;
   const int ne = bd.ne[t];
+  if (ne == 0 && !fb_all) {
+#pragma unroll
+    for (int k = 0; k < nd; ++k) bd.m_origin[((size_t)t * nx + k) * B + b] = bd.xs[((size_t)t * nx + k) * B + b];
+    return;
+  }
   const size_t eo = bd.eq_off[t];
   double dxm[nd], dxf[nd];
 #pragma unroll
