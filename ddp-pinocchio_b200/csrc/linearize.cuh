@@ -540,7 +540,8 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const double* vals = which == 0 ? SM(kk, pl.o_fval) + k : SM(kk, pl.o_eqv) + k;
         const int vs = which == 0 ? nx : ne_sm;
         const double f0 = vals[0], ca = jc[ga * dgs], da = dg[ga * dgs];
-        for (int bl = 0; bl < LB; ++bl) {
+#pragma unroll 4
+        for (int bl = 0; bl < LB; ++bl) {  // independent entries: unrolled so that their loads and stores overlap
           const int gb = b0_ + bl;
           double v;
           if (gb == ga) {
