@@ -366,6 +366,11 @@ def main():
                                  "entries (csrc/batch.cuh), so traffic (ncu dram bytes per knot, profiles/r02_kernel_counts.json, x knots "
                                  "per launch) is BELOW the algorithmic bytes and achieved_stored_records is the rate on the bytes "
                                  "actually stored"},
+            "roofline_fp64": ({"kernel": "linearize", "bound": "fp64", "achieved": kout["linearize"]["fp64_tflops"], "peak": fp64_peak, "unit": "TFLOP/s",
+                               "frac": kout["linearize"]["fp64_frac_of_measured_peak"],
+                               "note": "executed FP64 flops per knot (ncu, profiles/r02_kernel_counts.json: 2*dfma + dadd + dmul) x knots per "
+                                       "pass / mean duration of a linearization pass; peak = ddpb_measure_fp64_peak on this GPU"}
+                              if "fp64_tflops" in kout["linearize"] else None),
             "kernels": kout,
             "kernel_timing": {"steps": ksteps, "ms_per_step_one_stream": ms_one_stream,
                               "note": "launch durations measured with the solver on one stream (no overlap between sub-batches)"},

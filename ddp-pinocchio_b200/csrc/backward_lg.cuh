@@ -34,7 +34,7 @@ template <int NJ, bool DENSE> struct LgRec {
   static constexpr int o_f = 0, o_fx = nx, o_fu = o_fx + n * nd, o_lu = o_fu + n * nu, o_fxx = o_lu + nu, o_fux = o_fxx + RT * nd * nd,
                        o_fuu = o_fux + RT * nu * RI, o_end = o_fuu + (DENSE ? nd * nu * nu : 0);
   static constexpr int NCH = (o_end - o_fx + 1) / 2;  // 16-byte chunks staged per knot (f is not used by the backward pass)
-  static constexpr int NS = 4;                        // ring depth
+  static constexpr int NS = 8;                        // ring depth (knots in flight: HBM latency / time of one knot)
   static constexpr int GPW = 32 / LG;                 // groups (problems) per warp
   static constexpr int STAGE = 2 * NCH;               // doubles per ring slot
   static constexpr int smem_per_warp = GPW * NS * STAGE;
