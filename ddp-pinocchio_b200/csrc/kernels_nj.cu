@@ -51,7 +51,10 @@ template <int NJ> __global__ void fb_origin_kernel(const __grid_constant__ Batch
 #if DDPB_NJ <= 2
 // one thread per evaluation point (linearize_pt.cuh): 4 independent warps per CTA, 255 registers per thread
 constexpr int PT_WARPS = 4;
-template <int NJ> __global__ void __launch_bounds__(32 * PT_WARPS, 2) linearize_pt_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, int t0, int nt) {
+#ifndef DDPB_PT_BLOCKS
+#define DDPB_PT_BLOCKS 2   // CTAs per SM the register allocation aims at (2: 255 registers, no spill)
+#endif
+template <int NJ> __global__ void __launch_bounds__(32 * PT_WARPS, DDPB_PT_BLOCKS) linearize_pt_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd, int t0, int nt) {
   __shared__ __align__(16) double stage[PT_WARPS][PtGeom<NJ>::KPW * PtGeom<NJ>::SIZE];
   linearize_pt_warp<NJ>(m, bd, t0, nt, stage[threadIdx.x >> 5]);
 }
@@ -173,6 +176,12 @@ template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
 #if DDPB_NJ > 0
   cudaError_t e = cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_JACOBIANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
   if (e != cudaSuccess) return e;
+#if DDPB_NJ <= 2
+  // the record rings of the lane-group backward pass (8 knots per problem) exceed the default 48 KB in value-based mode
+  e = cudaFuncSetAttribute(backward_lg_kernel<KNJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(HESS_FD_VALUES));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(backward_lg_kernel<KNJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(HESS_FD_JACOBIANS));
+  if (e != cudaSuccess) return e;
+#endif
 #if DDPB_NJ <= 2
 #endif
   return cudaFuncSetAttribute(linearize_kernel<KNJ, HESS_FD_VALUES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_smem);
