@@ -151,7 +151,7 @@ struct ddpb_batch {
   std::vector<PhaseEv> events;
   float phase_ms[4] = {0, 0, 0, 0};
   size_t lin_smem = 0;
-  int lin_threads = 128, bwd_threads = 128, lin_kpb = 1;
+  int lin_threads = 128, bwd_threads = 128, lin_kpb = 1, lin_kpb_pref = 1;  // knots per CTA: for the most constrained knot / preferred
   bool lin_pt = true;  // use the thread-per-point linearization where it exists (DDPB_LIN_PT=0: development switch)
   // ddpb_solve runs the batch as `nsub` sub-batches, each on its own stream: the latency-bound sweeps (backward pass,
   // rollouts) of one sub-batch overlap the throughput-bound linearization of another, and a problem that needs
@@ -235,7 +235,15 @@ static int launch_linearize(const LaunchCtx& c) {
     // knots without equality rows of a short chain go to the thread-per-point kernel where one exists
     bool done = false;
     if (h->ne[t0] == 0 && h->lin_pt) DISPATCH(h->mt, done = L::linearize_pt(h->model, c.bd, t0, t1, c.s));
-    if (!done) DISPATCH(h->mt, L::linearize(h->model, c.bd, h->lin_threads, h->lin_kpb, t0, t1, h->ne[t0], c.s));
+    if (!done) {
+      // knots per CTA for THIS run of knots: its workspace depends on its row count (a constrained knot of the horizon must
+      // not shrink the groups of all the others)
+      size_t knot_smem = 0;
+      DISPATCH(h->mt, knot_smem = L::lin_smem_bytes(c.bd.hess_mode, h->ne[t0], c.bd.eq_kind));
+      int kpb = h->lin_kpb_pref;
+      while (kpb > 1 && knot_smem * kpb > h->lin_smem) --kpb;
+      DISPATCH(h->mt, L::linearize(h->model, c.bd, h->lin_threads, kpb, t0, t1, h->ne[t0], c.s));
+    }
     int rc = check_launch(h, "linearize");
     if (rc) return rc;
     t0 = t1;
@@ -392,8 +400,11 @@ static int batch_init(ddpb_batch* h, const ddpb_model* m, int B, int T, const in
   h->lin_kpb = fdv ? 1 : (n <= 1 ? 16 : (n == 2 ? 16 : 2));
   if (!fdv && n >= 5 && knot_smem > 0) h->lin_kpb = (int)std::min<size_t>(3, std::max<size_t>(1, ((size_t)113 << 10) / knot_smem));
   if (const char* e = getenv("DDPB_LIN_KPB")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->lin_kpb = v; }
+  h->lin_kpb_pref = h->lin_kpb;
   while (h->lin_kpb > 1 && knot_smem_max * h->lin_kpb > (size_t)prop.sharedMemPerBlockOptin) --h->lin_kpb;
-  h->lin_smem = knot_smem_max * h->lin_kpb;
+  // dynamic shared memory the kernels may ask for: the larger of (most constrained knot x its group size) and
+  // (unconstrained knot x preferred group size); every launch sizes its own request (launch_linearize)
+  h->lin_smem = std::max(knot_smem_max * h->lin_kpb, std::min<size_t>(knot_smem * h->lin_kpb_pref, (size_t)prop.sharedMemPerBlockOptin));
   if (h->lin_smem > (size_t)prop.sharedMemPerBlockOptin) return fail(DDPB_ERR_UNSUPPORTED, "linearization workspace exceeds shared memory");
   DISPATCH(h->mt, { CU(L::prepare(h->lin_smem)); });
   DISPATCH(h->nj, { h->bwd_smem = L::bwd_smem_bytes(p->hess_mode); });

@@ -57,7 +57,7 @@ template <int NJ> struct LinPlan {
     v_sz = NT * VRec<NJ>::SIZE;
     o_fval = o; o += P * 2 * NJ;
     o_eqv = o; o += P * ne_max;
-    o_J = o; o += eq_kind == EQ_SPATIAL ? NT * 3 * NJ : 0;  // frame Jacobians of a spatial constraint
+    o_J = o; o += (eq_kind == EQ_SPATIAL && ne_max > 0) ? NT * 3 * NJ : 0;  // frame Jacobians of a spatial constraint (knots with rows only)
     o_eqxu = o; o += NT * ne_max * N;
     // value-based mode only: per-body column terms of the base point, diagonal second differences of f and eq
     o_cterm = o; o += mode == HESS_FD_VALUES ? 2 * NJ * NJ * 6 : 0;
