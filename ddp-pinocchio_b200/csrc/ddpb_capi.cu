@@ -142,6 +142,8 @@ struct ddpb_batch {
   double *ls_xs = nullptr, *ls_us = nullptr;  // scratch trajectories of the concurrent line-search trials
   double* ls_res = nullptr;                   // [34][3][B] (sum, merit, plain) of every trial
   int* ls_win = nullptr;                      // [B] line-search state per problem
+  int* ls_wide[2] = {nullptr, nullptr};       // [B/32] per block of 32 problems: run all trials in the first wave (ping-pong between passes)
+  int ls_pass = 0;                            // parity of the line-search pass being enqueued
   double* stage = nullptr;
   size_t stage_bytes = 0;
   double* h_stage = nullptr;  // pinned bounce buffer for small scalar traffic
@@ -267,7 +269,8 @@ static int launch_forward(const LaunchCtx& c, bool with_cost_old = true) {
   ddpb_batch* h = c.h;
   if (with_cost_old) { int rc = launch_cost_old(c); if (rc) return rc; }
   PhaseScope ps(h, 2, c.s);
-  DISPATCH(h->mt, L::forward(h->model, c.bd, h->costs_old, h->ls_xs, h->ls_us, h->ls_res, h->ls_win, c.s));
+  DISPATCH(h->mt, L::forward(h->model, c.bd, h->costs_old, h->ls_xs, h->ls_us, h->ls_res, h->ls_win, h->ls_wide[h->ls_pass & 1],
+                             h->ls_wide[(h->ls_pass + 1) & 1], c.s));
   h->launches += 3;  // two waves of trials, each with its selection kernel
   return check_launch(h, "forward");
 }
@@ -367,6 +370,7 @@ static int batch_init(ddpb_batch* h, const ddpb_model* m, int B, int T, const in
     DISPATCH(h->mt, { slots = L::linesearch_slots(); });
     A(h->ls_xs, (size_t)slots * (T + 1) * nx * B); A(h->ls_us, (size_t)slots * T * nu * B);
     A(h->ls_res, (size_t)34 * 3 * B); A(h->ls_win, (size_t)B);
+    A(h->ls_wide[0], (size_t)(B + 31) / 32 + 1); A(h->ls_wide[1], (size_t)(B + 31) / 32 + 1);
   }
 #undef A
   if (rc) return rc;
@@ -380,6 +384,8 @@ static int batch_init(ddpb_batch* h, const ddpb_model* m, int B, int T, const in
   CU(cudaMemsetAsync(bd.m_jac, 0, std::max<size_t>(net * nd * B, 1) * sizeof(double), h->stream));
   CU(cudaMemsetAsync(bd.targets, 0, std::max<size_t>(net * B, 1) * sizeof(double), h->stream));
   CU(cudaMemsetAsync(bd.fb_k, 0, T * nu * B * sizeof(double), h->stream));
+  CU(cudaMemsetAsync(h->ls_wide[0], 0, ((size_t)(B + 31) / 32 + 1) * sizeof(int), h->stream));
+  CU(cudaMemsetAsync(h->ls_wide[1], 0, ((size_t)(B + 31) / 32 + 1) * sizeof(int), h->stream));
   CU(cudaMemsetAsync(bd.fb_K, 0, T * nu * nd * B * sizeof(double), h->stream));
   CU(cudaHostAlloc((void**)&h->h_stage, (size_t)NSCALARS * B * sizeof(double), cudaHostAllocDefault));
   // launch geometry
@@ -934,6 +940,7 @@ static int enqueue_solve(ddpb_batch* h, const ddpb_solver_params* p) {
     if (cudaEventRecord(h->sub_lin[i], lo.s) != cudaSuccess || cudaStreamWaitEvent(c.s, h->sub_lin[i], 0) != cudaSuccess) return fail(DDPB_ERR_CUDA, "stream join");
     return DDPB_OK;
   };
+  h->ls_pass = 0;  // the line-search passes of a solve alternate the two flag buffers from a fixed start (graph replay)
   for (size_t i = 0; i < sub.size(); ++i) {
     LaunchCtx& c = sub[i];
     R(scalar_copy(c, S_SPARE, S_REG));
@@ -945,6 +952,7 @@ static int enqueue_solve(ddpb_batch* h, const ddpb_solver_params* p) {
     CU(cudaMemsetAsync(bd.scal + S_RESTARTS * B + c.bd.b0, 0, c.bd.nb * sizeof(double), c.s));
   }
   for (int iter = 0; iter < p->max_iterations; ++iter) {
+    ++h->ls_pass;
     for (size_t i = 0; i < sub.size(); ++i) {
       LaunchCtx& c = sub[i];
       c.bd.xs = bd.xs; c.bd.us = bd.us; c.bd.xs_new = bd.xs_new; c.bd.us_new = bd.us_new;

@@ -98,12 +98,12 @@ template <int NJ> __global__ void cost_old_kernel(const __grid_constant__ ModelD
 }
 template <int NJ> __global__ void __launch_bounds__(32 * LsGeom<NJ>::WPB) ls_trials_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd,
                                                                                          const double* costs_old, double* xs_c, double* us_c, double* res,
-                                                                                         const int* win, int c0, int c1) {
-  ls_trials_block<NJ>(m, bd, costs_old, xs_c, us_c, res, win, c0, c1, thread_scratch());
+                                                                                         const int* win, const int* wide, int c0, int c1) {
+  ls_trials_block<NJ>(m, bd, costs_old, xs_c, us_c, res, win, wide, c0, c1, thread_scratch());
 }
 template <int NJ> __global__ void ls_select_kernel(const __grid_constant__ BatchDev bd, const double* xs_c, const double* us_c, const double* res, int* win,
-                                                   int c0, int c1, int last) {
-  ls_select_warp<NJ>(bd, xs_c, us_c, res, win, c0, c1, last != 0);
+                                                   const int* wide, int* wide_next, int c0, int c1, int last) {
+  ls_select_warp<NJ>(bd, xs_c, us_c, res, win, wide, wide_next, c0, c1, last != 0);
 }
 template <int NJ> __global__ void rollout_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ BatchDev bd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,15 +243,20 @@ template <> void Launch<KNJ>::cost_old(const ModelDev& m, const BatchDev& bd, do
   const size_t nkb = (size_t)bd.nb * (bd.T + 1);
   cost_old_kernel<KNJ><<<(unsigned)((nkb + TPP - 1) / TPP), TPP, scr_bytes(TPP), s>>>(m, bd, costs_old);
 }
-template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, double* ls_res, int* ls_win, cudaStream_t s) {
+template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, double* ls_res, int* ls_win,
+                                      const int* wide, int* wide_next, cudaStream_t s) {
   using G = LsGeom<KNJ>;
   const unsigned pb = (unsigned)((bd.nb + 31) / 32), sb = (unsigned)(((size_t)bd.nb * 32 + 127) / 128);
-  const int waves[3] = {0, G::NC1, LS_MAX_TRIALS};
-  for (int wv = 0; wv < 2; ++wv) {
-    const int c0 = waves[wv], c1 = waves[wv + 1];
-    ls_trials_kernel<KNJ><<<dim3(pb, (unsigned)((c1 - c0 + G::WPB - 1) / G::WPB)), 32 * G::WPB, scr_bytes(32 * G::WPB), s>>>(m, bd, costs_old, xs_c, us_c, ls_res, ls_win, c0, c1);
-    ls_select_kernel<KNJ><<<sb, 128, 0, s>>>(bd, xs_c, us_c, ls_res, ls_win, c0, c1, wv == 1);
-  }
+  // this pass's verdicts start from "narrow" (sub-batches start on multiples of 32 problems)
+  cudaMemsetAsync(wide_next + (bd.b0 >> 5), 0, pb * sizeof(int), s);
+  // first wave: the grid covers all 34 trials, the blocks of the trials past NC1 leave at once unless their problems are flagged
+  ls_trials_kernel<KNJ><<<dim3(pb, (unsigned)((LS_MAX_TRIALS + G::WPB - 1) / G::WPB)), 32 * G::WPB, scr_bytes(32 * G::WPB), s>>>(
+      m, bd, costs_old, xs_c, us_c, ls_res, ls_win, wide, 0, LS_MAX_TRIALS);
+  ls_select_kernel<KNJ><<<sb, 128, 0, s>>>(bd, xs_c, us_c, ls_res, ls_win, wide, wide_next, 0, G::NC1, 0);
+  // second wave: the remaining trials of the problems still unresolved
+  ls_trials_kernel<KNJ><<<dim3(pb, (unsigned)((LS_MAX_TRIALS - G::NC1 + G::WPB - 1) / G::WPB)), 32 * G::WPB, scr_bytes(32 * G::WPB), s>>>(
+      m, bd, costs_old, xs_c, us_c, ls_res, ls_win, wide, G::NC1, LS_MAX_TRIALS);
+  ls_select_kernel<KNJ><<<sb, 128, 0, s>>>(bd, xs_c, us_c, ls_res, ls_win, wide, wide_next, G::NC1, LS_MAX_TRIALS, 1);
 }
 template <> int Launch<KNJ>::linesearch_slots() { return ls_slots<KNJ>(); }
 template <> void Launch<KNJ>::rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s) {

@@ -21,7 +21,8 @@ template <int NJ> struct Launch {
   // xs_c / us_c: scratch trajectories of the concurrent line-search trials, linesearch_slots() x the trajectory size
   // cost_seq_aug of the current trajectory (independent of the backward pass), then the concurrent line-search trials
   static void cost_old(const ModelDev& m, const BatchDev& bd, double* costs_old, cudaStream_t s);
-  static void forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, double* ls_res, int* ls_win, cudaStream_t s);
+  static void forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, double* ls_res, int* ls_win,
+                      const int* wide, int* wide_next, cudaStream_t s);
   static int linesearch_slots();
   static void rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s);
   static void cost(const ModelDev& m, const BatchDev& bd, double* costs, cudaStream_t s);

@@ -230,8 +230,10 @@ template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev&
 // into the new-trajectory storage: the usual case, the full step, copies nothing), and a selection kernel then takes the
 // smallest accepted trial index exactly as the sequential scan would (34 trials at most, the last one kept on give-up,
 // ddp_fwd.ipp:35-37) and copies the winner.  Two waves: trials [0, NC1) for everybody, trials [NC1, 34) for the problems
-// still unresolved (almost always none: those threads exit at once).  The `rollouts` scalar keeps counting what the
-// sequential algorithm would have run.
+// still unresolved (almost always none: those threads exit at once).  A block of 32 problems that needed the second wave in
+// the previous pass runs ALL 34 trials in its first wave of this pass (`wide` flags, ping-pong between passes): workloads
+// whose line searches regularly go deep (C4) then pay one rollout latency per pass instead of two; which wave computes a
+// trial does not change its result.  The `rollouts` scalar keeps counting what the sequential algorithm would have run.
 //   NC1: 8 for models of <= 2 joints (a 4096-problem batch is then ~2 warps per SM sub-partition: the FP64 pipe is the
 //   limit, more speculative trials would cost time), 16 for the arms (their batches leave most of the machine idle).
 template <int NJ> struct LsGeom {
@@ -239,22 +241,24 @@ template <int NJ> struct LsGeom {
   static constexpr int WPB = 4;  // trial warps per block
 };
 constexpr int LS_MAX_TRIALS = 34;  // 2^-33 >= 1e-10 > 2^-34
-// scratch slots: trial c of wave 0 uses slot c (slot 0 is the new-trajectory storage itself), trial c of wave 1 slot c - NC1
-template <int NJ> constexpr int ls_slots() { return LsGeom<NJ>::NC1 > LS_MAX_TRIALS - LsGeom<NJ>::NC1 ? LsGeom<NJ>::NC1 : LS_MAX_TRIALS - LsGeom<NJ>::NC1; }
+// scratch slots: trial c uses slot c (slot 0 is the new-trajectory storage itself)
+template <int NJ> constexpr int ls_slots() { return LS_MAX_TRIALS; }
 
 // per-problem line-search state in `win` [B] ints: -1 unresolved, >= 0 resolved.  res: [LS_MAX_TRIALS][3][B] (sum, merit, plain)
 template <int NJ>
 __device__ __forceinline__ void ls_trials_block(const ModelDev& m, const BatchDev& bd, const double* costs_old, double* xs_c, double* us_c, double* res,
-                                                const int* win, int c0, int c1, const Scratch& sc) {
+                                                const int* win, const int* wide, int c0, int c1, const Scratch& sc) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
   const int B = bd.B, T = bd.T;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = bd.b0 + blockIdx.x * 32 + lane;
   const int c = c0 + blockIdx.y * LsGeom<NJ>::WPB + w;
   if (b >= bd.b0 + bd.nb || c >= c1) return;
+  // first wave: the trials past NC1 only run for blocks of problems that needed them in the previous pass
+  if (c0 == 0 && c >= LsGeom<NJ>::NC1 && !wide[(bd.b0 >> 5) + blockIdx.x]) return;
   if (bd.scal[(size_t)S_STATUS * B + b] != 0.0 || (c0 > 0 && win[b] != -1)) return;  // frozen, or resolved by the first wave
   const size_t xs_slot = (size_t)(T + 1) * nx * B, us_slot = (size_t)T * nu * B;
-  const int slot = c - c0;
+  const int slot = c;
   double* xo = c == 0 ? bd.xs_new : xs_c + slot * xs_slot;
   double* uo = c == 0 ? bd.us_new : us_c + slot * us_slot;
   double sum, merit, plain;
@@ -267,7 +271,8 @@ __device__ __forceinline__ void ls_trials_block(const ModelDev& m, const BatchDe
 // one warp per problem: the smallest accepted trial of [c0, c1) wins; last wave: give up on the last trial.  The winner's
 // scratch trajectory is copied into the new-trajectory storage by the warp (element index strided by the batch size).
 template <int NJ>
-__device__ __forceinline__ void ls_select_warp(const BatchDev& bd, const double* xs_c, const double* us_c, const double* res, int* win, int c0, int c1, bool last) {
+__device__ __forceinline__ void ls_select_warp(const BatchDev& bd, const double* xs_c, const double* us_c, const double* res, int* win, const int* wide,
+                                               int* wide_next, int c0, int c1, bool last) {
   constexpr int n = Dim<NJ>::n, nx = 2 * n, nu = n;
   const int B = bd.B, T = bd.T;
   const int lane = threadIdx.x & 31;
@@ -283,18 +288,23 @@ __device__ __forceinline__ void ls_select_warp(const BatchDev& bd, const double*
     return;
   }
   if (c0 > 0 && win[b] != -1) return;
+  const int blk = b >> 5;
+  // first wave: trials [0, NC1), or all of them where the block ran wide
+  const int c_hi = (c0 == 0 && wide[blk]) ? LS_MAX_TRIALS : c1;
   int found = -1;
-  for (int c = c0; c < c1; ++c)
+  for (int c = c0; c < c_hi; ++c)
     if (found < 0 && res[((size_t)c * 3 + 0) * B + b] <= 0.0) found = c;
+  if (c0 == 0 && c_hi == LS_MAX_TRIALS) last = true;
   const bool accepted = found >= 0;
   if (!accepted && last) found = LS_MAX_TRIALS - 1;  // give up: keep the last trial
   if (found < 0) {
     if (lane == 0) win[b] = -1;
     return;
   }
+  if (lane == 0 && found >= LsGeom<NJ>::NC1) wide_next[blk] = 1;  // this block goes deep: all trials at once next time
   if (found != 0) {
-    const double* xw = xs_c + (size_t)(found - c0) * xs_slot;
-    const double* uw = us_c + (size_t)(found - c0) * us_slot;
+    const double* xw = xs_c + (size_t)found * xs_slot;
+    const double* uw = us_c + (size_t)found * us_slot;
     for (int e = nx + lane; e < (T + 1) * nx; e += 32) bd.xs_new[(size_t)e * B + b] = xw[(size_t)e * B + b];
     for (int e = lane; e < T * nu; e += 32) bd.us_new[(size_t)e * B + b] = uw[(size_t)e * B + b];
   }
