@@ -215,12 +215,15 @@ def main():
     h2d = h_x0.nbytes + h_us.nbytes + h_tg.nbytes + h_mj.nbytes
     d2h = (capi.NSCALARS * B + B * (T + 1) * w.nx + B * T * w.nu) * 8
 
+    # results land in pinned host buffers too (a D2H copy into pageable memory is staged by the driver at a fraction of the link rate)
+    h_xs = pin(np.zeros((B, T + 1, w.nx))); h_uso = pin(np.zeros((B, T, w.nu))); h_sc = pin(np.zeros((capi.NSCALARS, B)))
+
     def e2e_step():
         bt.set_targets(h_tg)
         bt.make_trajectory(h_x0, h_us)
         bt.set_multipliers(None, h_mj)
-        sc = bt.solve(its, w.mu)
-        xs, us = bt.get_trajectory()
+        sc = bt.solve(its, w.mu, out=h_sc)
+        xs, us = bt.get_trajectory(out=(h_xs, h_uso))
         return sc, xs
 
     # resident leg: snapshot once, restore per step

@@ -194,8 +194,13 @@ class Batch(BatchBase):
         assert xs.size == self.B * (self.T + 1) * self.nx and us.size == self.B * self.T * self.nu
         _check(lib().ddpb_set_trajectory(self._h, _d(xs), _d(us)))
 
-    def get_trajectory(self):
-        xs = np.empty((self.B, self.T + 1, self.nx)); us = np.empty((self.B, self.T, self.nu))
+    def get_trajectory(self, out=None):
+        """out = (xs, us): caller-owned destination arrays (e.g. pinned, capi.host_alloc) instead of fresh pageable ones."""
+        if out is None:
+            xs = np.empty((self.B, self.T + 1, self.nx)); us = np.empty((self.B, self.T, self.nu))
+        else:
+            xs, us = out
+            assert xs.size == self.B * (self.T + 1) * self.nx and us.size == self.B * self.T * self.nu and xs.flags.c_contiguous and us.flags.c_contiguous
         _check(lib().ddpb_get_trajectory(self._h, _d(xs), _d(us)))
         return xs, us
 
@@ -296,14 +301,15 @@ class Batch(BatchBase):
         _check(lib().ddpb_optimality(self._h, _d(a), _d(b)))
         return a, b
 
-    def solve(self, max_iterations, mu, reg=0.0, w=None, n=None, thr=0.0, read_back=True):
+    def solve(self, max_iterations, mu, reg=0.0, w=None, n=None, thr=0.0, read_back=True, out=None):
         w = 1.0 / mu if w is None else w
         n = 1.0 / mu ** 0.1 if n is None else n
         sp = SolverParamsC(max_iterations, thr, mu, reg, w, n)
         if not read_back:
             _check(lib().ddpb_solve_async(self._h, C.byref(sp)))
             return None
-        out = np.empty((NSCALARS, self.B))
+        if out is None:
+            out = np.empty((NSCALARS, self.B))
         _check(lib().ddpb_solve(self._h, C.byref(sp), _d(out)))
         return {nm: out[i].copy() for i, nm in enumerate(SCALAR_FIELDS)}
 
