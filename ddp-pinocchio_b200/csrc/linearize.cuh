@@ -309,6 +309,10 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     // once: 2R chain 1.62 -> 1.56 ms).  From 4 joints on the two kinds stay separate tasks: together they spill at 128
     // registers (6R: 656 B of spill stores per thread) and measured slower (3.04 -> 3.30 ms).
     constexpr bool MERGED = DDPB_COL_MERGED < 0 ? NJ <= 3 : DDPB_COL_MERGED != 0;
+#ifndef DDPB_FUSE_PROD
+#define DDPB_FUSE_PROD 1
+#endif
+    constexpr bool FUSE_PROD = DDPB_FUSE_PROD && MINV_EARLY && !MERGED;
     constexpr int KINDS = MERGED ? 1 : 2;
     const int n_tan = pl.NT * KINDS * NJ;
     const int n_minv = MINV_EARLY ? 0 : pl.NQ * NJ;
@@ -332,10 +336,26 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
           for (int k = 0; k < NJ; ++k) { vr[V::DQ + j * NJ + k] = cq[k]; vr[V::DV + j * NJ + k] = cv[k]; }
         } else {
           double col[NJ];
-          col_task<NJ>(QR(kk, pl.point_qset(p)), vr, j, wrt, col);
+          const double* qr = QR(kk, pl.point_qset(p));
+          col_task<NJ>(qr, vr, j, wrt, col);
           double* dst = vr + (wrt ? V::DV : V::DQ) + j * NJ;
+          if (FUSE_PROD) {
+            // phase 4 fused: M^-1 of the configuration is ready (MINV_EARLY), so the column goes straight to
+            // dt * da/dq resp. dt * da/dv + I (problem.hpp:495-502) without a round trip through shared memory and a barrier
+            const double* Mi = qr + Q::MINV;
 #pragma unroll
-          for (int k = 0; k < NJ; ++k) dst[k] = col[k];
+            for (int r = 0; r < NJ; ++r) {
+              double acc = 0.0;
+#pragma unroll
+              for (int k = 0; k < NJ; ++k) acc += Mi[k * NJ + r] * col[k];
+              double d = (-acc) * dt;
+              if (wrt && r == j) d += 1.0;
+              dst[r] = d;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) dst[k] = col[k];
+          }
         }
       } else {
         minv_task(idx - nk * n_tan);
@@ -346,8 +366,9 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   DDPB_PHASE_MARK(bd, 3, pc_);
 
   // phase 4: da/dq = -M^-1 dtau/dq, da/dv = -M^-1 dtau/dv, already scaled into the bottom blocks of
-  // fx (problem.hpp:495-502): DQ <- dt * da/dq ; DV <- dt * da/dv + I
-  for (int idx = tid; idx < nk * pl.NT * 2 * NJ; idx += nthr) {
+  // fx (problem.hpp:495-502): DQ <- dt * da/dq ; DV <- dt * da/dv + I   (done inside phase 3 where M^-1 is ready by then)
+  constexpr bool PROD_DONE = MODE == HESS_FD_JACOBIANS && MINV_EARLY && DDPB_FUSE_PROD && !(DDPB_COL_MERGED < 0 ? NJ <= 3 : DDPB_COL_MERGED != 0);
+  for (int idx = tid; idx < (PROD_DONE ? 0 : nk * pl.NT * 2 * NJ); idx += nthr) {
     const int wc = idx / (nk * pl.NT), task = idx - wc * (nk * pl.NT);  // (derivative kind, column) slowest, point fastest
     const int kk = task / pl.NT, p = task - kk * pl.NT;
     const int wrt = wc / NJ, c = wc - wrt * NJ;
@@ -368,7 +389,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
 #pragma unroll
     for (int k = 0; k < NJ; ++k) colp[k] = dst[k];
   }
-  ex.sync();
+  if (!PROD_DONE) ex.sync();
   DDPB_PHASE_MARK(bd, 4, pc_);
 
   // element accessors of fx / fu at point p (p < NT) of knot kk
