@@ -16,6 +16,14 @@
 #pragma once
 #include "batch.cuh"
 
+// development switches (geometry sweeps, tools/lin_variants.sh)
+#ifndef DDPB_COL_MERGED
+#define DDPB_COL_MERGED -1  // both derivative kinds of a column in one task: -1 = by model size; 0 / 1 force one form
+#endif
+#ifndef DDPB_FUSE_PROD
+#define DDPB_FUSE_PROD 1    // M^-1 products inside the column tasks where M^-1 is ready by then
+#endif
+
 namespace ddpb {
 
 DDPB_HD int pair_rank(int i, int j, int N) { return i * N - (i * (i + 1)) / 2 + (j - i - 1); }
@@ -141,6 +149,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   // Short tasks (<= 3 joints) run each narrow phase as one task per configuration / point; longer chains split them
   // into parallel and serial sub-phases (more barriers, much shorter serial parts).
   constexpr bool SPLIT = NJ >= 4;
+  constexpr bool COL_MERGED = DDPB_COL_MERGED < 0 ? NJ <= 3 : DDPB_COL_MERGED != 0;
   if (!SPLIT) {
     for (int idx = tid; idx < nk * pl.NQ; idx += nthr) {
       const int kk = idx / pl.NQ, s = idx - kk * pl.NQ;
@@ -257,6 +266,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 14, pc_);
+    // (folding these suffix sums into the column tasks was measured slower: 2.63 -> 2.74 ms on C3)
     for (int idx = tid; idx < nk * pl.NT; idx += nthr) {
       const int kk = idx / pl.NT, p = idx - kk * pl.NT;
       v_suffix<NJ>(VR(kk, p));
@@ -302,16 +312,10 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     }
   } else {
 
-#ifndef DDPB_COL_MERGED
-#define DDPB_COL_MERGED -1  // -1: by model size; 0 / 1 force one form (geometry sweeps)
-#endif
     // short chains: one tangent task = both derivative kinds of column j at point p (col_task2 loads the body data
     // once: 2R chain 1.62 -> 1.56 ms).  From 4 joints on the two kinds stay separate tasks: together they spill at 128
     // registers (6R: 656 B of spill stores per thread) and measured slower (3.04 -> 3.30 ms).
-    constexpr bool MERGED = DDPB_COL_MERGED < 0 ? NJ <= 3 : DDPB_COL_MERGED != 0;
-#ifndef DDPB_FUSE_PROD
-#define DDPB_FUSE_PROD 1
-#endif
+    constexpr bool MERGED = COL_MERGED;
     constexpr bool FUSE_PROD = DDPB_FUSE_PROD && MINV_EARLY && !MERGED;
     constexpr int KINDS = MERGED ? 1 : 2;
     const int n_tan = pl.NT * KINDS * NJ;
@@ -367,7 +371,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
 
   // phase 4: da/dq = -M^-1 dtau/dq, da/dv = -M^-1 dtau/dv, already scaled into the bottom blocks of
   // fx (problem.hpp:495-502): DQ <- dt * da/dq ; DV <- dt * da/dv + I   (done inside phase 3 where M^-1 is ready by then)
-  constexpr bool PROD_DONE = MODE == HESS_FD_JACOBIANS && MINV_EARLY && DDPB_FUSE_PROD && !(DDPB_COL_MERGED < 0 ? NJ <= 3 : DDPB_COL_MERGED != 0);
+  constexpr bool PROD_DONE = MODE == HESS_FD_JACOBIANS && MINV_EARLY && DDPB_FUSE_PROD && !COL_MERGED;
   for (int idx = tid; idx < (PROD_DONE ? 0 : nk * pl.NT * 2 * NJ); idx += nthr) {
     const int wc = idx / (nk * pl.NT), task = idx - wc * (nk * pl.NT);  // (derivative kind, column) slowest, point fastest
     const int kk = task / pl.NT, p = task - kk * pl.NT;
@@ -421,7 +425,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       for (int r = 0; r < ne; ++r) eqv[p * ne_sm + r] = p3[r] - tgt[r];
     }
   }
-  ex.sync();
+  if (ne > 0) ex.sync();  // (uniform over the CTA: all knots of a launch have the same number of rows)
   DDPB_PHASE_MARK(bd, 5, pc_);
   // eq_x = c_x [I, dt I] fx ; eq_u = c_x [I, dt I] fu   (problem.hpp:603-604, applied twice)
   for (int idx = tid; idx < (ne > 0 ? nk * pl.NT * ne * N : 0); idx += nthr) {
@@ -441,7 +445,7 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
     }
     SM(kk, pl.o_eqxu)[(size_t)p * ne_sm * N + c * ne + r] = acc;
   }
-  ex.sync();
+  if (ne > 0) ex.sync();
   DDPB_PHASE_MARK(bd, 6, pc_);
 
   // phase 6: assemble the stored part of the records (batch.cuh: the structural entries -- cost blocks except lu, rows
