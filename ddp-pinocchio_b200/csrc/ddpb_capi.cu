@@ -256,6 +256,7 @@ static int launch_backward(const LaunchCtx& c) {
   ddpb_batch* h = c.h;
   PhaseScope ps(h, 1, c.s);
   DISPATCH(h->nj, L::backward(c.bd, h->bwd_threads, h->bwd_smem, c.s));
+  h->launches += 1;  // the origin copy that precedes the recursion
   return check_launch(h, "backward");
 }
 static int launch_cost_old(const LaunchCtx& c) {

@@ -242,3 +242,13 @@ def test_guarded_exit_while_other_kernels_run():
         stop.set(); th.join()
     assert seen_guard and max(seen_guard) > wa.B // 2, seen_guard[:5]     # the guarded exit was really taken
     bta.close(); btb.close()
+
+
+@pytest.mark.parametrize("name,B,T,iters", [("c2", 33, 12, 3), ("c2", 1, 9, 3), ("c1", 5, 14, 4), ("c3", 9, 6, 2)])
+def test_solve_ragged_batch_sizes(name, B, T, iters):
+    """Batch sizes that do not fill a warp / a lane group / a block of 32 line-search problems: same checks as test_solve."""
+    w = pc.S.workload(name, B=B, T=T)
+    stats = pc.check_solve(make, w, iters)
+    for s in stats:
+        assert s["dev_vs_quad"] <= 50 * s["double_vs_quad"] + 1e-8, s
+    assert sum(s["same_flow"] for s in stats) >= len(stats) - max(1, len(stats) // 10), stats
