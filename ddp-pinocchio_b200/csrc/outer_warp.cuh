@@ -238,7 +238,10 @@ template <int NJ> __device__ __forceinline__ void al_decide_warp(const BatchDev&
 //   limit, more speculative trials would cost time), 16 for the arms (their batches leave most of the machine idle).
 template <int NJ> struct LsGeom {
   static constexpr int NC1 = Dim<NJ>::n <= 2 ? 8 : 16;
-  static constexpr int WPB = 4;  // trial warps per block
+#ifndef DDPB_LS_WPB_ARMS
+#define DDPB_LS_WPB_ARMS 4
+#endif
+  static constexpr int WPB = Dim<NJ>::n <= 3 ? 4 : DDPB_LS_WPB_ARMS;  // trial warps per block
 };
 constexpr int LS_MAX_TRIALS = 34;  // 2^-33 >= 1e-10 > 2^-34
 // scratch slots: trial c uses slot c (slot 0 is the new-trajectory storage itself)
