@@ -23,7 +23,7 @@ EXPORTS = ["ddpb_model_create", "ddpb_model_destroy", "ddpb_batch_create", "ddpb
            "ddpb_cost_seq_aug", "ddpb_optimality", "ddpb_solve", "ddpb_solve_async", "ddpb_batch_dims", "ddpb_launch_count",
            "ddpb_phase_times", "ddpb_enable_phase_timing", "ddpb_snapshot_save", "ddpb_snapshot_restore",
            "ddpb_measure_fp64_peak", "ddpb_set_subbatches", "ddpb_model_create_from_urdf", "ddpb_model_dims", "ddpb_model_get",
-           "ddpb_model_frame_name"]
+           "ddpb_model_frame_name", "ddpb_model_joint_types"]
 
 
 class DdpbError(RuntimeError):
@@ -33,7 +33,8 @@ class DdpbError(RuntimeError):
 class ModelDescC(C.Structure):
     _fields_ = [("kind", C.c_int), ("n_joints", C.c_int), ("parent", _ip), ("placement_rot", _dp), ("placement_trans", _dp),
                 ("axis", _dp), ("mass", _dp), ("com", _dp), ("inertia", _dp), ("gravity", C.c_double * 3), ("n_frames", C.c_int),
-                ("frame_parent", _ip), ("frame_rot", _dp), ("frame_trans", _dp), ("pend_mass", C.c_double), ("pend_length", C.c_double)]
+                ("frame_parent", _ip), ("frame_rot", _dp), ("frame_trans", _dp), ("pend_mass", C.c_double), ("pend_length", C.c_double),
+                ("joint_type", _ip)]
 
 
 class ParamsC(C.Structure):
@@ -94,12 +95,13 @@ def model_desc_c(m, keep):
         arrs = dict(parent=np.ascontiguousarray(m.parent, dtype=np.int32), placement_rot=_c(m.placement_rot),
                     placement_trans=_c(m.placement_trans), axis=_c(m.axis), mass=_c(m.mass), com=_c(m.com), inertia=_c(m.inertia),
                     frame_parent=np.ascontiguousarray(m.frame_parent, dtype=np.int32), frame_rot=_c(m.frame_rot),
-                    frame_trans=_c(m.frame_trans))
+                    frame_trans=_c(m.frame_trans), joint_type=np.ascontiguousarray(m.joint_types, dtype=np.int32))
         keep.append(arrs)
         md.parent = _i(arrs["parent"]); md.placement_rot = _d(arrs["placement_rot"]); md.placement_trans = _d(arrs["placement_trans"])
         md.axis = _d(arrs["axis"]); md.mass = _d(arrs["mass"]); md.com = _d(arrs["com"]); md.inertia = _d(arrs["inertia"])
         md.n_frames = m.n_frames
         md.frame_parent = _i(arrs["frame_parent"]); md.frame_rot = _d(arrs["frame_rot"]); md.frame_trans = _d(arrs["frame_trans"])
+        md.joint_type = _i(arrs["joint_type"])
     return md
 
 
@@ -120,11 +122,14 @@ def model_from_urdf(text):
         fpar = np.zeros(f, dtype=np.int32); fp = np.zeros((f, 3))
         _check(L.ddpb_model_get(h, _d(R), _d(p), _d(ax), _d(m), _d(c), _d(I), _i(fpar), _d(fp)))
         names = [L.ddpb_model_frame_name(h, i).decode() for i in range(f)]
+        jt = np.zeros(n, dtype=np.int32)
+        _check(L.ddpb_model_joint_types(h, _i(jt)))
     finally:
         L.ddpb_model_destroy(h)
     return models.ModelDesc(name="urdf", kind=models.KIND_REVOLUTE_CHAIN, n_joints=n, parent=np.arange(-1, n - 1, dtype=np.int32),
                             placement_rot=R, placement_trans=p, axis=ax, mass=m, com=c, inertia=I, frame_parent=fpar,
-                            frame_rot=np.tile(np.eye(3), (f, 1, 1)), frame_trans=fp, frame_names=names)
+                            frame_rot=np.tile(np.eye(3), (f, 1, 1)), frame_trans=fp, frame_names=names,
+                            joint_type=jt if jt.any() else None)
 
 
 class BatchBase:

@@ -444,6 +444,7 @@ int ddpb_model_create(const ddpb_model_desc* d, ddpb_model** out) {
     s.placement_rot.assign(d->placement_rot, d->placement_rot + 9 * n); s.placement_trans.assign(d->placement_trans, d->placement_trans + 3 * n);
     s.axis.assign(d->axis, d->axis + 3 * n); s.mass.assign(d->mass, d->mass + n); s.com.assign(d->com, d->com + 3 * n);
     s.inertia.assign(d->inertia, d->inertia + 6 * n);
+    s.joint_type.assign(m->dev.jtype, m->dev.jtype + n);
     if (f > 0) { s.frame_parent.assign(d->frame_parent, d->frame_parent + f); s.frame_trans.assign(d->frame_trans, d->frame_trans + 3 * f); }
   }
   *out = m;
@@ -476,6 +477,11 @@ int ddpb_model_get(const ddpb_model* m, double* placement_rot, double* placement
   auto put = [](auto* dst, const auto& v) { if (dst) std::copy(v.begin(), v.end(), dst); };
   put(placement_rot, s.placement_rot); put(placement_trans, s.placement_trans); put(axis, s.axis); put(mass, s.mass); put(com, s.com);
   put(inertia, s.inertia); put(frame_parent, s.frame_parent); put(frame_trans, s.frame_trans);
+  return DDPB_OK;
+}
+int ddpb_model_joint_types(const ddpb_model* m, int* joint_type) {
+  if (!m || !joint_type) return fail(DDPB_ERR_INVALID, "null argument");
+  for (int i = 0; i < m->dev.n; ++i) joint_type[i] = m->dev.jtype[i];
   return DDPB_OK;
 }
 const char* ddpb_model_frame_name(const ddpb_model* m, int frame) {

@@ -171,11 +171,14 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       int i, j;
       pl.qset_pert(s, &i, &j);
       const double qj = SM(kk, pl.o_base)[jn] + ((jn == i || jn == j) ? eps : 0.0);
-      double Rl[9];
+      double Rl[9], plc[3];
       joint_local_rot(m, jn, qj, Rl);
-      double* dst = QR(kk, s) + Q::SCR + QScratch<NJ>::RL + 9 * jn;
+      joint_local_trans(m, jn, qj, plc);
+      double* dst = QR(kk, s) + Q::SCR + QScratch<NJ>::RL + 12 * jn;
   #pragma unroll
       for (int k = 0; k < 9; ++k) dst[k] = Rl[k];
+  #pragma unroll
+      for (int k = 0; k < 3; ++k) dst[9 + k] = plc[k];
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 8, pc_);

@@ -35,6 +35,9 @@ inline int model_from_desc(const ddpb_model_desc* d, ModelDev& M, std::string& e
     double an = 0;
     for (int k = 0; k < 3; ++k) { M.pp[i][k] = d->placement_trans[i * 3 + k]; M.axis[i][k] = d->axis[i * 3 + k]; an += M.axis[i][k] * M.axis[i][k]; }
     if (std::fabs(an - 1.0) > 1e-9) { err = "joint axes must be unit vectors"; return DDPB_ERR_INVALID; }
+    const int jt = d->joint_type ? d->joint_type[i] : DDPB_JOINT_REVOLUTE;
+    if (jt != DDPB_JOINT_REVOLUTE && jt != DDPB_JOINT_PRISMATIC) { err = "joint types must be revolute (0) or prismatic (1)"; return DDPB_ERR_UNSUPPORTED; }
+    M.jtype[i] = jt;
     const double ms = d->mass[i];
     const double* c = d->com + 3 * i;
     const double* I = d->inertia + 6 * i;

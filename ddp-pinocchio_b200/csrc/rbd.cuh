@@ -1,4 +1,4 @@
-// rbd.cuh -- rigid-body dynamics of a serial revolute chain, written as small independent
+// rbd.cuh -- rigid-body dynamics of a serial chain of revolute / prismatic joints, written as small independent
 // per-thread tasks whose inputs/outputs live in shared-memory records.
 //
 // Replaces the third-party Pinocchio calls behind the reference's Model concept
@@ -44,6 +44,10 @@ struct ModelDev {
   double mass[MAXJ];
   int fparent[MAXF];
   double fp[MAXF][3];
+  // joint types (what pinocchio::urdf::buildModel makes of URDF revolute / prismatic joints): 0 = revolute about `axis`,
+  // 1 = prismatic along it.  Only the q-dependent placement (joint_local_*) and the motion subspace S_i (body_world,
+  // frame_task) depend on the type; everything downstream is written on S_i and holds for both.
+  int jtype[MAXJ + 1];
 };
 
 // ---- small vector helpers -------------------------------------------------------------------
@@ -102,6 +106,13 @@ DDPB_HD void sincos_(double q, double* s, double* c) {
 // E_i(q) = (Rp_i * R_axis(q))^T, row-major (used by frame_task only: frame positions follow the body-frame recursion
 // of the reference's forward kinematics)
 DDPB_HD void joint_E(const ModelDev& m, int i, double q, double* E) {
+  if (m.jtype[i] != 0) {  // prismatic: no rotation, E = Rp^T
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) E[cc * 3 + r] = m.Rp[i][r * 3 + cc];
+    return;
+  }
   double s, c;
   sincos_(q, &s, &c);
   const double v = 1.0 - c;
@@ -157,9 +168,9 @@ template <int NJ> struct QRec {
   // [NJ][NJ] column-major, ALIASED onto the IA block: M^-1 is computed (minv_col: S, U, 1/D only) in the phase after
   // the last reader of IA, so the two never live at the same time -- 8 NJ^2 bytes of shared memory less per record
   static constexpr int MINV = IA;
-  // scratch of the q sub-phases (QScratch, 21 NJ doubles): over U | DINV | IA, all written by q_articulate afterwards
+  // scratch of the q sub-phases (QScratch, 24 NJ doubles): over U | DINV | IA, all written by q_articulate afterwards
   static constexpr int SCR = U;
-  static constexpr int END_IA = IA + 21 * (NJ - 1), END_MINV = MINV + NJ * NJ, END_SCR = SCR + 21 * NJ;
+  static constexpr int END_IA = IA + 21 * (NJ - 1), END_MINV = MINV + NJ * NJ, END_SCR = SCR + 24 * NJ;
   static constexpr int RAW = END_IA > END_MINV ? (END_IA > END_SCR ? END_IA : END_SCR) : (END_MINV > END_SCR ? END_MINV : END_SCR);
   static constexpr int SIZE = RAW | 1;
 };
@@ -176,6 +187,11 @@ template <int NJ> struct VRec {
 
 // local rotation of joint i:  Rl = Rp_i Rot(axis_i, q_i)   (row-major 3x3)
 DDPB_HD void joint_local_rot(const ModelDev& m, int i, double q, double* Rl) {
+  if (m.jtype[i] != 0) {  // prismatic: Rl = Rp_i
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rl[k] = m.Rp[i][k];
+    return;
+  }
   double s, c;
   sincos_(q, &s, &c);
   const double v = 1.0 - c;
@@ -189,10 +205,20 @@ DDPB_HD void joint_local_rot(const ModelDev& m, int i, double q, double* Rl) {
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) Rl[r * 3 + cc] = Rp[r * 3 + 0] * RJ[0 * 3 + cc] + Rp[r * 3 + 1] * RJ[1 * 3 + cc] + Rp[r * 3 + 2] * RJ[2 * 3 + cc];
 }
-// world rotation / origin of joint frame i from those of its parent:  p <- p + R_parent pp_i ,  R <- R Rl_i
-DDPB_HD void joint_compose(const ModelDev& m, int i, const double* Rl, double* R, double* p) {
+// origin of joint frame i in parent coordinates:  pl = pp_i (revolute) ,  pp_i + Rp_i (axis_i q) (prismatic)
+DDPB_HD void joint_local_trans(const ModelDev& m, int i, double q, double* pl) {
+  pl[0] = m.pp[i][0]; pl[1] = m.pp[i][1]; pl[2] = m.pp[i][2];
+  if (m.jtype[i] != 0) {
+    const double d[3] = {m.axis[i][0] * q, m.axis[i][1] * q, m.axis[i][2] * q};
+    double t[3];
+    m3v(m.Rp[i], d, t);
+    pl[0] += t[0]; pl[1] += t[1]; pl[2] += t[2];
+  }
+}
+// world rotation / origin of joint frame i from those of its parent:  p <- p + R_parent pl_i ,  R <- R Rl_i
+DDPB_HD void joint_compose(const double* pl, const double* Rl, double* R, double* p) {
   double t[3];
-  m3v(R, m.pp[i], t);
+  m3v(R, pl, t);
   p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
   double Rn[9];
 #pragma unroll
@@ -203,18 +229,24 @@ DDPB_HD void joint_compose(const ModelDev& m, int i, const double* Rl, double* R
   for (int k = 0; k < 9; ++k) R[k] = Rn[k];
 }
 DDPB_HD void joint_advance(const ModelDev& m, int i, double q, double* R, double* p) {
-  double Rl[9];
+  double Rl[9], pl[3];
   joint_local_rot(m, i, q, Rl);
-  joint_compose(m, i, Rl, R, p);
+  joint_local_trans(m, i, q, pl);
+  joint_compose(pl, Rl, R, p);
 }
-// joint axis S = [w ; p x w] and rigid-body inertia Y of body i in world coordinates about the world origin.
+// joint axis S = [w ; p x w] (revolute) or [0 ; w] (prismatic) and rigid-body inertia Y of body i in world coordinates
+// about the world origin.
 // With h_p = R h_i (first moment about the joint origin), g = h_p + (m/2) p:
 //   h_O = h_p + m p ,  I_O = R Io_i R^T + 2 (g . p) Id - (g p^T + p g^T)      (parallel-axis shift, no division by m)
 DDPB_HD void body_world(const ModelDev& m, int i, const double* R, const double* p, double* S, double* Y) {
   double w[3], mo[3];
   m3v(R, m.axis[i], w);
-  cross3(p, w, mo);
-  S[0] = w[0]; S[1] = w[1]; S[2] = w[2]; S[3] = mo[0]; S[4] = mo[1]; S[5] = mo[2];
+  if (m.jtype[i] != 0) {
+    S[0] = 0.0; S[1] = 0.0; S[2] = 0.0; S[3] = w[0]; S[4] = w[1]; S[5] = w[2];
+  } else {
+    cross3(p, w, mo);
+    S[0] = w[0]; S[1] = w[1]; S[2] = w[2]; S[3] = mo[0]; S[4] = mo[1]; S[5] = mo[2];
+  }
   const double mass = m.mass[i];
   double hp[3];
   m3v(R, m.h[i], hp);
@@ -251,9 +283,9 @@ DDPB_HD void ia_add_body(double* IA, const double* Y) {
 //   body_world       per (configuration, body)    -> S_i, Y_i        (parallel)
 //   q_articulate     per configuration            -> IA_i, U_i, 1/D_i (serial, leaf to root)
 // q_task is the same arithmetic in one call (rollouts of small models, tests).
-template <int NJ> struct QScratch {  // scratch at QRec::SCR (21 * NJ doubles) until q_articulate overwrites it
-  static constexpr int RL = 0;            // [NJ][9]
-  static constexpr int RP = 9 * NJ;       // [NJ][12]: R_i (9) | p_i (3)
+template <int NJ> struct QScratch {  // scratch at QRec::SCR (24 * NJ doubles) until q_articulate overwrites it
+  static constexpr int RL = 0;            // [NJ][12]: local Rl_i (9) | pl_i (3)
+  static constexpr int RP = 12 * NJ;      // [NJ][12]: world R_i (9) | p_i (3)
 };
 template <int NJ> DDPB_HD void q_chain(const ModelDev& m, double* rec) {
   using Q = QRec<NJ>;
@@ -261,10 +293,12 @@ template <int NJ> DDPB_HD void q_chain(const ModelDev& m, double* rec) {
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0};
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
-    double Rl[9];
+    double Rl[9], pl[3];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Rl[k] = rec[Q::SCR + X::RL + 9 * i + k];
-    joint_compose(m, i, Rl, R, p);
+    for (int k = 0; k < 9; ++k) Rl[k] = rec[Q::SCR + X::RL + 12 * i + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pl[k] = rec[Q::SCR + X::RL + 12 * i + 9 + k];
+    joint_compose(pl, Rl, R, p);
 #pragma unroll
     for (int k = 0; k < 9; ++k) rec[Q::SCR + X::RP + 12 * i + k] = R[k];
 #pragma unroll
@@ -809,9 +843,10 @@ template <int NJ> DDPB_HD void frame_task(const ModelDev& m, const double* q, in
 #pragma unroll
   for (int i = 0; i < NJ; ++i) {
     if (i > jf) continue;
-    double E[9], t[3], Rn[9];
+    double E[9], t[3], Rn[9], pl[3];
     joint_E(m, i, q[i], E);
-    m3v(R, m.pp[i], t);
+    joint_local_trans(m, i, q[i], pl);
+    m3v(R, pl, t);
     p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
     // R_world_i = R_world_parent * E^T
 #pragma unroll
@@ -831,7 +866,9 @@ template <int NJ> DDPB_HD void frame_task(const ModelDev& m, const double* q, in
     for (int i = 0; i < NJ; ++i) {
       double lin[3] = {0, 0, 0};
       if (i <= jf) {
-        if (mode == 0) {
+        if (m.jtype[i] != 0) {  // prismatic: the linear part of [0 ; w_i], the same in both conventions
+          lin[0] = w[i][0]; lin[1] = w[i][1]; lin[2] = w[i][2];
+        } else if (mode == 0) {
           cross3(pj[i], w[i], lin);
         } else {
           double d[3] = {p3[0] - pj[i][0], p3[1] - pj[i][1], p3[2] - pj[i][2]};

@@ -2,7 +2,10 @@
 //
 // Replaces pinocchio::urdf::buildModel as the reference uses it (/root/reference/include/ddp/pinocchio_model.ipp:98-113:
 // model_t{urdf_path} -> buildModel(path, model), fixed base) for the models this library supports: serial chains of
-// revolute / continuous joints.  Follows the URDF semantics Pinocchio's parser implements:
+// revolute / continuous / prismatic joints (one degree of freedom each, nq = nv).  A continuous joint is taken as a revolute
+// joint without limits on the plain angle; Pinocchio's parser gives it the (cos, sin) parametrisation (nq = 2), with which
+// the reference's FD-of-Jacobians mode refuses to run (nq == nv required, problem.hpp:78-81).  Follows the URDF semantics
+// Pinocchio's parser implements:
 //   * the root link (never a child) is attached to the world; its own inertia does not move and is dropped;
 //   * <joint type="fixed"> merges the child link into the body of the supporting joint: the joint's <origin> composes
 //     into the placement of everything below it, the child's inertia is added to the body (parallel-axis theorem), and
@@ -10,7 +13,7 @@
 //   * <origin xyz rpy>: translation, then fixed-axis roll-pitch-yaw, R = Rz(yaw) Ry(pitch) Rx(roll);
 //   * <inertial><origin> places the centre of mass and rotates the inertia tensor into the link frame;
 //   * every link is a BODY frame (name = link name) on its supporting joint, in document order of the traversal.
-// Anything else (prismatic / floating / planar joints, a link with two movable sub-trees, more joints or frames than
+// Anything else (floating / planar joints, a link with two movable sub-trees, more joints or frames than
 // the kernels are built for) is refused with DDPB_ERR_UNSUPPORTED; malformed text with DDPB_ERR_INVALID.
 #pragma once
 #include <cctype>
@@ -187,7 +190,7 @@ inline void add_body(Body& a, const Body& b) {  // a <- a + b (composite rigid b
 // ---- the converter ------------------------------------------------------------------------------------------------------------
 struct Model {  // owns the arrays a ddpb_model_desc points into
   std::string name;
-  std::vector<int> parent, frame_parent;
+  std::vector<int> parent, frame_parent, joint_type;
   std::vector<double> placement_rot, placement_trans, axis, mass, com, inertia, frame_rot, frame_trans;
   std::vector<std::string> joint_names, frame_names;
   double gravity[3] = {0.0, 0.0, -9.81};
@@ -202,6 +205,7 @@ struct Model {  // owns the arrays a ddpb_model_desc points into
     d.n_frames = (int)frame_parent.size();
     d.frame_parent = frame_parent.data(); d.frame_rot = frame_rot.data(); d.frame_trans = frame_trans.data();
     d.pend_mass = 1.0; d.pend_length = 1.0;
+    d.joint_type = joint_type.empty() ? nullptr : joint_type.data();
     return d;
   }
 };
@@ -317,7 +321,7 @@ inline int model_from_urdf(const char* text, size_t len, Model& out, std::string
       const Xf xj = compose(it.x, o);  // joint frame in the supporting joint's frame
       if (type == "fixed") {
         stack.push_back({cl, it.jid, xj});
-      } else if (type == "revolute" || type == "continuous") {
+      } else if (type == "revolute" || type == "continuous" || type == "prismatic") {
         if (++movable > 1) {
           err = "link " + it.link + " carries two movable joints: only serial chains are supported"; return DDPB_ERR_UNSUPPORTED;
         }
@@ -332,10 +336,11 @@ inline int model_from_urdf(const char* text, size_t len, Model& out, std::string
         out.placement_trans.insert(out.placement_trans.end(), xj.p, xj.p + 3);
         for (int k = 0; k < 3; ++k) out.axis.push_back(ax[k] / nrm);
         out.joint_names.push_back(j->attr.at("name"));
+        out.joint_type.push_back(type == "prismatic" ? DDPB_JOINT_PRISMATIC : DDPB_JOINT_REVOLUTE);
         bodies.emplace_back();
         stack.push_back({cl, id, Xf()});
       } else {
-        err = "joint " + j->attr.at("name") + " has type \"" + type + "\": only revolute, continuous and fixed joints are supported";
+        err = "joint " + j->attr.at("name") + " has type \"" + type + "\": only revolute, continuous, prismatic and fixed joints are supported";
         return DDPB_ERR_UNSUPPORTED;
       }
     }

@@ -54,7 +54,7 @@ struct model_t {
     frames = d.n_frames;
   }
   // model_t{urdf_path} (pinocchio_model.ipp:155: pinocchio::urdf::buildModel with a fixed base; a leading '~' is the home
-  // directory as in builder_from_urdf_t, :98-113).  Serial chains of revolute / continuous joints, fixed joints merged.
+  // directory as in builder_from_urdf_t, :98-113).  Serial chains of revolute / continuous / prismatic joints, fixed joints merged.
   explicit model_t(const std::string& urdf_path) {
     std::string path = urdf_path;
     if (!path.empty() && path[0] == '~') { const char* home = std::getenv("HOME"); path = std::string(home ? home : "") + path.substr(1); }

@@ -10,7 +10,9 @@ from dataclasses import dataclass, field
 import numpy as np
 
 KIND_PENDULUM = 0
-KIND_REVOLUTE_CHAIN = 1
+KIND_REVOLUTE_CHAIN = 1   # serial chain of one-degree-of-freedom joints (the name predates the prismatic joints)
+JOINT_REVOLUTE = 0
+JOINT_PRISMATIC = 1
 
 
 def _rpy(r, p, y):
@@ -40,6 +42,11 @@ class ModelDesc:
     frame_names: list = None
     pend_mass: float = 1.0
     pend_length: float = 1.0
+    joint_type: np.ndarray = None      # int32 [n]: JOINT_REVOLUTE / JOINT_PRISMATIC (None = all revolute)
+
+    @property
+    def joint_types(self):
+        return np.zeros(self.n_joints, dtype=np.int32) if self.joint_type is None else np.asarray(self.joint_type, dtype=np.int32)
 
     @property
     def nq(self):
@@ -60,9 +67,9 @@ def pendulum(mass=1.0, length=1.0):
 def _chain(name, joints, frames_extra):
     n = len(joints)
     R = np.zeros((n, 3, 3)); p = np.zeros((n, 3)); ax = np.zeros((n, 3))
-    m = np.zeros(n); c = np.zeros((n, 3)); I = np.zeros((n, 6))
+    m = np.zeros(n); c = np.zeros((n, 3)); I = np.zeros((n, 6)); jt = np.zeros(n, dtype=np.int32)
     for i, j in enumerate(joints):
-        R[i] = _rpy(*j["rpy"]); p[i] = j["xyz"]; ax[i] = j["axis"]
+        R[i] = _rpy(*j["rpy"]); p[i] = j["xyz"]; ax[i] = j["axis"]; jt[i] = j.get("type", JOINT_REVOLUTE)
         m[i] = j["mass"]; c[i] = j["com"]; I[i] = j["inertia"]
     # one frame per joint (as Pinocchio adds a frame for every URDF joint/link) + extras
     fpar = list(range(n)); fR = [np.eye(3)] * n; fp = [np.zeros(3)] * n; names = [f"joint{i + 1}" for i in range(n)]
@@ -71,7 +78,7 @@ def _chain(name, joints, frames_extra):
     return ModelDesc(name=name, kind=KIND_REVOLUTE_CHAIN, n_joints=n, parent=np.arange(-1, n - 1, dtype=np.int32),
                      placement_rot=R, placement_trans=p, axis=ax, mass=m, com=c, inertia=I,
                      frame_parent=np.array(fpar, dtype=np.int32), frame_rot=np.array(fR), frame_trans=np.array(fp),
-                     frame_names=names)
+                     frame_names=names, joint_type=jt if jt.any() else None)
 
 
 def chain_2r():
@@ -131,17 +138,49 @@ def chain_nr(n, seed=7):
     return _chain(f"chain_{n}r_random", J, [("tip", n - 1, tuple(rng.uniform(-1, 1, 3)), tuple(rng.uniform(-0.2, 0.2, 3)))])
 
 
+def chain_mixed(n, types, seed=11):
+    """chain_nr with the given joint types ('R' / 'P' per joint): general axes, placements and inertias."""
+    m = chain_nr(n, seed)
+    m.name = "chain_" + types.lower()
+    m.joint_type = np.array([JOINT_PRISMATIC if t == "P" else JOINT_REVOLUTE for t in types], dtype=np.int32)
+    assert len(m.joint_type) == n
+    return m
+
+
+def scara_rrpr():
+    """SCARA-style arm: two vertical revolute joints, a vertical prismatic quill and a wrist rotation (gravity along the
+    prismatic axis; what pinocchio::urdf::buildModel makes of a URDF with revolute + prismatic joints)."""
+    z = (0, 0, 1)
+    J = [
+        dict(xyz=(0, 0, 0.4), rpy=(0, 0, 0), axis=z, mass=6.0, com=(0.2, 0, 0.03), inertia=(0.02, 0, 0, 0.12, 0, 0.125)),
+        dict(xyz=(0.4, 0, 0.05), rpy=(0, 0, 0), axis=z, mass=4.0, com=(0.15, 0, 0.02), inertia=(0.012, 0, 0, 0.05, 0, 0.055)),
+        dict(xyz=(0.3, 0, 0), rpy=(np.pi, 0, 0), axis=z, mass=1.2, com=(0, 0, -0.1), inertia=(0.01, 0, 0, 0.01, 0, 0.0008),
+             type=JOINT_PRISMATIC),
+        dict(xyz=(0, 0, 0.05), rpy=(0, 0, 0), axis=z, mass=1.0, com=(0.01, 0, 0.03), inertia=(0.004, 0, 0, 0.004, 0, 0.003)),
+    ]
+    return _chain("scara_rrpr", J, [("flange", 3, (0, 0, 0), (0, 0, 0.06))])
+
+
 def _rodrigues(a, q):
     K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
     return np.eye(3) + np.sin(q) * K + (1 - np.cos(q)) * (K @ K)
+
+
+def joint_step(m, i, qi, R, p):
+    """World rotation / origin of joint frame i from those of its parent (revolute: rotation about the axis; prismatic:
+    translation along it)."""
+    p = p + R @ m.placement_trans[i]
+    if m.joint_types[i] == JOINT_PRISMATIC:
+        R = R @ m.placement_rot[i]
+        return R, p + R @ (m.axis[i] * qi)
+    return R @ m.placement_rot[i] @ _rodrigues(m.axis[i], qi), p
 
 
 def potential_energy(m, q):
     """U(q) = -sum_i m_i g . p_com_i(q) of a serial chain (numpy forward kinematics; input generation only)."""
     R, p, U = np.eye(3), np.zeros(3), 0.0
     for i in range(m.n_joints):
-        p = p + R @ m.placement_trans[i]
-        R = R @ m.placement_rot[i] @ _rodrigues(m.axis[i], q[i])
+        R, p = joint_step(m, i, q[i], R, p)
         U -= m.mass[i] * float(m.gravity @ (p + R @ m.com[i]))
     return U
 
@@ -150,8 +189,7 @@ def frame_position(m, q, frame):
     """World position of an operational frame (numpy forward kinematics; input generation only)."""
     R, p = np.eye(3), np.zeros(3)
     for i in range(int(m.frame_parent[frame]) + 1):
-        p = p + R @ m.placement_trans[i]
-        R = R @ m.placement_rot[i] @ _rodrigues(m.axis[i], q[i])
+        R, p = joint_step(m, i, q[i], R, p)
     return p + R @ m.frame_trans[frame]
 
 
@@ -166,4 +204,4 @@ def gravity_torque(m, q, h=1e-6):
     return g
 
 
-BY_NAME = {"pendulum": pendulum, "chain_2r": chain_2r, "arm_6r": arm_6r, "arm_7r": arm_7r}
+BY_NAME = {"pendulum": pendulum, "chain_2r": chain_2r, "arm_6r": arm_6r, "arm_7r": arm_7r, "scara_rrpr": scara_rrpr}

@@ -28,7 +28,11 @@ typedef struct ddpb_batch ddpb_batch;
 enum ddpb_status { DDPB_OK = 0, DDPB_ERR_INVALID = 1, DDPB_ERR_UNSUPPORTED = 2, DDPB_ERR_CUDA = 3, DDPB_ERR_NOMEM = 4 };
 enum ddpb_model_kind {
   DDPB_MODEL_PENDULUM = 0,       /* pendulum_model_t, include/ddp/pendulum_model.hpp:12-132 */
-  DDPB_MODEL_REVOLUTE_CHAIN = 1  /* pinocchio::model_t restricted to a serial chain of revolute joints */
+  DDPB_MODEL_REVOLUTE_CHAIN = 1  /* pinocchio::model_t restricted to a serial chain of revolute / prismatic joints */
+};
+enum ddpb_joint_type {           /* what pinocchio::urdf::buildModel (pinocchio_model.ipp:111) makes of URDF joints */
+  DDPB_JOINT_REVOLUTE = 0,       /* rotation about `axis`: motion subspace [axis; 0] in the joint frame */
+  DDPB_JOINT_PRISMATIC = 1       /* translation along `axis`: motion subspace [0; axis]; nq = nv = 1 as well */
 };
 enum ddpb_eq_kind {
   DDPB_EQ_NONE = 0,
@@ -51,7 +55,7 @@ typedef struct ddpb_model_desc {
   const int* parent;             /* [n] parent joint, -1 = fixed base; must be i-1 (serial chain) */
   const double* placement_rot;   /* [n][9] row-major rotation joint frame -> parent coordinates */
   const double* placement_trans; /* [n][3] */
-  const double* axis;            /* [n][3] unit rotation axis in the joint frame */
+  const double* axis;            /* [n][3] unit joint axis in the joint frame */
   const double* mass;            /* [n] */
   const double* com;             /* [n][3] centre of mass in the body frame */
   const double* inertia;         /* [n][6] xx,xy,xz,yy,yz,zz about the centre of mass */
@@ -61,6 +65,8 @@ typedef struct ddpb_model_desc {
   const double* frame_rot;       /* [f][9] (unused by the path: only translations enter) */
   const double* frame_trans;     /* [f][3] */
   double pend_mass, pend_length; /* pendulum_model_t{mass, length} */
+  const int* joint_type;         /* [n] ddpb_joint_type; NULL = all revolute (last member: a zero-initialised descriptor
+                                  * written before this field existed keeps its meaning) */
 } ddpb_model_desc;
 
 /* dynamics_t{model, dt, second_order_finite_diff} (problem.hpp:522-524), problem_t{begin,end,c,...}
@@ -108,7 +114,7 @@ enum ddpb_scalar_field {
 /* ---- lifetime -------------------------------------------------------------------------- */
 int ddpb_model_create(const ddpb_model_desc* desc, ddpb_model** out);
 /* model_t{urdf_path} -> pinocchio::urdf::buildModel(path, model) with a fixed base (pinocchio_model.ipp:98-113, :155): the same
- * from URDF TEXT (the caller reads the file).  Revolute / continuous joints in a serial chain; fixed joints are merged into
+ * from URDF TEXT (the caller reads the file).  Revolute / continuous / prismatic joints in a serial chain; fixed joints are merged into
  * the body of their supporting joint and their child links become operational frames (every link is a BODY frame, in
  * traversal order); anything else returns DDPB_ERR_UNSUPPORTED, malformed text DDPB_ERR_INVALID. */
 int ddpb_model_create_from_urdf(const char* urdf_xml, unsigned long long length, ddpb_model** out);
@@ -116,6 +122,7 @@ int ddpb_model_create_from_urdf(const char* urdf_xml, unsigned long long length,
 int ddpb_model_dims(const ddpb_model* m, int* dims2);
 int ddpb_model_get(const ddpb_model* m, double* placement_rot, double* placement_trans, double* axis, double* mass, double* com,
                    double* inertia, int* frame_parent, double* frame_trans);
+int ddpb_model_joint_types(const ddpb_model* m, int* joint_type /* [joints] ddpb_joint_type */);
 const char* ddpb_model_frame_name(const ddpb_model* m, int frame); /* "" when the model was built from arrays */
 void ddpb_model_destroy(ddpb_model* m);
 /* ne_per_knot[t] (t in [0,T)) = equality rows at knot t, i.e. rows of the doubly advanced

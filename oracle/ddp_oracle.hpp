@@ -93,6 +93,7 @@ constexpr int MAXF = 16;  // operational frames
 constexpr int MAXE = 8;   // equality rows per knot
 
 enum ModelKind { KIND_PENDULUM = 0, KIND_REVOLUTE_TREE = 1 };
+enum JointType { JOINT_REVOLUTE = 0, JOINT_PRISMATIC = 1 };  // what pinocchio::urdf::buildModel makes of URDF revolute / prismatic joints
 enum ConstraintKind { EQ_NONE = 0, EQ_CONFIG = 1, EQ_SPATIAL = 2 };
 enum FrameJacMode { FJ_WORLD = 0, FJ_LOCAL_WORLD_ALIGNED = 1 };
 
@@ -173,11 +174,13 @@ template <class S> inline void xf_dense(const Xform<S>& X, S* M) {
 // ----------------------------------------------------------------------------------
 template <class S> struct Model {
   int kind = KIND_REVOLUTE_TREE;
-  int n = 0;                 // number of revolute joints (nq = nv = n)
+  int n = 0;                 // number of one-degree-of-freedom joints (nq = nv = n)
+  int jtype[MAXJ] = {0, 0, 0, 0, 0, 0, 0, 0};  // JointType: the motion subspace is [axis; 0] (revolute) or [0; axis] (prismatic)
   int parent[MAXJ];          // -1 = fixed base
   S Rp[MAXJ][9];             // joint placement rotation (joint frame -> parent coordinates), row-major
   S pp[MAXJ][3];             // joint placement translation in parent coordinates
   S axis[MAXJ][3];           // unit joint axis in the joint frame
+  int so(int i) const { return jtype[i] == JOINT_PRISMATIC ? 3 : 0; }  // offset of the axis inside the 6-vector S_i
   S mass[MAXJ];
   S com[MAXJ][3];            // centre of mass in body frame
   S Ic[MAXJ][6];             // rotational inertia about the COM: xx,xy,xz,yy,yz,zz
@@ -219,8 +222,17 @@ template <class S> inline void mat6_mul_vec(const S* M, const S* v, S* o) {
 
 // joint transforms X_i(q_i) = X_J(q_i) X_T(i)   (Rodrigues rotation about the joint axis)
 template <class S> inline void joint_xform(const Model<S>& m, int i, S q, Xform<S>& X) {
-  S s = Sin(q), c = Cos(q), v = S(1) - c;
   const S* a = m.axis[i];
+  if (m.jtype[i] == JOINT_PRISMATIC) {
+    // translation by q along the axis: E = Rp^T, child origin = pp + Rp (axis q)
+    S d[3] = {a[0] * q, a[1] * q, a[2] * q}, t[3];
+    mat3_mul_vec(m.Rp[i], d, t);
+    for (int r = 0; r < 3; ++r)
+      for (int cidx = 0; cidx < 3; ++cidx) X.E[cidx * 3 + r] = m.Rp[i][r * 3 + cidx];
+    for (int k = 0; k < 3; ++k) X.r[k] = m.pp[i][k] + t[k];
+    return;
+  }
+  S s = Sin(q), c = Cos(q), v = S(1) - c;
   S RJ[9] = {c + v * a[0] * a[0],        v * a[0] * a[1] - s * a[2], v * a[0] * a[2] + s * a[1],
              v * a[1] * a[0] + s * a[2], c + v * a[1] * a[1],        v * a[1] * a[2] - s * a[0],
              v * a[2] * a[0] - s * a[1], v * a[2] * a[1] + s * a[0], c + v * a[2] * a[2]};
@@ -251,7 +263,9 @@ inline void aba(const Model<S>& m, const S* q, const S* qd, const S* tau, AbaDat
   for (int i = 0; i < n; ++i) {
     joint_xform(m, i, q[i], d.X[i]);
     body_inertia(m, i, d.I6[i]);
-    S Sq[6] = {m.axis[i][0] * qd[i], m.axis[i][1] * qd[i], m.axis[i][2] * qd[i], S(0), S(0), S(0)};
+    const int o = m.so(i);
+    S Sq[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
+    for (int k = 0; k < 3; ++k) Sq[o + k] = m.axis[i][k] * qd[i];
     if (m.parent[i] >= 0) {
       xf_motion(d.X[i], d.v[m.parent[i]], d.v[i]);
       for (int k = 0; k < 6; ++k) d.v[i][k] += Sq[k];
@@ -265,10 +279,12 @@ inline void aba(const Model<S>& m, const S* q, const S* qd, const S* tau, AbaDat
     for (int k = 0; k < 36; ++k) d.IA[i][k] = d.I6[i][k];
   }
   for (int i = n - 1; i >= 0; --i) {
-    S Sv[6] = {m.axis[i][0], m.axis[i][1], m.axis[i][2], S(0), S(0), S(0)};
+    const int o = m.so(i);
+    S Sv[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
+    for (int k = 0; k < 3; ++k) Sv[o + k] = m.axis[i][k];
     mat6_mul_vec(d.IA[i], Sv, d.U[i]);
     S D = S(0), SpA = S(0);
-    for (int k = 0; k < 3; ++k) { D += Sv[k] * d.U[i][k]; SpA += Sv[k] * d.pA[i][k]; }
+    for (int k = 0; k < 3; ++k) { D += Sv[o + k] * d.U[i][o + k]; SpA += Sv[o + k] * d.pA[i][o + k]; }
     d.Dinv[i] = S(1) / D;
     d.u[i] = tau[i] - SpA;
     if (m.parent[i] >= 0) {
@@ -307,7 +323,7 @@ inline void aba(const Model<S>& m, const S* q, const S* qd, const S* tau, AbaDat
     for (int k = 0; k < 6; ++k) Ua += d.U[i][k] * ap[k];
     d.qdd[i] = d.Dinv[i] * (d.u[i] - Ua);
     for (int k = 0; k < 6; ++k) d.a[i][k] = ap[k];
-    for (int k = 0; k < 3; ++k) d.a[i][k] += m.axis[i][k] * d.qdd[i];
+    for (int k = 0; k < 3; ++k) d.a[i][m.so(i) + k] += m.axis[i][k] * d.qdd[i];
   }
 }
 
@@ -322,7 +338,8 @@ inline void rnea(const Model<S>& m, const S* q, const S* qd, const S* qdd, S* ta
     joint_xform(m, i, q[i], X[i]);
     S I6[36];
     body_inertia(m, i, I6);
-    S Sq[6] = {m.axis[i][0] * qd[i], m.axis[i][1] * qd[i], m.axis[i][2] * qd[i], S(0), S(0), S(0)};
+    S Sq[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
+    for (int k = 0; k < 3; ++k) Sq[m.so(i) + k] = m.axis[i][k] * qd[i];
     S vp[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
     if (m.parent[i] >= 0) xf_motion(X[i], v[m.parent[i]], vp);
     for (int k = 0; k < 6; ++k) v[i][k] = vp[k] + Sq[k];
@@ -330,7 +347,7 @@ inline void rnea(const Model<S>& m, const S* q, const S* qd, const S* qdd, S* ta
     xf_motion(X[i], m.parent[i] >= 0 ? a[m.parent[i]] : a0, ap);
     crm(v[i], Sq, cr);
     for (int k = 0; k < 6; ++k) a[i][k] = ap[k] + cr[k];
-    for (int k = 0; k < 3; ++k) a[i][k] += m.axis[i][k] * qdd[i];
+    for (int k = 0; k < 3; ++k) a[i][m.so(i) + k] += m.axis[i][k] * qdd[i];
     S Ia[6], Iv[6], vf[6];
     mat6_mul_vec(I6, a[i], Ia);
     mat6_mul_vec(I6, v[i], Iv);
@@ -339,7 +356,7 @@ inline void rnea(const Model<S>& m, const S* q, const S* qd, const S* qdd, S* ta
   }
   for (int i = n - 1; i >= 0; --i) {
     S t = S(0);
-    for (int k = 0; k < 3; ++k) t += m.axis[i][k] * f[i][k];
+    for (int k = 0; k < 3; ++k) t += m.axis[i][k] * f[i][m.so(i) + k];
     tau[i] = t;
     if (m.parent[i] >= 0) {
       S fp[6];
@@ -361,7 +378,7 @@ inline void minv_from_aba(const Model<S>& m, const AbaData<S>& d, S* Minv /* n x
       for (int k = 0; k < 6; ++k) pA[i][k] = S(0);
     for (int i = n - 1; i >= 0; --i) {
       S SpA = S(0);
-      for (int k = 0; k < 3; ++k) SpA += m.axis[i][k] * pA[i][k];
+      for (int k = 0; k < 3; ++k) SpA += m.axis[i][k] * pA[i][m.so(i) + k];
       u[i] = (i == col ? S(1) : S(0)) - SpA;
       if (m.parent[i] >= 0) {
         S pa[6], pf[6];
@@ -377,7 +394,7 @@ inline void minv_from_aba(const Model<S>& m, const AbaData<S>& d, S* Minv /* n x
       for (int k = 0; k < 6; ++k) Ua += d.U[i][k] * ap[k];
       S qdd = d.Dinv[i] * (u[i] - Ua);
       for (int k = 0; k < 6; ++k) a[i][k] = ap[k];
-      for (int k = 0; k < 3; ++k) a[i][k] += m.axis[i][k] * qdd;
+      for (int k = 0; k < 3; ++k) a[i][m.so(i) + k] += m.axis[i][k] * qdd;
       Minv[col * n + i] = qdd;
     }
   }
@@ -407,7 +424,8 @@ inline void rnea_tangents(const Model<S>& m, const S* qd, const AbaData<S>& d, S
     for (int j = 0; j < n; ++j) {
       S dv[MAXJ][6], da[MAXJ][6], dF[MAXJ][6];
       for (int i = 0; i < n; ++i) {
-        S Sj[6] = {m.axis[i][0], m.axis[i][1], m.axis[i][2], S(0), S(0), S(0)};
+        S Sj[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
+        for (int k = 0; k < 3; ++k) Sj[m.so(i) + k] = m.axis[i][k];
         S Sq[6];
         for (int k = 0; k < 6; ++k) Sq[k] = Sj[k] * qd[i];
         for (int k = 0; k < 6; ++k) { dv[i][k] = S(0); da[i][k] = S(0); }
@@ -447,13 +465,14 @@ inline void rnea_tangents(const Model<S>& m, const S* qd, const AbaData<S>& d, S
       S* out = wrt_v ? dtau_dv : dtau_dq;
       for (int i = n - 1; i >= 0; --i) {
         S t = S(0);
-        for (int k = 0; k < 3; ++k) t += m.axis[i][k] * dF[i][k];
+        for (int k = 0; k < 3; ++k) t += m.axis[i][k] * dF[i][m.so(i) + k];
         out[j * n + i] = t;
         if (m.parent[i] >= 0) {
           S tot[6], fp[6];
           for (int k = 0; k < 6; ++k) tot[k] = dF[i][k];
           if (i == j && !wrt_v) {
-            S Sj[6] = {m.axis[i][0], m.axis[i][1], m.axis[i][2], S(0), S(0), S(0)};
+            S Sj[6] = {S(0), S(0), S(0), S(0), S(0), S(0)};
+            for (int k = 0; k < 3; ++k) Sj[m.so(i) + k] = m.axis[i][k];
             S t3[6];
             crf(Sj, F[i], t3);
             for (int k = 0; k < 6; ++k) tot[k] += t3[k];
@@ -578,7 +597,9 @@ inline void d_frame_coordinates(const Model<S>& m, int frame, const S* q, int mo
   for (int j = jf; j >= 0; j = m.parent[j]) {
     S wj[3], lin[3];
     mat3_mul_vec(w.R[j], m.axis[j], wj);
-    if (mode == FJ_WORLD) {
+    if (m.jtype[j] == JOINT_PRISMATIC) {
+      for (int k = 0; k < 3; ++k) lin[k] = wj[k];  // linear part of [0; w_j]: the same in both conventions
+    } else if (mode == FJ_WORLD) {
       cross3(w.p[j], wj, lin);
     } else {
       S dlt[3] = {pf[0] - w.p[j][0], pf[1] - w.p[j][1], pf[2] - w.p[j][2]};

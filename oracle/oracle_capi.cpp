@@ -33,6 +33,7 @@ struct orc_model_desc {
   const double* frame_rot;        // 9 f
   const double* frame_trans;      // 3 f
   double pend_mass, pend_length;
+  const int* joint_type;          // n: 0 revolute, 1 prismatic (NULL = all revolute)
 };
 struct orc_problem_desc {
   int T;
@@ -60,6 +61,7 @@ template <class S> static void fill_problem(Problem<S>& p, const orc_model_desc*
   if (m->kind == KIND_REVOLUTE_TREE) {
     for (int i = 0; i < M.n; ++i) {
       M.parent[i] = m->parent[i];
+      M.jtype[i] = m->joint_type ? m->joint_type[i] : JOINT_REVOLUTE;
       for (int k = 0; k < 9; ++k) M.Rp[i][k] = S(m->placement_rot[i * 9 + k]);
       for (int k = 0; k < 3; ++k) {
         M.pp[i][k] = S(m->placement_trans[i * 3 + k]);

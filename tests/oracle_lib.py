@@ -16,7 +16,8 @@ DERIV_FIELDS = ["lfx", "lfxx", "lx", "lu", "lxx", "lux", "luu", "f_val", "fx", "
 class ModelDescC(C.Structure):
     _fields_ = [("kind", C.c_int), ("n_joints", C.c_int), ("parent", _ip), ("placement_rot", _dp), ("placement_trans", _dp),
                 ("axis", _dp), ("mass", _dp), ("com", _dp), ("inertia", _dp), ("gravity", C.c_double * 3), ("n_frames", C.c_int),
-                ("frame_parent", _ip), ("frame_rot", _dp), ("frame_trans", _dp), ("pend_mass", C.c_double), ("pend_length", C.c_double)]
+                ("frame_parent", _ip), ("frame_rot", _dp), ("frame_trans", _dp), ("pend_mass", C.c_double), ("pend_length", C.c_double),
+                ("joint_type", _ip)]
 
 
 class ProblemDescC(C.Structure):
@@ -74,12 +75,14 @@ def model_desc_c(m, keep):
                     com=np.ascontiguousarray(m.com, dtype=np.float64), inertia=np.ascontiguousarray(m.inertia, dtype=np.float64),
                     frame_parent=np.ascontiguousarray(m.frame_parent, dtype=np.int32),
                     frame_rot=np.ascontiguousarray(m.frame_rot, dtype=np.float64),
-                    frame_trans=np.ascontiguousarray(m.frame_trans, dtype=np.float64))
+                    frame_trans=np.ascontiguousarray(m.frame_trans, dtype=np.float64),
+                    joint_type=np.ascontiguousarray(m.joint_types, dtype=np.int32))
         keep.append(arrs)
         md.parent = _i(arrs["parent"]); md.placement_rot = _d(arrs["placement_rot"]); md.placement_trans = _d(arrs["placement_trans"])
         md.axis = _d(arrs["axis"]); md.mass = _d(arrs["mass"]); md.com = _d(arrs["com"]); md.inertia = _d(arrs["inertia"])
         md.n_frames = m.n_frames
         md.frame_parent = _i(arrs["frame_parent"]); md.frame_rot = _d(arrs["frame_rot"]); md.frame_trans = _d(arrs["frame_trans"])
+        md.joint_type = _i(arrs["joint_type"])
     return md
 
 

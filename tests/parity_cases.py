@@ -54,7 +54,30 @@ def cases():
     out.append(("chain5r_random_spatial", w))
     w = S.Workload("chain1r", P.models.chain_nr(1), 2, 6)
     out.append(("chain1r", w))
+    # prismatic joints (URDF type="prismatic"): every kernel family -- arms (4 and 5 joints, both Hessian modes, both
+    # constraint kinds), the register-resident <= 2-joint kernels, a single sliding joint
+    m = P.models.scara_rrpr()
+    out.append(("scara_rrpr_spatial", S.Workload("scara_rrpr_spatial", m, 3, 8, eq_kind=S.EQ_SPATIAL, frame=m.n_frames - 1)))
+    out.append(("scara_rrpr_fdvalues", S.Workload("scara_rrpr_fdvalues", P.models.scara_rrpr(), 2, 6, hess_mode=S.HESS_FD_VALUES)))
+    out.append(("chain_prprr_random", S.Workload("chain_prprr_random", P.models.chain_mixed(5, "PRPRR"), 2, 6)))
+    out.append(("chain_rp_random", S.Workload("chain_rp_random", P.models.chain_mixed(2, "RP"), 4, 9)))
+    out.append(("chain_pr_random_fdvalues", S.Workload("chain_pr_random_fdvalues", P.models.chain_mixed(2, "PR"), 3, 7, hess_mode=S.HESS_FD_VALUES)))
+    out.append(("chain_p_random", S.Workload("chain_p_random", P.models.chain_mixed(1, "P"), 2, 6)))
     return out
+
+
+def prismatic_workload(tag, B, T):
+    """Workloads on chains with prismatic joints (models.scara_rrpr, models.chain_mixed) for the external / end-to-end checks."""
+    if tag == "scara":
+        return S.Workload("scara_rrpr", P.models.scara_rrpr(), B, T)
+    if tag == "scara_spatial":
+        m = P.models.scara_rrpr()
+        return S.Workload("scara_rrpr_spatial", m, B, T, eq_kind=S.EQ_SPATIAL, frame=m.n_frames - 1)
+    if tag == "prprr":
+        return S.Workload("chain_prprr_random", P.models.chain_mixed(5, "PRPRR"), B, T)
+    if tag == "rp":
+        return S.Workload("chain_rp_random", P.models.chain_mixed(2, "RP"), B, T)
+    raise ValueError(tag)
 
 
 def setup(make, w, seed=1, random_controls=True):
@@ -116,7 +139,7 @@ def planar_2r_closed_form(m, q, v, tau):
 
 
 def lagrangian_forward_dynamics(m, q, v, tau, h=1e-5):
-    """Forward dynamics of a revolute chain from Lagrangian mechanics, written with numpy forward kinematics only:
+    """Forward dynamics of a chain of revolute / prismatic joints from Lagrangian mechanics, written with numpy forward kinematics only:
         M(q) = sum_i m_i Jv_i^T Jv_i + Jw_i^T (R_i I_i R_i^T) Jw_i      (geometric link Jacobians at the COM),
         c_i  = sum_jk (dM_ij/dq_k - 1/2 dM_jk/dq_i) v_j v_k              (Christoffel symbols, dM/dq by central differences),
         g_j  = -sum_i m_i gravity . Jv_i[:, j],      qdd = M^-1 (tau - c - g).
@@ -124,6 +147,7 @@ def lagrangian_forward_dynamics(m, q, v, tau, h=1e-5):
     central differences (~1e-9 relative)."""
     from ddp_pinocchio_b200.models import _rodrigues
     n = m.n_joints
+    jt = m.joint_types
 
     def mass_and_gravity(q):
         R, p = np.eye(3), np.zeros(3)
@@ -132,13 +156,20 @@ def lagrangian_forward_dynamics(m, q, v, tau, h=1e-5):
             p = p + R @ m.placement_trans[i]
             Rp = R @ m.placement_rot[i]
             ax.append(Rp @ m.axis[i]); org.append(p.copy())
-            R = Rp @ _rodrigues(m.axis[i], q[i])
+            if jt[i]:    # prismatic: translation along the axis, no rotation
+                R = Rp
+                p = p + ax[i] * q[i]
+            else:
+                R = Rp @ _rodrigues(m.axis[i], q[i])
             c = p + R @ m.com[i]
             xx, xy, xz, yy, yz, zz = m.inertia[i]
             Iw = R @ np.array([[xx, xy, xz], [xy, yy, yz], [xz, yz, zz]]) @ R.T
             Jv, Jw = np.zeros((3, n)), np.zeros((3, n))
             for j in range(i + 1):
-                Jv[:, j] = np.cross(ax[j], c - org[j]); Jw[:, j] = ax[j]
+                if jt[j]:
+                    Jv[:, j] = ax[j]
+                else:
+                    Jv[:, j] = np.cross(ax[j], c - org[j]); Jw[:, j] = ax[j]
             M += m.mass[i] * Jv.T @ Jv + Jw.T @ Iw @ Jw
             g -= m.mass[i] * (m.gravity @ Jv)
         return M, g

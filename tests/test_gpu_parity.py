@@ -44,6 +44,25 @@ def test_arm_records_vs_lagrangian_mechanics(name):
     pc.check_vs_lagrangian(make, pc.S.workload(name, B=2, T=4))
 
 
+@pytest.mark.parametrize("tag", ["scara", "prprr", "rp"])
+def test_prismatic_records_vs_lagrangian_mechanics(tag):
+    """Chains with sliding joints: f(x,u) and f_u = dt M^-1 of the records against Lagrange's equations (numpy kinematics only)."""
+    pc.check_vs_lagrangian(make, pc.prismatic_workload(tag, 2, 4))
+
+
+@pytest.mark.parametrize("tag,T,iters,floor", [("scara", 16, 4, 1e-6), ("scara_spatial", 12, 4, 1e-6), ("rp", 20, 5, 1e-8)])
+def test_solve_prismatic(tag, T, iters, floor):
+    """End to end on chains with a sliding joint.  The SCARA's light wrist turns about an axis 0.7 m from the world origin:
+    in world-origin Pluecker coordinates its 0.003 kg m^2 is what is left of terms of 0.5 kg m^2, so the first-order records
+    carry 1e-13 instead of 1e-15 (still 4 digits inside the 1e-9 tolerance) and the reference's forward-difference Hessians
+    (eps = 2^-26) amplify that to 1e-7 in the trajectories: the floor of the end-to-end distance is 1e-6 there."""
+    stats = pc.check_solve(make, pc.prismatic_workload(tag, 3, T), iters)
+    for s in stats:
+        assert s["dev_vs_quad"] <= 50 * s["double_vs_quad"] + floor, s
+        assert s["dev_vs_double"] <= 50 * s["double_vs_quad"] + floor, s
+    assert sum(s["same_flow"] for s in stats) >= len(stats) - 1, stats
+
+
 @pytest.mark.parametrize("name,T,iters", [("c2", 40, 6), ("c3", 20, 5), ("c4", 12, 4), ("c5", 10, 3)])
 def test_solve(name, T, iters):
     w = pc.S.workload(name, B=3, T=T)

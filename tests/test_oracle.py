@@ -15,10 +15,13 @@ from parity_cases import planar_2r_closed_form, lagrangian_forward_dynamics  # n
 
 S = P.synthetic
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = [P.models.chain_2r, P.models.arm_6r, P.models.arm_7r, lambda: P.models.chain_nr(5), lambda: P.models.chain_nr(1)]
+MODELS = [P.models.chain_2r, P.models.arm_6r, P.models.arm_7r, lambda: P.models.chain_nr(5), lambda: P.models.chain_nr(1),
+          P.models.scara_rrpr, lambda: P.models.chain_mixed(5, "PRPRR"), lambda: P.models.chain_mixed(2, "RP"),
+          lambda: P.models.chain_mixed(1, "P")]
+MODEL_IDS = ["2r", "6r", "7r", "5r_random", "1r_random", "scara_rrpr", "prprr_random", "rp_random", "p_random"]
 
 
-@pytest.mark.parametrize("mk", MODELS, ids=["2r", "6r", "7r", "5r_random", "1r_random"])
+@pytest.mark.parametrize("mk", MODELS, ids=MODEL_IDS)
 def test_aba_satisfies_inverse_dynamics(mk):
     """M(q) aba(q,v,tau) + nle(q,v) = tau, with an independently written RNEA."""
     m = mk(); n = m.nq
@@ -31,7 +34,7 @@ def test_aba_satisfies_inverse_dynamics(mk):
         assert np.abs(a - o.aba(q, v, tau, prec=1)).max() < 1e-12 * max(1.0, np.abs(a).max())
 
 
-@pytest.mark.parametrize("mk", MODELS, ids=["2r", "6r", "7r", "5r_random", "1r_random"])
+@pytest.mark.parametrize("mk", MODELS, ids=MODEL_IDS)
 def test_aba_derivatives_vs_quad_central_differences(mk):
     m = mk(); n = m.nq
     o = ol.Oracle(m, 4)
@@ -67,7 +70,7 @@ def test_aba_2r_chain_vs_textbook_closed_form():
         assert np.abs(minv - np.linalg.inv(M)).max() < 1e-12 * np.abs(minv).max()
 
 
-@pytest.mark.parametrize("mk", MODELS, ids=["2r", "6r", "7r", "5r_random", "1r_random"])
+@pytest.mark.parametrize("mk", MODELS, ids=MODEL_IDS)
 def test_aba_vs_lagrangian_mechanics(mk):
     """External check of ABA and M^-1 for every model (the arms have no closed form): Lagrange's equations with the
     mass matrix from geometric link Jacobians and Christoffel symbols by central differences."""
@@ -83,8 +86,9 @@ def test_aba_vs_lagrangian_mechanics(mk):
         assert np.abs(minv @ M - np.eye(n)).max() < 1e-10 * np.linalg.cond(M)
 
 
-def test_frame_jacobian_conventions():
-    m = P.models.arm_6r(); n = m.nq
+@pytest.mark.parametrize("mk", [P.models.arm_6r, P.models.scara_rrpr, lambda: P.models.chain_mixed(5, "PRPRR")], ids=["6r", "scara_rrpr", "prprr_random"])
+def test_frame_jacobian_conventions(mk):
+    m = mk(); n = m.nq
     o = ol.Oracle(m, 4)
     q = np.random.RandomState(2).uniform(-2, 2, n)
     fr = m.n_frames - 1
@@ -98,7 +102,9 @@ def test_frame_jacobian_conventions():
     assert np.abs(p - P.models.frame_position(m, q, fr)).max() < 1e-13   # numpy FK of the input generator
     # WORLD convention (what the reference uses, Appendix B.1): velocity of the point at the world origin;
     # J_world(:,j) = J_lwa(:,j) - w_j x p, so the two agree only for a frame at the origin
-    assert np.abs(J_world - J_lwa).max() > 1e-2
+    rev = m.joint_types == 0
+    assert np.abs(J_world - J_lwa)[:, rev].max() > 1e-2
+    assert np.abs(J_world - J_lwa)[:, ~rev].max() == 0.0 if (~rev).any() else True   # a prismatic column is its axis in both
     w = np.stack([np.cross(J_lwa[:, j], J_world[:, j] - J_lwa[:, j]) for j in range(n)])  # orthogonality sanity
     assert np.isfinite(w).all()
 

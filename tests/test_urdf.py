@@ -1,5 +1,5 @@
 """URDF text -> model through the C ABI (ddpb_model_create_from_urdf, csrc/urdf_host.hpp): the replacement of
-pinocchio::urdf::buildModel (/root/reference/include/ddp/pinocchio_model.ipp:98-113) for serial revolute chains.  No GPU needed:
+pinocchio::urdf::buildModel (/root/reference/include/ddp/pinocchio_model.ipp:98-113) for serial chains of revolute / prismatic joints.  No GPU needed:
 model construction is host code."""
 import numpy as np
 import pytest
@@ -83,8 +83,41 @@ def test_fixed_joint_merges_inertia_into_the_supporting_body():
     assert np.allclose(m.frame_trans[1], [0.2, 0, -1.0], atol=1e-16)
 
 
+# the SCARA of models.scara_rrpr() as a URDF: two revolute joints, a prismatic quill (joint frame rolled by pi), a revolute wrist
+SCARA = """<robot name="scara">
+  <link name="base"/>
+  <joint name="j1" type="revolute"><parent link="base"/><child link="arm1"/><origin xyz="0 0 0.4"/><axis xyz="0 0 1"/></joint>
+  <link name="arm1"><inertial><mass value="6.0"/><origin xyz="0.2 0 0.03"/><inertia ixx="0.02" ixy="0" ixz="0" iyy="0.12" iyz="0" izz="0.125"/></inertial></link>
+  <joint name="j2" type="revolute"><parent link="arm1"/><child link="arm2"/><origin xyz="0.4 0 0.05"/><axis xyz="0 0 1"/></joint>
+  <link name="arm2"><inertial><mass value="4.0"/><origin xyz="0.15 0 0.02"/><inertia ixx="0.012" ixy="0" ixz="0" iyy="0.05" iyz="0" izz="0.055"/></inertial></link>
+  <joint name="quill" type="prismatic"><parent link="arm2"/><child link="quill_link"/><origin xyz="0.3 0 0" rpy="3.141592653589793 0 0"/><axis xyz="0 0 3"/>
+    <limit lower="0" upper="0.3" effort="100" velocity="1"/></joint>
+  <link name="quill_link"><inertial><mass value="1.2"/><origin xyz="0 0 -0.1"/><inertia ixx="0.01" ixy="0" ixz="0" iyy="0.01" iyz="0" izz="0.0008"/></inertial></link>
+  <joint name="wrist" type="revolute"><parent link="quill_link"/><child link="wrist_link"/><origin xyz="0 0 0.05"/><axis xyz="0 0 1"/></joint>
+  <link name="wrist_link"><inertial><mass value="1.0"/><origin xyz="0.01 0 0.03"/><inertia ixx="0.004" ixy="0" ixz="0" iyy="0.004" iyz="0" izz="0.003"/></inertial></link>
+  <joint name="flange_fixed" type="fixed"><parent link="wrist_link"/><child link="flange"/><origin xyz="0 0 0.06"/></joint>
+  <link name="flange"/>
+</robot>"""
+
+
+def test_prismatic_joint_from_urdf():
+    """<joint type="prismatic"> becomes a one-degree-of-freedom sliding joint (as Pinocchio's parser makes it): the URDF of
+    the SCARA gives the embedded table, joint types included, and its forward kinematics slides along the rolled axis."""
+    m = capi.model_from_urdf(SCARA)
+    ref = models.scara_rrpr()
+    assert m.n_joints == 4 and list(m.joint_types) == [0, 0, 1, 0] and list(ref.joint_types) == [0, 0, 1, 0]
+    for f in ("placement_trans", "axis", "mass", "com", "inertia"):
+        assert np.array_equal(getattr(m, f), getattr(ref, f)), f
+    assert np.abs(m.placement_rot - ref.placement_rot).max() < 1e-15     # rpy = (pi, 0, 0): sin(pi) is not exactly 0 on either side
+    assert m.frame_names == ["arm1", "arm2", "quill_link", "wrist_link", "flange"] and list(m.frame_parent) == [0, 1, 2, 3, 3]
+    q = np.array([0.3, -0.7, 0.12, 0.5])
+    tip0, tip1 = models.frame_position(m, q, 4), models.frame_position(m, q + np.array([0, 0, 0.05, 0]), 4)
+    assert np.allclose(tip1 - tip0, [0, 0, -0.05], atol=1e-15)           # the quill's z axis points down
+
+
 @pytest.mark.parametrize("text,code,what", [
-    ("<robot name='r'><link name='a'/><link name='b'/><joint name='j' type='prismatic'><parent link='a'/><child link='b'/></joint></robot>", 2, "prismatic"),
+    ("<robot name='r'><link name='a'/><link name='b'/><joint name='j' type='planar'><parent link='a'/><child link='b'/></joint></robot>", 2, "planar"),
+    ("<robot name='r'><link name='a'/><link name='b'/><joint name='j' type='floating'><parent link='a'/><child link='b'/></joint></robot>", 2, "floating"),
     ("<robot name='r'><link name='a'/><link name='b'/><link name='c'/>"
      "<joint name='j1' type='revolute'><parent link='a'/><child link='b'/></joint>"
      "<joint name='j2' type='revolute'><parent link='a'/><child link='c'/></joint></robot>", 2, "serial chains"),
