@@ -131,7 +131,7 @@ struct ddpb_batch {
   ModelDev model;
   BatchDev bd;
   int device = 0;
-  int mt = 0;        // model tag for thread-per-problem kernels: 0 = pendulum, else number of joints
+  int mt = 0;        // model tag of DISPATCH: 0 = pendulum, else number of joints (+ 8 for chains with prismatic joints)
   int nj = 1;        // joints (1 for the pendulum)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -203,9 +203,17 @@ struct LaunchCtx {
   LaunchCtx(ddpb_batch* hh, int b0, int nb, cudaStream_t ss) : h(hh), bd(hh->bd), s(ss) { bd.b0 = b0; bd.nb = nb; }
 };
 
-// run STMT with L = Launch<k> for the model tag k (0 = pendulum, 1..7 = joints)
+// run STMT with L = Launch<k, PR> for the model tag: 0 = pendulum, 1..7 = joints of an all-revolute chain, 8 + (1..7) = joints
+// of a chain with prismatic joints (the device code compiled with the joint-type tests, variant.cuh)
 #define DISPATCH(tag, STMT)                                     \
   switch (tag) {                                                \
+    case 9: { using L = Launch<1, true>; STMT; } break;         \
+    case 10: { using L = Launch<2, true>; STMT; } break;        \
+    case 11: { using L = Launch<3, true>; STMT; } break;        \
+    case 12: { using L = Launch<4, true>; STMT; } break;        \
+    case 13: { using L = Launch<5, true>; STMT; } break;        \
+    case 14: { using L = Launch<6, true>; STMT; } break;        \
+    case 15: { using L = Launch<7, true>; STMT; } break;        \
     case 0: { using L = Launch<0>; STMT; } break;               \
     case 1: { using L = Launch<1>; STMT; } break;               \
     case 2: { using L = Launch<2>; STMT; } break;               \
@@ -334,7 +342,7 @@ static int batch_init(ddpb_batch* h, const ddpb_model* m, int B, int T, const in
   const int n = m->nq;
   h->model = m->dev;
   h->device = device;
-  h->mt = m->dev.kind == DDPB_MODEL_PENDULUM ? 0 : n;
+  h->mt = m->dev.kind == DDPB_MODEL_PENDULUM ? 0 : n + (m->dev.any_prismatic ? 8 : 0);
   h->nj = n;
   BatchDev& bd = h->bd;
   std::memset(&bd, 0, sizeof(bd));

@@ -16,7 +16,7 @@
 #include "batch.cuh"
 #include "linearize.cuh"
 
-namespace ddpb {
+DDPB_VARIANT_BEGIN
 
 // x_{t+1} = f(x_t, u_t): explicit Euler on forward dynamics (problem.hpp:441-461)
 // per-thread scratch of the fused forward dynamics: element e at p[e * stride] (rbd.cuh aba_fused)
@@ -439,4 +439,4 @@ DDPB_HD void post_forward_problem(const BatchDev& bd, int b) {
   bd.scal[(size_t)S_ITERATIONS * B + b] += 1.0;
 }
 
-}  // namespace ddpb
+DDPB_VARIANT_END

@@ -1,4 +1,5 @@
-// kernels_nj.cu -- the hot-path kernels for one model size; compile with -DDDPB_NJ=<0..7>.
+// kernels_nj.cu -- the hot-path kernels for one model size and joint-type variant; compile with -DDDPB_NJ=<0..7>
+// [-DDDPB_PRISMATIC=1] (variant.cuh; the pendulum, NJ = 0, has no prismatic variant).
 #ifndef DDPB_NJ
 #error "compile with -DDDPB_NJ=<n>"
 #endif
@@ -10,7 +11,7 @@
 #include "linearize_pt.cuh"
 #include "outer_warp.cuh"
 
-namespace ddpb {
+DDPB_VARIANT_BEGIN
 
 constexpr int KNJ = DDPB_NJ;
 
@@ -145,7 +146,11 @@ template <int NJ> __global__ void optimality_kernel(const __grid_constant__ Batc
 constexpr int TPP = 32;  // threads per block of the thread-per-problem kernels
 static size_t scr_bytes(int threads) { return (size_t)DynOps<KNJ>::SCR * threads * sizeof(double); }
 
-template <> size_t Launch<KNJ>::lin_smem_bytes(int hess_mode, int ne_max, int eq_kind) {
+DDPB_VARIANT_END
+
+namespace ddpb {
+
+template <> size_t Launch<KNJ, HAS_PRISMATIC>::lin_smem_bytes(int hess_mode, int ne_max, int eq_kind) {
 #if DDPB_NJ > 0
   LinPlan<KNJ> pl;
   pl.init(hess_mode, ne_max, ne_max, eq_kind);
@@ -155,7 +160,7 @@ template <> size_t Launch<KNJ>::lin_smem_bytes(int hess_mode, int ne_max, int eq
   return 0;
 #endif
 }
-template <> size_t Launch<KNJ>::bwd_smem_bytes(int hess_mode) {
+template <> size_t Launch<KNJ, HAS_PRISMATIC>::bwd_smem_bytes(int hess_mode) {
 #if DDPB_NJ > 2
   return (size_t)BwdSmem<KNJ>::size_for(BwdGeom<KNJ>::BT, hess_mode == HESS_FD_VALUES) * sizeof(double);
 #elif DDPB_NJ > 0
@@ -165,7 +170,7 @@ template <> size_t Launch<KNJ>::bwd_smem_bytes(int hess_mode) {
   return 0;
 #endif
 }
-template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
+template <> cudaError_t Launch<KNJ, HAS_PRISMATIC>::prepare(size_t lin_smem) {
   {
     cudaError_t e = cudaFuncSetAttribute(ls_trials_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(32 * LsGeom<KNJ>::WPB));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(cost_old_kernel<KNJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scr_bytes(TPP));
@@ -190,7 +195,7 @@ template <> cudaError_t Launch<KNJ>::prepare(size_t lin_smem) {
   return cudaSuccess;
 #endif
 }
-template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, int threads, int kpb, int t0, int t1, int ne_sm, cudaStream_t s) {
+template <> void Launch<KNJ, HAS_PRISMATIC>::linearize(const ModelDev& m, const BatchDev& bd, int threads, int kpb, int t0, int t1, int ne_sm, cudaStream_t s) {
 #if DDPB_NJ > 0
   const size_t smem = lin_smem_bytes(bd.hess_mode, ne_sm, bd.eq_kind) * kpb;
   const int groups = (bd.nb + kpb - 1) / kpb;
@@ -203,7 +208,7 @@ template <> void Launch<KNJ>::linearize(const ModelDev& m, const BatchDev& bd, i
   linearize_kernel<KNJ><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(m, bd, t0, t1);
 #endif
 }
-template <> bool Launch<KNJ>::linearize_pt(const ModelDev& m, const BatchDev& bd, int t0, int t1, cudaStream_t s) {
+template <> bool Launch<KNJ, HAS_PRISMATIC>::linearize_pt(const ModelDev& m, const BatchDev& bd, int t0, int t1, cudaStream_t s) {
 #if DDPB_NJ > 0 && DDPB_NJ <= 2
   if (bd.hess_mode != HESS_FD_JACOBIANS) return false;
   const long long knots = (long long)(t1 - t0) * bd.nb;
@@ -215,7 +220,7 @@ template <> bool Launch<KNJ>::linearize_pt(const ModelDev& m, const BatchDev& bd
   return false;
 #endif
 }
-template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
+template <> void Launch<KNJ, HAS_PRISMATIC>::backward(const BatchDev& bd, int threads, size_t smem, cudaStream_t s) {
 #if DDPB_NJ > 0
   {
     const size_t ne_ = (size_t)bd.T * bd.nx * bd.nb;
@@ -239,11 +244,11 @@ template <> void Launch<KNJ>::backward(const BatchDev& bd, int threads, size_t s
   (void)bd; (void)threads; (void)smem; (void)s;
 #endif
 }
-template <> void Launch<KNJ>::cost_old(const ModelDev& m, const BatchDev& bd, double* costs_old, cudaStream_t s) {
+template <> void Launch<KNJ, HAS_PRISMATIC>::cost_old(const ModelDev& m, const BatchDev& bd, double* costs_old, cudaStream_t s) {
   const size_t nkb = (size_t)bd.nb * (bd.T + 1);
   cost_old_kernel<KNJ><<<(unsigned)((nkb + TPP - 1) / TPP), TPP, scr_bytes(TPP), s>>>(m, bd, costs_old);
 }
-template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, double* ls_res, int* ls_win,
+template <> void Launch<KNJ, HAS_PRISMATIC>::forward(const ModelDev& m, const BatchDev& bd, double* costs_old, double* xs_c, double* us_c, double* ls_res, int* ls_win,
                                       const int* wide, int* wide_next, cudaStream_t s) {
   using G = LsGeom<KNJ>;
   const unsigned pb = (unsigned)((bd.nb + 31) / 32), sb = (unsigned)(((size_t)bd.nb * 32 + 127) / 128);
@@ -258,14 +263,14 @@ template <> void Launch<KNJ>::forward(const ModelDev& m, const BatchDev& bd, dou
       m, bd, costs_old, xs_c, us_c, ls_res, ls_win, wide, G::NC1, LS_MAX_TRIALS);
   ls_select_kernel<KNJ><<<sb, 128, 0, s>>>(bd, xs_c, us_c, ls_res, ls_win, wide, wide_next, G::NC1, LS_MAX_TRIALS, 1);
 }
-template <> int Launch<KNJ>::linesearch_slots() { return ls_slots<KNJ>(); }
-template <> void Launch<KNJ>::rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s) {
+template <> int Launch<KNJ, HAS_PRISMATIC>::linesearch_slots() { return ls_slots<KNJ>(); }
+template <> void Launch<KNJ, HAS_PRISMATIC>::rollout(const ModelDev& m, const BatchDev& bd, cudaStream_t s) {
   rollout_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd);
 }
-template <> void Launch<KNJ>::cost(const ModelDev& m, const BatchDev& bd, double* costs, cudaStream_t s) {
+template <> void Launch<KNJ, HAS_PRISMATIC>::cost(const ModelDev& m, const BatchDev& bd, double* costs, cudaStream_t s) {
   cost_kernel<KNJ><<<(bd.nb + TPP - 1) / TPP, TPP, scr_bytes(TPP), s>>>(m, bd, costs);
 }
-template <> void Launch<KNJ>::al_update(const BatchDev& bd, double thr, cudaStream_t s) {
+template <> void Launch<KNJ, HAS_PRISMATIC>::al_update(const BatchDev& bd, double thr, cudaStream_t s) {
   const size_t nkb = (size_t)bd.nb * bd.T;
   const unsigned wblocks = (unsigned)(((size_t)bd.nb * AdjGeom<KNJ>::G + 127) / 128);
   origin_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd, thr > 0.0 ? 1 : 0);
@@ -273,7 +278,7 @@ template <> void Launch<KNJ>::al_update(const BatchDev& bd, double thr, cudaStre
   mult_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 1);
 }
-template <> void Launch<KNJ>::optimality(const BatchDev& bd, cudaStream_t s) {
+template <> void Launch<KNJ, HAS_PRISMATIC>::optimality(const BatchDev& bd, cudaStream_t s) {
   optimality_kernel<KNJ><<<(unsigned)(((size_t)bd.nb * AdjGeom<KNJ>::G + 127) / 128), 128, 0, s>>>(bd);
 }
 

@@ -1,5 +1,6 @@
-// launch.cuh -- per-model-size kernel launchers.  Each instantiation Launch<NJ> lives in its own
-// translation unit (kernels_nj.cu compiled with -DDDPB_NJ=<n>) so the build parallelises.
+// launch.cuh -- per-model-size kernel launchers.  Each instantiation Launch<NJ, PR> lives in its own
+// translation unit (kernels_nj.cu compiled with -DDDPB_NJ=<n> -DDDPB_PRISMATIC=<0|1>, variant.cuh) so the build
+// parallelises.  PR = false: every joint revolute; PR = true: the device code with the joint-type tests.
 // NJ = 0 is the analytic pendulum (thread-per-problem kernels only; its backward pass is Launch<1>'s).
 #pragma once
 #include <cuda_runtime.h>
@@ -8,7 +9,7 @@
 
 namespace ddpb {
 
-template <int NJ> struct Launch {
+template <int NJ, bool PR = false> struct Launch {
   static size_t lin_smem_bytes(int hess_mode, int ne_max, int eq_kind);
   static size_t bwd_smem_bytes(int hess_mode);
   static cudaError_t prepare(size_t lin_smem);

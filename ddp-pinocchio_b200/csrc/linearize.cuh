@@ -24,7 +24,7 @@
 #define DDPB_FUSE_PROD 1    // M^-1 products inside the column tasks where M^-1 is ready by then
 #endif
 
-namespace ddpb {
+DDPB_VARIANT_BEGIN
 
 DDPB_HD int pair_rank(int i, int j, int N) { return i * N - (i * (i + 1)) / 2 + (j - i - 1); }
 DDPB_HD void pair_unrank(int r, int N, int* i, int* j) {
@@ -177,8 +177,10 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       double* dst = QR(kk, s) + Q::SCR + QScratch<NJ>::RL + 12 * jn;
   #pragma unroll
       for (int k = 0; k < 9; ++k) dst[k] = Rl[k];
+      if (HAS_PRISMATIC) {
   #pragma unroll
-      for (int k = 0; k < 3; ++k) dst[9 + k] = plc[k];
+        for (int k = 0; k < 3; ++k) dst[9 + k] = plc[k];
+      }
     }
     ex.sync();
     DDPB_PHASE_MARK(bd, 8, pc_);
@@ -747,4 +749,4 @@ DDPB_HD void linearize_pendulum(const ModelDev& m, const BatchDev& bd, int b, in
   }
 }
 
-}  // namespace ddpb
+DDPB_VARIANT_END

@@ -16,7 +16,7 @@
 #pragma once
 #include "batch.cuh"
 
-namespace ddpb {
+DDPB_VARIANT_BEGIN
 
 template <int NJ> struct PtGeom {
   static constexpr int n = NJ, nd = 2 * NJ, nu = NJ, nx = 2 * NJ;
@@ -193,4 +193,4 @@ template <int NJ> __device__ __forceinline__ void linearize_pt_warp(const ModelD
 }
 #endif
 
-}  // namespace ddpb
+DDPB_VARIANT_END

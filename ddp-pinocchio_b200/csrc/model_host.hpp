@@ -38,6 +38,8 @@ inline int model_from_desc(const ddpb_model_desc* d, ModelDev& M, std::string& e
     const int jt = d->joint_type ? d->joint_type[i] : DDPB_JOINT_REVOLUTE;
     if (jt != DDPB_JOINT_REVOLUTE && jt != DDPB_JOINT_PRISMATIC) { err = "joint types must be revolute (0) or prismatic (1)"; return DDPB_ERR_UNSUPPORTED; }
     M.jtype[i] = jt;
+    if (jt != DDPB_JOINT_REVOLUTE) M.any_prismatic = 1;
+    if (jt != DDPB_JOINT_REVOLUTE) M.any_prismatic = 1;
     const double ms = d->mass[i];
     const double* c = d->com + 3 * i;
     const double* I = d->inertia + 6 * i;

@@ -12,7 +12,7 @@
 #if defined(__CUDACC__)
 #include "forward.cuh"
 
-namespace ddpb {
+DDPB_VARIANT_BEGIN
 
 // fb_all = false: the feedback sequence is re-centred only at knots with equality rows.  Its re-centred k is read once,
 // by the multiplier update at such knots (ddp.hpp:686-687); at every other knot k, K and the origin are overwritten by
@@ -320,5 +320,5 @@ __device__ __forceinline__ void ls_select_warp(const BatchDev& bd, const double*
   }
 }
 
-}  // namespace ddpb
+DDPB_VARIANT_END
 #endif

@@ -20,6 +20,8 @@
 #pragma once
 #include <math.h>
 
+#include "variant.cuh"
+
 #if defined(__CUDACC__)
 #define DDPB_HD __host__ __device__ __forceinline__
 #else
@@ -33,7 +35,8 @@ constexpr int MAXF = 16;
 constexpr int MAXE = 7;
 
 struct ModelDev {
-  int kind, n, nframes, pad_;
+  int kind, n, nframes;
+  int any_prismatic;    // some jtype[i] != 0 (host: picks the kernels of the HAS_PRISMATIC variant)
   double pend_m, pend_l;
   double grav[3];
   double Rp[MAXJ][9];
@@ -46,9 +49,14 @@ struct ModelDev {
   double fp[MAXF][3];
   // joint types (what pinocchio::urdf::buildModel makes of URDF revolute / prismatic joints): 0 = revolute about `axis`,
   // 1 = prismatic along it.  Only the q-dependent placement (joint_local_*) and the motion subspace S_i (body_world,
-  // frame_task) depend on the type; everything downstream is written on S_i and holds for both.
+  // frame_task) depend on the type; everything downstream is written on S_i and holds for both.  The tests on jtype are
+  // compiled only into the HAS_PRISMATIC variant of the device code (variant.cuh); any_prismatic selects that variant.
   int jtype[MAXJ + 1];
 };
+
+}  // namespace ddpb
+
+DDPB_VARIANT_BEGIN
 
 // ---- small vector helpers -------------------------------------------------------------------
 DDPB_HD void cross3(const double* a, const double* b, double* o) {
@@ -106,7 +114,7 @@ DDPB_HD void sincos_(double q, double* s, double* c) {
 // E_i(q) = (Rp_i * R_axis(q))^T, row-major (used by frame_task only: frame positions follow the body-frame recursion
 // of the reference's forward kinematics)
 DDPB_HD void joint_E(const ModelDev& m, int i, double q, double* E) {
-  if (m.jtype[i] != 0) {  // prismatic: no rotation, E = Rp^T
+  if (HAS_PRISMATIC && m.jtype[i] != 0) {  // prismatic: no rotation, E = Rp^T
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -187,7 +195,7 @@ template <int NJ> struct VRec {
 
 // local rotation of joint i:  Rl = Rp_i Rot(axis_i, q_i)   (row-major 3x3)
 DDPB_HD void joint_local_rot(const ModelDev& m, int i, double q, double* Rl) {
-  if (m.jtype[i] != 0) {  // prismatic: Rl = Rp_i
+  if (HAS_PRISMATIC && m.jtype[i] != 0) {  // prismatic: Rl = Rp_i
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rl[k] = m.Rp[i][k];
     return;
@@ -208,7 +216,7 @@ DDPB_HD void joint_local_rot(const ModelDev& m, int i, double q, double* Rl) {
 // origin of joint frame i in parent coordinates:  pl = pp_i (revolute) ,  pp_i + Rp_i (axis_i q) (prismatic)
 DDPB_HD void joint_local_trans(const ModelDev& m, int i, double q, double* pl) {
   pl[0] = m.pp[i][0]; pl[1] = m.pp[i][1]; pl[2] = m.pp[i][2];
-  if (m.jtype[i] != 0) {
+  if (HAS_PRISMATIC && m.jtype[i] != 0) {
     const double d[3] = {m.axis[i][0] * q, m.axis[i][1] * q, m.axis[i][2] * q};
     double t[3];
     m3v(m.Rp[i], d, t);
@@ -241,7 +249,7 @@ DDPB_HD void joint_advance(const ModelDev& m, int i, double q, double* R, double
 DDPB_HD void body_world(const ModelDev& m, int i, const double* R, const double* p, double* S, double* Y) {
   double w[3], mo[3];
   m3v(R, m.axis[i], w);
-  if (m.jtype[i] != 0) {
+  if (HAS_PRISMATIC && m.jtype[i] != 0) {
     S[0] = 0.0; S[1] = 0.0; S[2] = 0.0; S[3] = w[0]; S[4] = w[1]; S[5] = w[2];
   } else {
     cross3(p, w, mo);
@@ -297,7 +305,7 @@ template <int NJ> DDPB_HD void q_chain(const ModelDev& m, double* rec) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rl[k] = rec[Q::SCR + X::RL + 12 * i + k];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) pl[k] = rec[Q::SCR + X::RL + 12 * i + 9 + k];
+    for (int k = 0; k < 3; ++k) pl[k] = HAS_PRISMATIC ? rec[Q::SCR + X::RL + 12 * i + 9 + k] : m.pp[i][k];  // (constant when every joint is revolute)
     joint_compose(pl, Rl, R, p);
 #pragma unroll
     for (int k = 0; k < 9; ++k) rec[Q::SCR + X::RP + 12 * i + k] = R[k];
@@ -866,7 +874,7 @@ template <int NJ> DDPB_HD void frame_task(const ModelDev& m, const double* q, in
     for (int i = 0; i < NJ; ++i) {
       double lin[3] = {0, 0, 0};
       if (i <= jf) {
-        if (m.jtype[i] != 0) {  // prismatic: the linear part of [0 ; w_i], the same in both conventions
+        if (HAS_PRISMATIC && m.jtype[i] != 0) {  // prismatic: the linear part of [0 ; w_i], the same in both conventions
           lin[0] = w[i][0]; lin[1] = w[i][1]; lin[2] = w[i][2];
         } else if (mode == 0) {
           cross3(pj[i], w[i], lin);
@@ -884,4 +892,4 @@ template <int NJ> DDPB_HD void frame_task(const ModelDev& m, const double* q, in
 DDPB_HD double pend_acc(const ModelDev& m, double q, double tau) { return -9.81 / m.pend_l * sin(q) + tau / m.pend_m; }
 DDPB_HD double pend_dacc_dq(const ModelDev& m, double q) { return -9.81 / m.pend_l * cos(q); }
 
-}  // namespace ddpb
+DDPB_VARIANT_END

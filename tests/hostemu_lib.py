@@ -24,7 +24,7 @@ def build(force=False):
     csrc = os.path.join(ddpb_loader.PKG_DIR, "csrc")
     deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".hpp"))]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-march=x86-64-v3", "-std=c++17", "-fPIC", "-shared", "-x", "c++", SRC, "-o", LIB])
+        subprocess.check_call(["g++", "-O2", "-march=x86-64-v3", "-std=c++17", "-fPIC", "-shared", "-DDDPB_PRISMATIC=1", "-x", "c++", SRC, "-o", LIB])  # the variant with the joint-type tests (csrc/variant.cuh) serves every model
 
 
 def lib():

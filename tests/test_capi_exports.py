@@ -67,9 +67,10 @@ def test_backward_kernel_uses_tma_bulk_copies():
     if not os.path.exists(exe):
         pytest.skip("cuobjdump not available")
     lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ddp-pinocchio_b200", "libddpb.so")
-    for fun in ("_ZN4ddpb15backward_kernelILi6ELb0EEEvNS_8BatchDevE", "_ZN4ddpb15backward_kernelILi7ELb1EEEvNS_8BatchDevE"):
+    # (kin_r: the all-revolute variant of the device code, csrc/variant.cuh)
+    for fun in ("_ZN4ddpb5kin_r15backward_kernelILi6ELb0EEEvNS_8BatchDevE", "_ZN4ddpb5kin_r15backward_kernelILi7ELb1EEEvNS_8BatchDevE"):
         sass = subprocess.run([exe, "-sass", "-fun", fun, lib], capture_output=True, text=True).stdout
         assert "UBLKCP.S.G" in sass and "SYNCS.PHASECHK" in sass, fun
     # the lane-group kernel of the short chains streams its records with 16-byte cp.async (LDGSTS) and works in registers / shuffles
-    sass = subprocess.run([exe, "-sass", "-fun", "_ZN4ddpb18backward_lg_kernelILi2ELb0EEEvNS_8BatchDevE", lib], capture_output=True, text=True).stdout
+    sass = subprocess.run([exe, "-sass", "-fun", "_ZN4ddpb5kin_r18backward_lg_kernelILi2ELb0EEEvNS_8BatchDevE", lib], capture_output=True, text=True).stdout
     assert "LDGSTS" in sass and "SHFL.IDX" in sass and "DFMA" in sass
