@@ -136,8 +136,13 @@ DDPB_HD RecView rec_view(const BatchDev& bd, int t, int b, int rec_size) { retur
 
 // ---- execution context: the same CTA body runs on the device (threads of one block) and, for the
 // CPU unit tests of tests/hostemu, as a plain sequential loop over the tasks of every phase -------
-// development aid: accumulate the cycles thread 0 of a CTA spent since *t0 into bd.dbg[slot]
-#if defined(__CUDA_ARCH__)
+// development aid: accumulate the cycles thread 0 of a CTA spent since *t0 into bd.dbg[slot].  Compiled in only with
+// -DDDPB_PHASE_CYCLES=1 (tools/phase_cycles.py builds such a library): the ~30 guarded clock reads of the linearization and
+// backward kernels were measured to cost the product 2 % of a C3 solve although never taken (instruction fetch, see variant.cuh).
+#ifndef DDPB_PHASE_CYCLES
+#define DDPB_PHASE_CYCLES 0
+#endif
+#if defined(__CUDA_ARCH__) && DDPB_PHASE_CYCLES
 #define DDPB_PHASE_MARK(bd, slot, t0)                                                            \
   do {                                                                                           \
     if ((bd).dbg && threadIdx.x == 0) {                                                          \

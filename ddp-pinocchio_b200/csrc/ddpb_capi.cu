@@ -881,6 +881,7 @@ int ddpb_debug_timeline(ddpb_batch* h, float* out3, int max_entries) {
 // development aid (not declared in ddpb.h): per-phase cycle counters of the linearization kernel
 int ddpb_debug_phase_cycles(ddpb_batch* h, int enable, unsigned long long* out16) {
   ENTER(h);
+  if (!DDPB_PHASE_CYCLES) return fail(DDPB_ERR_UNSUPPORTED, "the per-phase cycle counters are compiled out: build with DDPB_NVCC_EXTRA=-DDDPB_PHASE_CYCLES=1");
   if (enable && !h->bd.dbg) {
     int rc = dev_alloc(h, &h->bd.dbg, 16);
     if (rc) return rc;

@@ -1,4 +1,5 @@
-"""Per-phase cycle breakdown of the backward kernel (development aid; uses the undeclared debug entry point)."""
+"""Per-phase cycle breakdown of the backward kernel (development aid; uses the undeclared debug entry point).
+Needs a library built with the counters: DDPB_NVCC_EXTRA=-DDDPB_PHASE_CYCLES=1 python -c "import __graft_entry__ as g; g.build_cuda(force=True)"."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
