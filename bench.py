@@ -366,9 +366,12 @@ def main():
                          "note": "algorithmic bytes per launch (BASELINE.md s3 / SURVEY 8d, counted on the reference's dense "
                                  "derivative_storage_t: 8*(slab+nx+nu) per knot written by the linearization, 8*(slab+2nx+nu+nu*ndx+eq) read "
                                  "by the backward pass) / mean CUDA-event launch duration; the kernels move only the state-dependent "
-                                 "entries (csrc/batch.cuh), so traffic (ncu dram bytes per knot, profiles/r02_kernel_counts.json, x knots "
-                                 "per launch) is BELOW the algorithmic bytes and achieved_stored_records is the rate on the bytes "
-                                 "actually stored"},
+                                 "entries (csrc/batch.cuh) and achieved_stored_records is the rate on the bytes actually stored; traffic "
+                                 "(ncu dram bytes per knot, profiles/r02_kernel_counts.json, x knots per launch) is " +
+                                 ("BELOW the algorithmic bytes for that reason" if not traffic or traffic * B * T <= rk["alg_bytes"] else
+                                  "%.2fx the algorithmic bytes: the value-based mode stores dense tensors and its kernel (255 registers) spills "
+                                  "to local memory, whose lines are evicted from L2 by the streamed records (DESIGN.md 4.1)"
+                                  % (traffic * B * T / rk["alg_bytes"]))},
             "roofline_fp64": ({"kernel": "linearize", "bound": "fp64", "achieved": kout["linearize"]["fp64_tflops"], "peak": fp64_peak, "unit": "TFLOP/s",
                                "frac": kout["linearize"]["fp64_frac_of_measured_peak"],
                                "note": "executed FP64 flops per knot (ncu, profiles/r02_kernel_counts.json: 2*dfma + dadd + dmul) x knots per "

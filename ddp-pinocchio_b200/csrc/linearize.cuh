@@ -42,9 +42,21 @@ template <int NJ> struct LinPlan {
   // Shared memory of a CTA that owns kpb knots: [kpb][NQ] q-records | [kpb][NT] v-records | [kpb] everything else.  The
   // two record arrays are region-major with one odd stride each, so the tasks of a phase (consecutive threads ->
   // consecutive records, whatever knot they belong to) hit different banks.
-  int o_base, o_tgt, o_fval, o_eqv, o_J, o_eqxu, o_cterm, o_dg, o_minv0, q_sz, v_sz, rest, total;
+  int o_base, o_tgt, o_fval, o_eqv, o_J, o_eqxu, o_cterm, o_dg, o_minv0, o_qdd, q_sz, v_sz, rest, total;
+  // value-based mode: the evaluation points whose perturbation touches no control index (the only ones that run the
+  // articulated-body sweeps, see "torque-affine points" in linearize_group), ND = 2 NJ tangent indices of the state
+  static constexpr int ND = 2 * NJ;
+  static constexpr int PA = 1 + ND + ND * (ND - 1) / 2;
+  DDPB_HD static int aba_point(int a, int* i, int* j) {  // a-th such point -> its index among all P points, its perturbation
+    *i = -1; *j = -1;
+    if (a == 0) return 0;
+    if (a <= ND) { *i = a - 1; return a; }
+    pair_unrank(a - 1 - ND, ND, i, j);  // (state tangent indices are the same numbers in both enumerations)
+    return 1 + N + pair_rank(*i, *j, N);
+  }
   // stride of the q-records (M^-1 aliases the articulated inertias inside a record; the value-based mode needs M^-1 of
-  // the base configuration only, while its value-only points still read IA, so that one M^-1 lives in its own slot)
+  // the base and the singly perturbed configurations only, while its value-only points still read IA, so those live in
+  // their own slots, o_minv0)
   DDPB_HD static int qstride(int) { return QRec<NJ>::SIZE; }
   DDPB_HD static int points(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + N : 1 + N + N * (N - 1) / 2; }
   DDPB_HD static int qsets(int mode) { return mode == HESS_FD_JACOBIANS ? 1 + NJ : 1 + NJ + NJ * (NJ - 1) / 2; }
@@ -70,7 +82,8 @@ template <int NJ> struct LinPlan {
     // value-based mode only: per-body column terms of the base point, diagonal second differences of f and eq
     o_cterm = o; o += mode == HESS_FD_VALUES ? 2 * NJ * NJ * 6 : 0;
     o_dg = o; o += mode == HESS_FD_VALUES ? 2 * N * (2 * NJ + ne_max) : 0;  // second differences | Jacobian entries
-    o_minv0 = o; o += mode == HESS_FD_VALUES ? NJ * NJ : 0;
+    o_minv0 = o; o += mode == HESS_FD_VALUES ? (1 + NJ) * NJ * NJ : 0;  // M^-1 of the base configuration and of the NJ singly perturbed ones
+    o_qdd = o; o += mode == HESS_FD_VALUES ? (1 + ND) * NJ : 0;          // accelerations at the base point and the ND state-perturbed single points
     rest = o;
     total = q_sz + v_sz + rest;
   }
@@ -81,12 +94,15 @@ template <int NJ> struct LinPlan {
     if (p <= N) { *i = p - 1; return; }
     pair_unrank(p - 1 - N, N, i, j);
   }
-  DDPB_HD int point_qset(int p) const {
-    int i, j;
-    point_pert(p, &i, &j);
+  DDPB_HD static int pert_qset(int i, int j) {  // configuration of the point that perturbs tangent indices i < j (-1 = none)
     if (i < 0 || i >= NJ) return 0;          // i < j, so j >= NJ as well
     if (j < 0 || j >= NJ) return 1 + i;
     return 1 + NJ + pair_rank(i, j, NJ);
+  }
+  DDPB_HD int point_qset(int p) const {
+    int i, j;
+    point_pert(p, &i, &j);
+    return pert_qset(i, j);
   }
   DDPB_HD void qset_pert(int s, int* i, int* j) const {
     *i = -1; *j = -1;
@@ -135,16 +151,19 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   DDPB_PHASE_MARK(bd, 0, pc_);
 
   // state of evaluation point p of knot kk: the base (x, u) with its tangent perturbation(s)
-  auto point_state = [&](int kk, int p, double* q, double* qd, double* tau) {
+  auto pert_state = [&](int kk, int i, int j, double* q, double* qd, double* tau) {
     const double* base = SM(kk, pl.o_base);
-    int i, j;
-    pl.point_pert(p, &i, &j);
 #pragma unroll
     for (int k = 0; k < NJ; ++k) {
       q[k] = base[k] + ((k == i || k == j) ? eps : 0.0);
       qd[k] = base[n + k] + ((n + k == i || n + k == j) ? eps : 0.0);
       tau[k] = base[2 * n + k] + ((2 * n + k == i || 2 * n + k == j) ? eps : 0.0);
     }
+  };
+  auto point_state = [&](int kk, int p, double* q, double* qd, double* tau) {
+    int i, j;
+    pl.point_pert(p, &i, &j);
+    pert_state(kk, i, j, q, qd, tau);
   };
   // Short tasks (<= 3 joints) run each narrow phase as one task per configuration / point; longer chains split them
   // into parallel and serial sub-phases (more barriers, much shorter serial parts).
@@ -215,6 +234,19 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   // phase 2: accelerations (and body data where derivative columns are needed) at every evaluation point.  Points with
   // a record (all of them in FD-of-Jacobians mode, the base point otherwise) run as sub-phases (rbd.cuh "v_task as
   // sub-phases"); value-only points run the whole of v_task<false> in the serial sub-phase.
+  // value-based mode: M^-1 of the base configuration and of the NJ singly perturbed ones (S, U, 1/D only; what the
+  // torque-affine points below need), threads taken from the top of the CTA
+  auto minv_value_tasks = [&]() {
+    for (int idx = nthr - 1 - tid; idx < nk * (1 + NJ) * NJ; idx += nthr) {
+      const int kk = idx / ((1 + NJ) * NJ), r2 = idx - kk * (1 + NJ) * NJ;
+      const int c = r2 % NJ, s = r2 / NJ;
+      double col[NJ];
+      minv_col<NJ>(QR(kk, s), c, col);
+      double* mi = SM(kk, pl.o_minv0) + (size_t)s * NJ * NJ + c * NJ;
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) mi[k] = col[k];
+    }
+  };
   if (SPLIT) {
     for (int idx = tid; idx < nk * pl.NT * NJ; idx += nthr) {
       const int jn = idx / (nk * pl.NT), r = idx - jn * (nk * pl.NT), kk = r / pl.NT, p = r - kk * pl.NT;
@@ -223,15 +255,30 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const double qdj = SM(kk, pl.o_base)[n + jn] + ((n + jn == i || n + jn == j) ? eps : 0.0);
       v_bias<NJ>(QR(kk, pl.point_qset(p)), jn, qdj, VR(kk, p));
     }
+    // (value-based mode: this phase has NJ bias tasks per knot; the M^-1 columns fill it instead of lengthening the sweeps)
+    if (MODE == HESS_FD_VALUES) minv_value_tasks();
     ex.sync();
     DDPB_PHASE_MARK(bd, 12, pc_);
   }
-  for (int idx = tid; idx < nk * pl.P; idx += nthr) {
-    const int kk = idx / pl.P, p = idx - kk * pl.P;
+  // Torque-affine points (value-based mode).  The forward dynamics is affine in the torque for fixed (q, v):
+  // qdd(q, v, tau + d) = qdd(q, v, tau) + M^-1(q) d.  More than half of the reference's stencil (problem.hpp:192-296:
+  // 3 NJ single and 3 NJ (3 NJ - 1) / 2 pair perturbations) touches a control index; those points are not run through the
+  // articulated-body sweeps again but derived from the point that has the same state perturbation (the base point or a
+  // single state-perturbed point) and the M^-1 columns of its configuration -- the same evaluation points, the same
+  // values up to rounding, PA = 1 + 2 NJ + NJ (2 NJ - 1) sweeps per knot instead of P (7R arm: 106 instead of 232, one
+  // round of a 128-thread CTA instead of two).
+  constexpr bool ULIN = MODE == HESS_FD_VALUES;
+  constexpr int PA = LinPlan<NJ>::PA;
+  const int n_eval = ULIN ? PA : pl.P;
+  for (int idx = tid; idx < nk * n_eval; idx += nthr) {
+    const int kk = idx / n_eval, a = idx - kk * n_eval;
+    int pi, pj, p = a;  // the point and the tangent indices it perturbs (decoded once)
+    if (ULIN) p = LinPlan<NJ>::aba_point(a, &pi, &pj);
+    else pl.point_pert(p, &pi, &pj);
     double* fval = SM(kk, pl.o_fval);
     double q[NJ], qd[NJ], tau[NJ], qdd[NJ];
-    point_state(kk, p, q, qd, tau);
-    const double* qr = QR(kk, pl.point_qset(p));
+    pert_state(kk, pi, pj, q, qd, tau);
+    const double* qr = QR(kk, LinPlan<NJ>::pert_qset(pi, pj));
     if (MODE == HESS_FD_JACOBIANS || p < pl.NT) {  // every point has a record in FD-of-Jacobians mode (NT == P)
       if (SPLIT) v_sweeps<NJ>(m, qr, tau, qdd, VR(kk, p));
       else v_task<NJ, true>(m, qr, qd, tau, qdd, VR(kk, p));
@@ -245,7 +292,37 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       fval[p * nx + k] = q[k] + vo;
       fval[p * nx + n + k] = qd[k] + qdd[k] * dt;
     }
+    if (ULIN && p <= nd) {  // the base point and the single state perturbations are what the control-perturbed points start from
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) SM(kk, pl.o_qdd)[p * NJ + k] = qdd[k];
+    }
   }
+  if (ULIN && !SPLIT) minv_value_tasks();  // short chains: beside the sweeps, from the top of the CTA
+  // the control-perturbed points of knot kk: d enumerates NJ singles u_j, 2 NJ * NJ pairs (x_i, u_j), NJ (NJ - 1) / 2 pairs (u_i, u_j)
+  auto derived_task = [&](int r) {
+    constexpr int NDER = NJ + nd * NJ + NJ * (NJ - 1) / 2;
+    const int kk = r / NDER, d = r - kk * NDER;
+    int i, j;
+    if (d < NJ) { i = -1; j = nd + d; }
+    else if (d < NJ + nd * NJ) { const int d2 = d - NJ; i = d2 / NJ; j = nd + (d2 - i * NJ); }
+    else { pair_unrank(d - NJ - nd * NJ, NJ, &i, &j); i += nd; j += nd; }
+    const int p = i < 0 ? 1 + j : 1 + N + pair_rank(i, j, N);
+    const int src = (i < 0 || i >= nd) ? 0 : 1 + i;        // the point with the same state perturbation
+    const int s = (i >= 0 && i < NJ) ? 1 + i : 0;          // its configuration
+    const double* Mi = SM(kk, pl.o_minv0) + (size_t)s * NJ * NJ;
+    const double* qdd0 = SM(kk, pl.o_qdd) + src * NJ;
+    const double* base = SM(kk, pl.o_base);
+    double* fval = SM(kk, pl.o_fval);
+#pragma unroll
+    for (int k = 0; k < NJ; ++k) {
+      double qdd = qdd0[k] + eps * Mi[(j - nd) * NJ + k];
+      if (i >= nd) qdd += eps * Mi[(i - nd) * NJ + k];
+      const double qdk = base[n + k] + (n + k == i ? eps : 0.0);
+      fval[p * nx + k] = fval[src * nx + k];
+      fval[p * nx + n + k] = qdk + qdd * dt;
+    }
+  };
+  constexpr int NDER = NJ + nd * NJ + NJ * (NJ - 1) / 2;
   // M^-1 columns need S, U and 1/D of their configuration only, and their destination (aliased onto the articulated
   // inertias, QRec::MINV) has had its last reader in v_bias: in split FD-of-Jacobians mode they run here, on the threads
   // the serial sweeps above leave idle (taken from the top of the CTA), instead of lengthening the column phase.
@@ -269,6 +346,8 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const int jn = idx / (nk * pl.NT), r = idx - jn * (nk * pl.NT), kk = r / pl.NT, p = r - kk * pl.NT;
       v_force<NJ>(QR(kk, pl.point_qset(p)), jn, VR(kk, p));
     }
+    if (ULIN)  // beside the (few) force tasks of the base point, from the top of the CTA
+      for (int idx = nthr - 1 - tid; idx < nk * NDER; idx += nthr) derived_task(idx);
     ex.sync();
     DDPB_PHASE_MARK(bd, 14, pc_);
     // (folding these suffix sums into the column tasks was measured slower: 2.63 -> 2.74 ms on C3)
@@ -276,6 +355,9 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
       const int kk = idx / pl.NT, p = idx - kk * pl.NT;
       v_suffix<NJ>(VR(kk, p));
     }
+  } else if (ULIN) {
+    ex.sync();
+    for (int idx = tid; idx < nk * NDER; idx += nthr) derived_task(idx);
   }
   ex.sync();
   DDPB_PHASE_MARK(bd, 2, pc_);
@@ -284,25 +366,17 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
   if (MODE == HESS_FD_VALUES) {
     // only the base point needs columns: too few tasks to fill even one warp, so every column is split by body
     // (col_term, NJ * NJ slots per derivative kind of which k >= j are used) and reduced afterwards (col_reduce)
-    for (int idx = tid; idx < nk * (2 * NJ * NJ + NJ); idx += nthr) {
-      const int kk = idx / (2 * NJ * NJ + NJ), r = idx - kk * (2 * NJ * NJ + NJ);
+    // (M^-1 of the base configuration is already there: phase 2)
+    for (int idx = tid; idx < nk * 2 * NJ * NJ; idx += nthr) {
+      const int kk = idx / (2 * NJ * NJ), r = idx - kk * (2 * NJ * NJ);
       double* qr = QR(kk, 0);
-      if (r < 2 * NJ * NJ) {
-        const int wrt = r / (NJ * NJ), r2 = r - wrt * NJ * NJ, j = r2 / NJ, k = r2 - j * NJ;
-        if (k >= j) {
-          double g[6];
-          col_term<NJ>(qr, VR(kk, 0), j, k, wrt, g);
-          double* dst = SM(kk, pl.o_cterm) + (size_t)(wrt * NJ + j) * NJ * 6 + 6 * k;
+      const int wrt = r / (NJ * NJ), r2 = r - wrt * NJ * NJ, j = r2 / NJ, k = r2 - j * NJ;
+      if (k >= j) {
+        double g[6];
+        col_term<NJ>(qr, VR(kk, 0), j, k, wrt, g);
+        double* dst = SM(kk, pl.o_cterm) + (size_t)(wrt * NJ + j) * NJ * 6 + 6 * k;
 #pragma unroll
-          for (int e = 0; e < 6; ++e) dst[e] = g[e];
-        }
-      } else {
-        const int c = r - 2 * NJ * NJ;
-        double col[NJ];
-        minv_col<NJ>(qr, c, col);
-        double* mi = minv_of(kk, 0);
-#pragma unroll
-        for (int k = 0; k < NJ; ++k) mi[c * NJ + k] = col[k];
+        for (int e = 0; e < 6; ++e) dst[e] = g[e];
       }
     }
     ex.sync();
@@ -315,6 +389,8 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
 #pragma unroll
       for (int k = 0; k < NJ; ++k) dst[k] = col[k];
     }
+    // (the base point's suffix sums beside the column terms and the M^-1 products fused into this reduction -- two barriers
+    // fewer per knot -- measured no gain: 7R 18.70 -> 18.80 ms)
   } else {
 
     // short chains: one tangent task = both derivative kinds of column j at point p (col_task2 loads the body data
@@ -570,6 +646,9 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         const double* vals = which == 0 ? SM(kk, pl.o_fval) + k : SM(kk, pl.o_eqv) + k;
         const int vs = which == 0 ? nx : ne_sm;
         const double f0 = vals[0], ca = jc[ga * dgs], da = dg[ga * dgs];
+        // (measured slower on the 7R arm, 18.8 ms per pass as it is: a select-free form with tables pre-scaled by powers of
+        // two and the index pair by min / max +0.5 ms; 7 entries in flight instead of 4, 21.5 ms; one copy of this code looped
+        // over the six blocks instead of six inlined copies -- 11.7 k instead of 18.3 k instructions -- 21.0 ms)
 #pragma unroll 4
         for (int bl = 0; bl < LB; ++bl) {  // independent entries: unrolled so that their loads and stores overlap
           const int gb = b0_ + bl;
@@ -586,12 +665,14 @@ DDPB_HD void linearize_group(const ModelDev& m, const BatchDev& bd, int t, int b
         }
       });
     };
+    if (ne > 0) {
+      for_block(ne, [&](int kk, int e) { REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e]; });
+      for_block(ne * N, [&](int kk, int e) { REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e]; });
+    }
     fill(0, L.fxx, nd, 0, nd, 0, nd);
     fill(0, L.fux, nd, nd, nu, 0, nd);
     fill(0, L.fuu, nd, nd, nu, nd, nu);
     if (ne > 0) {
-      for_block(ne, [&](int kk, int e) { REC(kk, L.eq + e) = SM(kk, pl.o_eqv)[e]; });
-      for_block(ne * N, [&](int kk, int e) { REC(kk, L.eq_x + e) = SM(kk, pl.o_eqxu)[e]; });
       fill(1, L.eq_xx, ne, 0, nd, 0, nd);
       fill(1, L.eq_ux, ne, nd, nu, 0, nd);
       fill(1, L.eq_uu, ne, nd, nu, nd, nu);

@@ -83,7 +83,7 @@ def tob(v, u):
 
 def main():
     os.makedirs(P, exist_ok=True)
-    for wl, label in (("c2", "c2_chain2r_4096x200"), ("c3", "c3_arm6r_1024x100")):
+    for wl, label in (("c2", "c2_chain2r_4096x200"), ("c3", "c3_arm6r_1024x100"), ("c5", "c5_arm7r_fd_8192x200, 1024 problems per GPU")):
         reps = [os.path.join(G, f"r02_full_{wl}_{k}.ncu-rep") for k in ("linearize_pt_kernel", "linearize_kernel", "backward_lg_kernel", "backward_kernel", "ls_trials_kernel")]
         reps = [r for r in reps if os.path.exists(r)]
         if not reps:
