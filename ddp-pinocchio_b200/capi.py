@@ -23,7 +23,8 @@ EXPORTS = ["ddpb_model_create", "ddpb_model_destroy", "ddpb_batch_create", "ddpb
            "ddpb_cost_seq_aug", "ddpb_optimality", "ddpb_solve", "ddpb_solve_async", "ddpb_batch_dims", "ddpb_launch_count",
            "ddpb_phase_times", "ddpb_enable_phase_timing", "ddpb_snapshot_save", "ddpb_snapshot_restore",
            "ddpb_measure_fp64_peak", "ddpb_set_subbatches", "ddpb_model_create_from_urdf", "ddpb_model_dims", "ddpb_model_get",
-           "ddpb_model_frame_name", "ddpb_model_joint_types"]
+           "ddpb_model_frame_name", "ddpb_model_joint_types", "ddpb_model_dynamics_aba", "ddpb_model_d_dynamics_aba",
+           "ddpb_model_inverse_dynamics_rnea", "ddpb_model_frame_coordinates", "ddpb_model_d_frame_coordinates"]
 
 
 class DdpbError(RuntimeError):
@@ -147,6 +148,92 @@ class BatchBase:
         return dict(lfx=nd, lfxx=nd * nd, lx=T * nd, lu=T * nu, lxx=T * nd * nd, lux=T * nu * nd, luu=T * nu * nu, f_val=T * nx,
                     fx=T * nd * nd, fu=T * nd * nu, fxx=T * nd ** 3, fux=T * nd * nu * nd, fuu=T * nd * nu * nu, eq_val=ne,
                     eq_x=ne * nd, eq_u=ne * nu, eq_xx=ne * nd * nd, eq_ux=ne * nu * nd, eq_uu=ne * nu * nu)
+
+
+class ModelBase:
+    """The Model concept's own functions for n samples (pinocchio_model.hpp:147-185): shapes and argument checks shared by
+    the C-ABI binding below and the CPU emulation of the tests; subclasses provide _eval(**arrays)."""
+
+    def _init_model(self, model):
+        self.model = model
+        self.nq = 1 if model.kind == 0 else model.n_joints
+
+    def _arr(self, a):
+        a = np.ascontiguousarray(np.atleast_2d(np.asarray(a, dtype=np.float64)))
+        assert a.shape[1] == self.nq, "samples are rows of nq entries"
+        return a
+
+    def dynamics_aba(self, q, v, tau):
+        q, v, tau = self._arr(q), self._arr(v), self._arr(tau)
+        a = np.zeros_like(q)
+        self._eval(n=len(q), q=q, v=v, tau=tau, a=a)
+        return a
+
+    def d_dynamics_aba(self, q, v, tau):
+        """(da/dq, da/dv, da/dtau), each [n][nv][nv] with out[s][r][c] = d a_r / d x_c."""
+        q, v, tau = self._arr(q), self._arr(v), self._arr(tau)
+        n, nq = q.shape
+        o = [np.zeros((n, nq * nq)) for _ in range(3)]
+        self._eval(n=n, q=q, v=v, tau=tau, a_dq=o[0], a_dv=o[1], a_dtau=o[2])
+        return tuple(x.reshape(n, nq, nq).transpose(0, 2, 1).copy() for x in o)  # column-major per sample -> [r][c]
+
+    def inverse_dynamics_rnea(self, q, v, a):
+        q, v, a = self._arr(q), self._arr(v), self._arr(a)
+        tau = np.zeros_like(q)
+        self._eval(n=len(q), q=q, v=v, acc=a, tau_out=tau)
+        return tau
+
+    def frame_coordinates(self, frame, q):
+        q = self._arr(q)
+        p = np.zeros((len(q), 3))
+        self._eval(n=len(q), frame=frame, q=q, p3=p)
+        return p
+
+    def d_frame_coordinates(self, frame, q, jac_mode=0):
+        """[n][3][nv]"""
+        q = self._arr(q)
+        n, nq = q.shape
+        J = np.zeros((n, 3 * nq))
+        self._eval(n=n, frame=frame, jac_mode=jac_mode, q=q, J=J)
+        return J.reshape(n, nq, 3).transpose(0, 2, 1).copy()
+
+
+class Model(ModelBase):
+    """ddpb_model + the batched Model-concept entry points of include/ddpb.h (device evaluation, host arrays)."""
+
+    def __init__(self, model, device=0):
+        self._keep = []
+        self._init_model(model)
+        self.device = device
+        md = model_desc_c(model, self._keep)
+        self._m = C.c_void_p()
+        _check(lib().ddpb_model_create(C.byref(md), C.byref(self._m)))
+
+    def close(self):
+        if getattr(self, "_m", None):
+            lib().ddpb_model_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _eval(self, n, q, v=None, tau=None, acc=None, a=None, a_dq=None, a_dv=None, a_dtau=None, tau_out=None, p3=None, J=None, frame=0,
+              jac_mode=0):
+        L = lib()
+        p = lambda x: _d(x) if x is not None else None
+        if a is not None:
+            _check(L.ddpb_model_dynamics_aba(self._m, self.device, n, p(q), p(v), p(tau), p(a)))
+        if a_dq is not None or a_dv is not None or a_dtau is not None:
+            _check(L.ddpb_model_d_dynamics_aba(self._m, self.device, n, p(q), p(v), p(tau), p(a_dq), p(a_dv), p(a_dtau)))
+        if tau_out is not None:
+            _check(L.ddpb_model_inverse_dynamics_rnea(self._m, self.device, n, p(q), p(v), p(acc), p(tau_out)))
+        if p3 is not None:
+            _check(L.ddpb_model_frame_coordinates(self._m, self.device, n, frame, p(q), p(p3)))
+        if J is not None:
+            _check(L.ddpb_model_d_frame_coordinates(self._m, self.device, n, frame, jac_mode, p(q), p(J)))
 
 
 class Batch(BatchBase):

@@ -498,6 +498,78 @@ const char* ddpb_model_frame_name(const ddpb_model* m, int frame) {
 }
 void ddpb_model_destroy(ddpb_model* m) { delete m; }
 
+// ---- the Model concept's own functions for n independent samples (csrc/model_eval.cuh) ---------------------------------------
+namespace {
+struct DevBuf {  // device copy of a host array, freed on scope exit
+  double* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t in(const double* h, size_t count) {
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(double));
+    return e != cudaSuccess ? e : cudaMemcpy(p, h, count * sizeof(double), cudaMemcpyHostToDevice);
+  }
+  cudaError_t out(size_t count) { return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(double)); }
+};
+int model_eval_host(const ddpb_model* m, int device, int n, int frame, int jac_mode, const double* q, const double* v, const double* tau,
+                    const double* acc, double* a, double* a_dq, double* a_dv, double* a_dtau, double* tau_out, double* p3, double* J) {
+  if (!m || !q) return fail(DDPB_ERR_INVALID, "null argument");
+  if (n < 0) return fail(DDPB_ERR_INVALID, "negative sample count");
+  const bool pend = m->dev.kind == DDPB_MODEL_PENDULUM;
+  const bool fwd = a || a_dq || a_dv;
+  if (fwd && (!v || !tau)) return fail(DDPB_ERR_INVALID, "forward dynamics needs v and tau");
+  if (tau_out && (!v || !acc)) return fail(DDPB_ERR_INVALID, "inverse dynamics needs v and a");
+  if (pend && (tau_out || p3 || J)) return fail(DDPB_ERR_UNSUPPORTED, "the pendulum model has no inverse dynamics and no frames (pendulum_model.hpp)");
+  if ((p3 || J) && (frame < 0 || frame >= m->dev.nframes)) return fail(DDPB_ERR_INVALID, "frame index out of range");
+  if (J && jac_mode != DDPB_FJ_WORLD && jac_mode != DDPB_FJ_LOCAL_WORLD_ALIGNED) return fail(DDPB_ERR_INVALID, "unknown frame Jacobian convention");
+  if (n == 0) return DDPB_OK;
+  CU(cudaSetDevice(device));
+  const size_t nq = (size_t)m->nq, N = (size_t)n;
+  DevBuf dq, dv, dtau, dacc, oa, oadq, oadv, oadtau, otau, op3, oJ;
+  CU(dq.in(q, N * nq));
+  if (v) CU(dv.in(v, N * nq));
+  if (tau) CU(dtau.in(tau, N * nq));
+  if (acc) CU(dacc.in(acc, N * nq));
+  if (a) CU(oa.out(N * nq));
+  if (a_dq) CU(oadq.out(N * nq * nq));
+  if (a_dv) CU(oadv.out(N * nq * nq));
+  if (a_dtau) CU(oadtau.out(N * nq * nq));
+  if (tau_out) CU(otau.out(N * nq));
+  if (p3) CU(op3.out(N * 3));
+  if (J) CU(oJ.out(N * 3 * nq));
+  ModelEvalArgs A{};
+  A.n = n; A.frame = frame; A.jac_mode = jac_mode;
+  A.q = dq.p; A.v = dv.p; A.tau = dtau.p; A.acc = dacc.p;
+  A.a = oa.p; A.a_dq = oadq.p; A.a_dv = oadv.p; A.a_dtau = oadtau.p; A.tau_out = otau.p; A.p3 = op3.p; A.J = oJ.p;
+  const int tag = pend ? 0 : m->dev.n + (m->dev.any_prismatic ? 8 : 0);
+  DISPATCH(tag, L::model_eval(m->dev, A, 0));
+  CU(cudaGetLastError());
+  auto back = [&](double* h, const DevBuf& d, size_t count) { return h ? cudaMemcpy(h, d.p, count * sizeof(double), cudaMemcpyDeviceToHost) : cudaSuccess; };
+  CU(back(a, oa, N * nq)); CU(back(a_dq, oadq, N * nq * nq)); CU(back(a_dv, oadv, N * nq * nq)); CU(back(a_dtau, oadtau, N * nq * nq));
+  CU(back(tau_out, otau, N * nq)); CU(back(p3, op3, N * 3)); CU(back(J, oJ, N * 3 * nq));
+  return DDPB_OK;
+}
+}  // namespace
+int ddpb_model_dynamics_aba(const ddpb_model* m, int device, int n, const double* q, const double* v, const double* tau, double* a) {
+  if (!a) return fail(DDPB_ERR_INVALID, "null output");
+  return model_eval_host(m, device, n, 0, 0, q, v, tau, nullptr, a, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+int ddpb_model_d_dynamics_aba(const ddpb_model* m, int device, int n, const double* q, const double* v, const double* tau, double* a_dq,
+                              double* a_dv, double* a_dtau) {
+  if (!a_dq && !a_dv && !a_dtau) return fail(DDPB_ERR_INVALID, "null outputs");
+  return model_eval_host(m, device, n, 0, 0, q, v, tau, nullptr, nullptr, a_dq, a_dv, a_dtau, nullptr, nullptr, nullptr);
+}
+int ddpb_model_inverse_dynamics_rnea(const ddpb_model* m, int device, int n, const double* q, const double* v, const double* a, double* tau) {
+  if (!tau) return fail(DDPB_ERR_INVALID, "null output");
+  return model_eval_host(m, device, n, 0, 0, q, v, nullptr, a, nullptr, nullptr, nullptr, nullptr, tau, nullptr, nullptr);
+}
+int ddpb_model_frame_coordinates(const ddpb_model* m, int device, int n, int frame, const double* q, double* p) {
+  if (!p) return fail(DDPB_ERR_INVALID, "null output");
+  return model_eval_host(m, device, n, frame, DDPB_FJ_WORLD, q, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, p, nullptr);
+}
+int ddpb_model_d_frame_coordinates(const ddpb_model* m, int device, int n, int frame, int frame_jac_mode, const double* q, double* J) {
+  if (!J) return fail(DDPB_ERR_INVALID, "null output");
+  return model_eval_host(m, device, n, frame, frame_jac_mode, q, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, J);
+}
+
 int ddpb_batch_create(const ddpb_model* m, int B, int T, const int* ne_per_knot, const ddpb_params* p, int device, ddpb_batch** out) {
   if (!m || !p || !out || B < 1 || T < 1) return fail(DDPB_ERR_INVALID, "bad arguments");
   if (p->hess_mode != DDPB_HESS_FD_JACOBIANS && p->hess_mode != DDPB_HESS_FD_VALUES) return fail(DDPB_ERR_INVALID, "bad hess_mode");

@@ -9,6 +9,7 @@
 #include "launch.cuh"
 #include "linearize.cuh"
 #include "linearize_pt.cuh"
+#include "model_eval.cuh"
 #include "outer_warp.cuh"
 
 DDPB_VARIANT_BEGIN
@@ -83,6 +84,18 @@ template <int NJ> __global__ void linearize_kernel(const __grid_constant__ Model
   linearize_pendulum(m, bd, b, t);
 }
 #endif
+
+// the Model concept's own functions for n independent samples (model_eval.cuh): one thread per sample, workspaces in local memory
+template <int NJ> __global__ void __launch_bounds__(64) model_eval_kernel(const __grid_constant__ ModelDev m, const __grid_constant__ ModelEvalArgs A) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= A.n) return;
+#if DDPB_NJ > 0
+  double qrec[QRec<NJ>::SIZE], vrec[VRec<NJ>::SIZE];
+  model_eval_sample<NJ>(m, A, s, qrec, vrec);
+#else
+  model_eval_pendulum(m, A, s);
+#endif
+}
 
 // line search: cost_seq_aug of the current trajectory, then all trials at once (outer_warp.cuh)
 // per-thread scratch of the fused forward dynamics in dynamic shared memory: element e of thread i at dyn_scr[e * blockDim.x + i]
@@ -277,6 +290,9 @@ template <> void Launch<KNJ, HAS_PRISMATIC>::al_update(const BatchDev& bd, doubl
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 0);
   mult_update_kernel<KNJ><<<(unsigned)((nkb + 127) / 128), 128, 0, s>>>(bd);
   al_decide_kernel<KNJ><<<wblocks, 128, 0, s>>>(bd, thr, 1);
+}
+template <> void Launch<KNJ, HAS_PRISMATIC>::model_eval(const ModelDev& m, const ModelEvalArgs& A, cudaStream_t s) {
+  if (A.n > 0) model_eval_kernel<KNJ><<<(unsigned)((A.n + 63) / 64), 64, 0, s>>>(m, A);
 }
 template <> void Launch<KNJ, HAS_PRISMATIC>::optimality(const BatchDev& bd, cudaStream_t s) {
   optimality_kernel<KNJ><<<(unsigned)(((size_t)bd.nb * AdjGeom<KNJ>::G + 127) / 128), 128, 0, s>>>(bd);

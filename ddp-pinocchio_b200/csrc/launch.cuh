@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "batch.cuh"
+#include "model_eval.cuh"
 
 namespace ddpb {
 
@@ -29,6 +30,8 @@ template <int NJ, bool PR = false> struct Launch {
   static void cost(const ModelDev& m, const BatchDev& bd, double* costs, cudaStream_t s);
   static void al_update(const BatchDev& bd, double thr, cudaStream_t s);
   static void optimality(const BatchDev& bd, cudaStream_t s);
+  // the Model concept's own functions for A.n independent samples (model_eval.cuh)
+  static void model_eval(const ModelDev& m, const ModelEvalArgs& A, cudaStream_t s);
 };
 
 }  // namespace ddpb

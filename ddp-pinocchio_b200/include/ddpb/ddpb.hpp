@@ -95,6 +95,49 @@ struct model_t {
   index_t configuration_dim() const { return nq; }
   index_t tangent_dim() const { return nq; }
   index_t n_frames() const { return frames; }
+
+  // ---- the Model concept's functions (pinocchio_model.hpp:96-185, pendulum_model.hpp:35-132).  Same names and argument
+  // order; the views are plain pointers into caller-owned storage, matrices column-major like the reference's Eigen maps.
+  // Every joint of the supported models has nq = nv = 1 (revolute on the plain angle, prismatic, the pendulum), so the
+  // configuration space is a vector space: integrate is q + v, difference is q1 - q0, their Jacobians the identity --
+  // exactly what pinocchio::integrate / difference / dIntegrate / dDifference return for such joints.
+  void neutral_configuration(double* out_q) const { for (int i = 0; i < nq; ++i) out_q[i] = 0.0; }
+  void integrate(double* out_q, const double* q, const double* v) const { for (int i = 0; i < nq; ++i) out_q[i] = q[i] + v[i]; }
+  void difference(double* out_v, const double* q_start, const double* q_finish) const { for (int i = 0; i < nq; ++i) out_v[i] = q_finish[i] - q_start[i]; }
+  void d_integrate_dq(double* out, const double*, const double*) const { identity(out, 1.0); }
+  void d_integrate_dv(double* out, const double*, const double*) const { identity(out, 1.0); }
+  void d_difference_dq_start(double* out, const double*, const double*) const { identity(out, -1.0); }
+  void d_difference_dq_finish(double* out, const double*, const double*) const { identity(out, 1.0); }
+  // The dynamics and frame functions run on the device (one thread per sample, csrc/model_eval.cuh): the single-sample
+  // forms keep the reference's signatures, the *_batch forms take n samples (sample-major arrays) in one launch.
+  void dynamics_aba(double* out_acceleration, const double* q, const double* v, const double* tau, int device = 0) const {
+    check(ddpb_model_dynamics_aba(h, device, 1, q, v, tau, out_acceleration));
+  }
+  void d_dynamics_aba(double* out_dq, double* out_dv, double* out_dtau, const double* q, const double* v, const double* tau, int device = 0) const {
+    check(ddpb_model_d_dynamics_aba(h, device, 1, q, v, tau, out_dq, out_dv, out_dtau));
+  }
+  void inverse_dynamics_rnea(double* out_tau, const double* q, const double* v, const double* a, int device = 0) const {
+    check(ddpb_model_inverse_dynamics_rnea(h, device, 1, q, v, a, out_tau));
+  }
+  void frame_coordinates(double* out_p3, index_t i, const double* q, int device = 0) const {
+    check(ddpb_model_frame_coordinates(h, device, 1, int(i), q, out_p3));
+  }
+  void d_frame_coordinates(double* out_3xnv, index_t i, const double* q, int frame_jac_mode = DDPB_FJ_WORLD, int device = 0) const {
+    check(ddpb_model_d_frame_coordinates(h, device, 1, int(i), frame_jac_mode, q, out_3xnv));
+  }
+  void dynamics_aba_batch(int n, double* out_acceleration, const double* q, const double* v, const double* tau, int device = 0) const {
+    check(ddpb_model_dynamics_aba(h, device, n, q, v, tau, out_acceleration));
+  }
+  void d_dynamics_aba_batch(int n, double* out_dq, double* out_dv, double* out_dtau, const double* q, const double* v, const double* tau,
+                            int device = 0) const {
+    check(ddpb_model_d_dynamics_aba(h, device, n, q, v, tau, out_dq, out_dv, out_dtau));
+  }
+
+ private:
+  void identity(double* out, double d) const {
+    for (int c = 0; c < nq; ++c)
+      for (int r = 0; r < nq; ++r) out[c * nq + r] = r == c ? d : 0.0;
+  }
 };
 
 // dynamics_t{model, dt, second_order_finite_diff = true} (problem.hpp:522-524)

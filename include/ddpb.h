@@ -125,6 +125,28 @@ int ddpb_model_get(const ddpb_model* m, double* placement_rot, double* placement
 int ddpb_model_joint_types(const ddpb_model* m, int* joint_type /* [joints] ddpb_joint_type */);
 const char* ddpb_model_frame_name(const ddpb_model* m, int frame); /* "" when the model was built from arrays */
 void ddpb_model_destroy(ddpb_model* m);
+
+/* ---- the Model concept's own functions, batched ------------------------------------------------
+ * The reference's dynamics and constraints call these once per knot on one shared pinocchio::Data; here every call
+ * evaluates n independent samples on the device (one thread per sample, csrc/model_eval.cuh) from / into HOST arrays,
+ * sample-major: q, v, tau, a [n][nq]; matrices [n][nv * nv] column-major per sample like the reference's Eigen maps.
+ * The solver never uses them (compute_derivatives evaluates whole stencils per knot); they are the reference-facing
+ * single-function interface and the direct check of the rigid-body layer.  Pendulum models: the two dynamics functions only. */
+/* model_t::dynamics_aba(out_acceleration, q, v, tau) -> pinocchio::aba (pinocchio_model.hpp:147-152, pinocchio_model.ipp:336-357);
+ * pendulum_model_t::dynamics_aba (pendulum_model.hpp:105-114) */
+int ddpb_model_dynamics_aba(const ddpb_model* m, int device, int n, const double* q, const double* v, const double* tau, double* a);
+/* model_t::d_dynamics_aba(out_dq, out_dv, out_dtau, q, v, tau) -> pinocchio::computeABADerivatives (pinocchio_model.hpp:154-161,
+ * pinocchio_model.ipp:359-400); pendulum_model.hpp:116-130.  Any output may be NULL (not all three). */
+int ddpb_model_d_dynamics_aba(const ddpb_model* m, int device, int n, const double* q, const double* v, const double* tau,
+                              double* a_dq, double* a_dv, double* a_dtau);
+/* model_t::inverse_dynamics_rnea(out_tau, q, v, a) -> pinocchio::rnea (pinocchio_model.hpp:180-185) */
+int ddpb_model_inverse_dynamics_rnea(const ddpb_model* m, int device, int n, const double* q, const double* v, const double* a, double* tau);
+/* model_t::frame_coordinates(i, q) -> framesForwardKinematics + oMf[i].translation() (pinocchio_model.hpp:163, pinocchio_model.ipp:417-432);
+ * p [n][3] */
+int ddpb_model_frame_coordinates(const ddpb_model* m, int device, int n, int frame, const double* q, double* p);
+/* model_t::d_frame_coordinates(out[3 x nv], i, q) -> top three rows of getFrameJacobian(..., WORLD) (pinocchio_model.hpp:164,
+ * pinocchio_model.ipp:434-462); frame_jac_mode: the frame_jac_mode field of the batch parameters, DDPB_FJ_WORLD reproduces the reference; J [n][3 * nv] column-major */
+int ddpb_model_d_frame_coordinates(const ddpb_model* m, int device, int n, int frame, int frame_jac_mode, const double* q, double* J);
 /* ne_per_knot[t] (t in [0,T)) = equality rows at knot t, i.e. rows of the doubly advanced
  * constraint that acts on x_{t+2} (indexing::shift_time_idx_t, indexer.hpp:291-318); the same for
  * every problem.  Replaces ddp_solver_t's constructor + uninit_derivative_storage (ddp.hpp:430-514,864-867). */

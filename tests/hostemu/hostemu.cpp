@@ -13,6 +13,7 @@
 #include "../../ddp-pinocchio_b200/csrc/forward.cuh"
 #include "../../ddp-pinocchio_b200/csrc/linearize.cuh"
 #include "../../ddp-pinocchio_b200/csrc/linearize_pt.cuh"
+#include "../../ddp-pinocchio_b200/csrc/model_eval.cuh"
 #include "../../ddp-pinocchio_b200/csrc/model_host.hpp"
 
 using namespace ddpb;
@@ -241,6 +242,23 @@ int emu_field(void* hv, double* packed, int field, int to_slab) {
       }
     }
   return bad;
+}
+
+// the Model concept's own functions for A->n samples: the body of model_eval_kernel (kernels_nj.cu) one sample at a time
+int emu_model_eval(const ddpb_model_desc* d, const ModelEvalArgs* A) {
+  ModelDev m;
+  std::string err;
+  if (model_from_desc(d, m, err) != DDPB_OK) return -1;
+  if (m.kind == DDPB_MODEL_PENDULUM) {
+    for (int s = 0; s < A->n; ++s) model_eval_pendulum(m, *A, s);
+    return 0;
+  }
+  EMU_NJ(m.n, {
+    std::vector<double> qrec(QRec<NJ>::SIZE);
+    std::vector<double> vrec(VRec<NJ>::SIZE);
+    for (int s = 0; s < A->n; ++s) model_eval_sample<NJ>(m, *A, s, qrec.data(), vrec.data());
+  });
+  return 0;
 }
 
 }  // extern "C"

@@ -177,3 +177,26 @@ class EmuBatch(capi.BatchBase):
         sp = capi.SolverParamsC(max_iterations, thr, mu, reg, w, n)
         lib().emu_solve(self._h, C.byref(sp))
         return self.get_scalars()
+
+
+class ModelEvalArgsC(C.Structure):  # csrc/model_eval.cuh ModelEvalArgs
+    _fields_ = [("n", C.c_int), ("frame", C.c_int), ("jac_mode", C.c_int), ("q", _dp), ("v", _dp), ("tau", _dp), ("acc", _dp), ("a", _dp),
+                ("a_dq", _dp), ("a_dv", _dp), ("a_dtau", _dp), ("tau_out", _dp), ("p3", _dp), ("J", _dp)]
+
+
+class EmuModel(capi.ModelBase):
+    """capi.Model on the CPU: the body of model_eval_kernel one sample at a time."""
+
+    def __init__(self, model):
+        self._keep = []
+        self._init_model(model)
+        self._md = capi.model_desc_c(model, self._keep)
+
+    def _eval(self, n, q, frame=0, jac_mode=0, **arrs):
+        A = ModelEvalArgsC()
+        A.n = n; A.frame = frame; A.jac_mode = jac_mode
+        A.q = q.ctypes.data_as(_dp)
+        for k, x in arrs.items():
+            if x is not None:
+                setattr(A, k, x.ctypes.data_as(_dp))
+        assert lib().emu_model_eval(C.byref(self._md), C.byref(A)) == 0

@@ -374,3 +374,58 @@ def check_solve(make, w, iters):
         assert int(sc["iterations"][b]) == iters
     bt.close()
     return stats
+
+
+# ---- the Model concept's own functions (capi.Model / hostemu_lib.EmuModel: dynamics_aba, d_dynamics_aba, inverse_dynamics_rnea,
+# frame_coordinates, d_frame_coordinates for n samples) ---------------------------------------------------------------------
+def model_concept_models():
+    return [("pendulum", P.models.pendulum()), ("chain_2r", S.workload("c2", B=1, T=2).model), ("arm_6r", P.models.arm_6r()),
+            ("arm_7r", S.workload("c5", B=1, T=2).model), ("scara_rrpr", P.models.scara_rrpr()), ("chain_prprr", P.models.chain_mixed(5, "PRPRR"))]
+
+
+def check_model_concept(make_model, m, n=7, seed=3):
+    """Every function against the oracle's (1e-10 relative; the oracle works in body coordinates with dense 6x6 algebra, the
+    kernels in world-frame Pluecker coordinates), inverse dynamics of the forward dynamics gives the torques back, M^-1 is
+    symmetric, the arms also against Lagrangian mechanics written with numpy kinematics only, and the frame Jacobian in the
+    LOCAL_WORLD_ALIGNED convention against central differences of the frame position."""
+    mm = make_model(m)
+    nq = mm.nq
+    rng = np.random.RandomState(seed)
+    q = rng.uniform(-1.5, 1.5, (n, nq)); v = rng.uniform(-1, 1, (n, nq)); tau = rng.uniform(-3, 3, (n, nq))
+    o = ol.Oracle(m, 2)
+    a = mm.dynamics_aba(q, v, tau)
+    dq, dv, dtau = mm.d_dynamics_aba(q, v, tau)
+    worst = 0.0
+    for s in range(n):
+        worst = max(worst, relerr(a[s], o.aba(q[s], v[s], tau[s])))
+        r = o.d_aba(q[s], v[s], tau[s])
+        for mine, ref in zip((dq[s], dv[s], dtau[s]), r):
+            ref = np.asarray(ref).reshape(nq, nq)
+            worst = max(worst, float(np.abs(mine - ref).max() / max(1.0, np.abs(ref).max())))
+        assert np.abs(dtau[s] - dtau[s].T).max() <= 1e-12 * np.abs(dtau[s]).max()
+    assert worst < 1e-10, worst
+    if m.kind == 0:
+        return worst
+    tau_back = mm.inverse_dynamics_rnea(q, v, a)
+    assert relerr(tau_back, tau) < 1e-10
+    for s in range(n):
+        assert relerr(tau_back[s], o.rnea(q[s], v[s], a[s])) < 1e-10
+    for s in range(2):
+        a_l, M = lagrangian_forward_dynamics(m, q[s], v[s], tau[s])
+        assert relerr(a[s], a_l) < 1e-7, (relerr(a[s], a_l))
+        assert relerr(dtau[s], np.linalg.inv(M)) < 1e-9
+    for f in range(m.n_frames):
+        p = mm.frame_coordinates(f, q)
+        for mode in (0, 1):
+            J = mm.d_frame_coordinates(f, q, mode)
+            for s in range(n):
+                po, Jo = o.frame(f, q[s], mode)
+                assert np.abs(p[s] - po).max() < 1e-12 * max(1.0, np.abs(po).max())
+                assert np.abs(J[s] - np.asarray(Jo).reshape(3, nq)).max() < 1e-12 * max(1.0, np.abs(Jo).max())
+        h = 1e-6
+        J1 = mm.d_frame_coordinates(f, q[:1], 1)[0]
+        for c in range(nq):
+            e = np.zeros(nq); e[c] = h
+            fd = (mm.frame_coordinates(f, q[:1] + e)[0] - mm.frame_coordinates(f, q[:1] - e)[0]) / (2 * h)
+            assert np.abs(fd - J1[:, c]).max() < 1e-8
+    return worst

@@ -57,6 +57,21 @@ def test_fails_loudly_without_a_gpu(pkg):
         capi.Batch.from_workload(synthetic.workload("c2", B=2, T=4))
 
 
+def test_model_functions_fail_loudly_without_a_gpu(pkg):
+    """The Model concept's own functions run on the device too: argument errors are reported first, then the missing device."""
+    import numpy as np
+    import torch
+    from ddp_pinocchio_b200 import capi, models
+    mm = capi.Model(models.arm_6r())
+    q = np.zeros((2, 6))
+    with pytest.raises(capi.DdpbError, match="frame index"):
+        mm.frame_coordinates(99, q)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.DdpbError, match="cudaSetDevice"):
+        mm.dynamics_aba(q, q, q)
+
+
 def test_backward_kernel_uses_tma_bulk_copies():
     """The backward pass stages slab records with TMA (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier (SYNCS);
     checked on the built library's SASS (skipped where cuobjdump is not installed)."""

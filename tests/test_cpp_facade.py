@@ -48,3 +48,37 @@ def test_model_from_urdf_path(tmp_path, pkg):
     assert "nq 6 nv 6 frames 8" in r.stdout and "frame 7 tool0" in r.stdout and "moved nq 6" in r.stdout
     r = subprocess.run([exe, str(tmp_path / "missing.urdf")], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open" in r.stdout
+
+
+def _build_model_concept(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_urdf import UR5
+    exe = str(tmp_path / "model_concept")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-I", os.path.join(PKG, "include"), os.path.join(ROOT, "tests", "cpp", "model_concept.cpp"),
+                           "-L", PKG, "-lddpb", f"-Wl,-rpath,{PKG}", "-o", exe])
+    path = tmp_path / "ur5_like.urdf"
+    path.write_text(UR5)
+    return exe, str(path)
+
+
+def test_model_concept_host_functions_and_loud_failure_without_gpu(tmp_path, pkg):
+    """integrate / difference / d_difference_dq_finish are host code (the identities of the reference's test/pinocchio.cpp);
+    the dynamics functions need the device."""
+    import torch
+    exe, urdf = _build_model_concept(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, urdf], capture_output=True, text=True)
+    assert "round trip 0.0e+00, d_difference_dq_finish(0,0) 1.0 (1,0) 0.0" in r.stdout
+    assert r.returncode == 1 and "cudaSetDevice" in r.stdout
+
+
+@pytest.mark.gpu
+def test_model_concept_main(tmp_path, pkg):
+    exe, urdf = _build_model_concept(tmp_path)
+    r = subprocess.run([exe, urdf], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "round trip 0.0e+00" in r.stdout
+    err = float(r.stdout.split("rnea(aba) - tau ")[1].split(",")[0])
+    assert err < 1e-12, r.stdout

@@ -81,3 +81,9 @@ def test_slab_structure_is_enforced(name):
 def test_forward_many_halvings(name):
     seen = pc.check_forward_many_halvings(make, pc.S.workload(name, B=7, T=8))
     assert max(seen) > 4      # some problem needed more than four trials
+
+
+@pytest.mark.parametrize("tag,m", pc.model_concept_models(), ids=[t for t, _ in pc.model_concept_models()])
+def test_model_concept_functions(tag, m):
+    """dynamics_aba / d_dynamics_aba / inverse_dynamics_rnea / frame_coordinates / d_frame_coordinates (csrc/model_eval.cuh)."""
+    pc.check_model_concept(he.EmuModel, m)

@@ -271,3 +271,40 @@ def test_solve_ragged_batch_sizes(name, B, T, iters):
     for s in stats:
         assert s["dev_vs_quad"] <= 50 * s["double_vs_quad"] + 1e-8, s
     assert sum(s["same_flow"] for s in stats) >= len(stats) - max(1, len(stats) // 10), stats
+
+
+def make_model(m):
+    from ddp_pinocchio_b200 import capi
+    return capi.Model(m)
+
+
+@pytest.mark.parametrize("tag,m", pc.model_concept_models(), ids=[t for t, _ in pc.model_concept_models()])
+def test_model_concept_functions(tag, m):
+    """ddpb_model_dynamics_aba / d_dynamics_aba / inverse_dynamics_rnea / frame_coordinates / d_frame_coordinates vs the oracle."""
+    pc.check_model_concept(make_model, m)
+
+
+def test_model_concept_functions_many_samples():
+    """A batch that spans several CTAs with a ragged tail, against the single-sample calls."""
+    from ddp_pinocchio_b200 import models
+    mm = make_model(models.arm_6r())
+    rng = np.random.RandomState(5)
+    n = 64 * 3 + 17
+    q, v, tau = rng.uniform(-2, 2, (n, 6)), rng.uniform(-1, 1, (n, 6)), rng.uniform(-5, 5, (n, 6))
+    a = mm.dynamics_aba(q, v, tau)
+    for s in (0, 63, 64, n - 1):
+        assert np.array_equal(a[s], mm.dynamics_aba(q[s], v[s], tau[s])[0])
+    assert pc.relerr(mm.inverse_dynamics_rnea(q, v, a), tau) < 1e-10
+
+
+def test_model_concept_argument_checks():
+    from ddp_pinocchio_b200 import capi, models
+    mm = make_model(models.arm_6r())
+    q = np.zeros((1, 6))
+    with pytest.raises(capi.DdpbError, match="frame index"):
+        mm.frame_coordinates(99, q)
+    with pytest.raises(capi.DdpbError, match="Jacobian convention"):
+        mm.d_frame_coordinates(0, q, jac_mode=7)
+    pm = make_model(models.pendulum())
+    with pytest.raises(capi.DdpbError, match="pendulum"):
+        pm.inverse_dynamics_rnea(np.zeros((1, 1)), np.zeros((1, 1)), np.zeros((1, 1)))
