@@ -140,6 +140,33 @@ struct model_t {
   }
 };
 
+namespace detail {
+// The per-call forms of the Dynamics / Constraint / Problem concepts (eval_to, first_order_deriv, second_order_deriv,
+// eval_eq_to ...) evaluate ONE knot of n independent (x, u) samples: a batch of n problems with horizon 1 goes through
+// ddpb_compute_derivatives, i.e. through the same linearization kernel as a solve.  A call creates and destroys its batch
+// (device allocations: milliseconds) -- bulk work belongs to ddp_solver_t, these exist so that code written against the
+// reference's concepts finds the functions it calls.
+inline void knot_derivatives(const ddpb_model* model, int nq, double dt, double c, bool second_order_finite_diff, int eq_kind, int ne,
+                             int frame_id, int frame_jac_mode, const double* targets, int n, const double* x, const double* u,
+                             const ddpb_derivs& out, int device) {
+  ddpb_params pr{};
+  pr.dt = dt; pr.c = c;
+  pr.hess_mode = second_order_finite_diff ? DDPB_HESS_FD_VALUES : DDPB_HESS_FD_JACOBIANS;
+  pr.eq_kind = ne > 0 ? eq_kind : DDPB_EQ_NONE; pr.frame_id = frame_id; pr.frame_jac_mode = frame_jac_mode;
+  ddpb_batch* b = nullptr;
+  check(ddpb_batch_create(model, n, 1, ne > 0 ? &ne : nullptr, &pr, device, &b));
+  struct guard { ddpb_batch* b; ~guard() { ddpb_batch_destroy(b); } } g{b};
+  const std::size_t nx = 2 * static_cast<std::size_t>(nq);
+  std::vector<double> xs(static_cast<std::size_t>(n) * 2 * nx, 0.0);  // [n][(T+1) nx]: x_0 = x; x_1 is not read by knot 0
+  for (int s = 0; s < n; ++s)
+    for (std::size_t k = 0; k < nx; ++k) xs[static_cast<std::size_t>(s) * 2 * nx + k] = x[static_cast<std::size_t>(s) * nx + k];
+  check(ddpb_set_trajectory(b, xs.data(), u));
+  if (ne > 0) check(ddpb_set_targets(b, targets));
+  check(ddpb_compute_derivatives(b));
+  check(ddpb_get_derivatives(b, &out));
+}
+}  // namespace detail
+
 // dynamics_t{model, dt, second_order_finite_diff = true} (problem.hpp:522-524)
 struct dynamics_t {
   model_t const& m_model;
@@ -148,6 +175,32 @@ struct dynamics_t {
   index_t state_dim() const { return 2 * m_model.nq; }
   index_t dstate_dim() const { return 2 * m_model.nq; }
   index_t control_dim(index_t) const { return m_model.nq; }
+
+  // Dynamics concept, per call (problem.hpp:441-521).  out: x_next [nx]; out_x: f_x [ndx x ndx], out_u: f_u [ndx x nu]
+  // (column-major); out_xx / out_ux / out_uu: the tensors T(k, i, j) at k + i O + j O L (detail/tensor.hpp:146).  The time index
+  // is ignored as in the reference.  `n` samples per call (sample-major arrays), default one.
+  void eval_to(double* out, index_t, const double* x, const double* u, int n = 1, int device = 0) const {
+    ddpb_derivs d{}; d.f_val = out;
+    run(d, x, u, n, device);
+  }
+  void first_order_deriv(double* out_x, double* out_u, double* out, index_t, const double* x, const double* u, int n = 1, int device = 0) const {
+    ddpb_derivs d{}; d.f_val = out; d.fx = out_x; d.fu = out_u;
+    run(d, x, u, n, device);
+  }
+  void second_order_deriv(double* out_xx, double* out_ux, double* out_uu, double* out_x, double* out_u, double* out, index_t, const double* x,
+                          const double* u, int n = 1, int device = 0) const {
+    ddpb_derivs d{}; d.f_val = out; d.fx = out_x; d.fu = out_u; d.fxx = out_xx; d.fux = out_ux; d.fuu = out_uu;
+    run(d, x, u, n, device);
+  }
+  // integrate_x / integrate_u / difference_out of the concept (problem.hpp:404-439) on the vector-space state of these models
+  void integrate_x(double* out, const double* x, const double* dx) const { for (index_t i = 0; i < state_dim(); ++i) out[i] = x[i] + dx[i]; }
+  void integrate_u(double* out, index_t, const double* u, const double* du) const { for (int i = 0; i < m_model.nq; ++i) out[i] = u[i] + du[i]; }
+  void difference_out(double* out, const double* start, const double* finish) const { for (index_t i = 0; i < state_dim(); ++i) out[i] = finish[i] - start[i]; }
+
+ private:
+  void run(const ddpb_derivs& d, const double* x, const double* u, int n, int device) const {
+    detail::knot_derivatives(m_model.h, m_model.nq, dt, 0.0, second_order_finite_diff, DDPB_EQ_NONE, 0, 0, DDPB_FJ_WORLD, nullptr, n, x, u, d, device);
+  }
 };
 
 // Constraint concept.  The reference composes constraint_advance_time(constraint_advance_time(c)) around a
@@ -179,6 +232,26 @@ struct problem_t {
   dynamics_t m_dynamics;
   constraint_t m_constraint;
   index_t horizon() const { return m_end - m_begin; }
+
+  // Problem concept, per call (problem.hpp:932-955): lf(x) = 0, l(t, x, u) = c/2 |u|^2, eval_f_to = the dynamics,
+  // eval_eq_to = the doubly advanced constraint at knot t (rows eq_dim(t), `target` = those rows of the target),
+  // and one knot of compute_derivatives for n samples (any pointer of `out` may be null).
+  double lf(const double*) const { return 0.0; }
+  double l(index_t, const double*, const double* u) const {
+    double s = 0.0;
+    for (int i = 0; i < m_dynamics.m_model.nq; ++i) s += u[i] * u[i];
+    return c / 2 * s;
+  }
+  void eval_f_to(double* x_out, index_t t, const double* x, const double* u, int n = 1, int device = 0) const { m_dynamics.eval_to(x_out, t, x, u, n, device); }
+  void eval_eq_to(double* eq_out, index_t t, const double* x, const double* u, const double* target, int n = 1, int device = 0) const {
+    ddpb_derivs d{}; d.eq_val = eq_out;
+    knot_derivatives(t, x, u, target, d, n, device);
+  }
+  void knot_derivatives(index_t t, const double* x, const double* u, const double* target, const ddpb_derivs& out, int n = 1, int device = 0) const {
+    const int ne = m_constraint.kind == DDPB_EQ_NONE ? 0 : m_constraint.eq_dim(t - m_begin);
+    detail::knot_derivatives(m_dynamics.m_model.h, m_dynamics.m_model.nq, m_dynamics.dt, c, m_dynamics.second_order_finite_diff, m_constraint.kind, ne,
+                             m_constraint.frame_id, m_constraint.frame_jac_mode, target, n, x, u, out, device);
+  }
 };
 
 // per-problem scalars returned by solve (replaces the reference's stdout / log files, ddp.hpp:651-671)

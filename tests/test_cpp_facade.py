@@ -82,3 +82,32 @@ def test_model_concept_main(tmp_path, pkg):
     assert "round trip 0.0e+00" in r.stdout
     err = float(r.stdout.split("rnea(aba) - tau ")[1].split(",")[0])
     assert err < 1e-12, r.stdout
+
+
+def _build_knot_functions(tmp_path):
+    exe = str(tmp_path / "knot_functions")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-I", os.path.join(PKG, "include"), os.path.join(ROOT, "tests", "cpp", "knot_functions.cpp"),
+                           "-L", PKG, "-lddpb", f"-Wl,-rpath,{PKG}", "-o", exe])
+    return exe
+
+
+def test_knot_functions_compile_and_fail_loudly_without_gpu(tmp_path, pkg):
+    """dynamics_t::eval_to / first_order_deriv / second_order_deriv, problem_t::eval_f_to / eval_eq_to / l of the facade."""
+    import torch
+    exe = _build_knot_functions(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_knot_functions_main(tmp_path, pkg):
+    """The per-call forms of the Dynamics / Problem concepts on the reference's pendulum against the closed forms (in the C++ main)."""
+    r = subprocess.run([_build_knot_functions(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    first = float(r.stdout.split("first order ")[1].split()[0])
+    second = float(r.stdout.split("second order ")[1].split()[0])
+    eq = float(r.stdout.split("eval_eq_to / eval_f_to ")[1].split(",")[0])
+    assert first < 1e-13 and second < 1e-6 and eq < 1e-13, r.stdout   # second order: forward differences of Jacobians, eps = 2^-26
+    assert "l 0.125, eq_dim(T-2) 1 eq_dim(0) 0" in r.stdout

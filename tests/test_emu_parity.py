@@ -87,3 +87,9 @@ def test_forward_many_halvings(name):
 def test_model_concept_functions(tag, m):
     """dynamics_aba / d_dynamics_aba / inverse_dynamics_rnea / frame_coordinates / d_frame_coordinates (csrc/model_eval.cuh)."""
     pc.check_model_concept(he.EmuModel, m)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c4", "c5"])
+def test_single_knot_batches(name):
+    """Horizon 1: what the per-call forms of the facade's Dynamics / Problem concepts run on (ddpb.hpp detail::knot_derivatives)."""
+    pc.check_linearization(make, pc.S.workload(name, B=3, T=1))

@@ -308,3 +308,9 @@ def test_model_concept_argument_checks():
     pm = make_model(models.pendulum())
     with pytest.raises(capi.DdpbError, match="pendulum"):
         pm.inverse_dynamics_rnea(np.zeros((1, 1)), np.zeros((1, 1)), np.zeros((1, 1)))
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c4", "c5"])
+def test_single_knot_batches(name):
+    """Horizon 1: what the per-call forms of the facade's Dynamics / Problem concepts run on (ddpb.hpp detail::knot_derivatives)."""
+    pc.check_linearization(make, pc.S.workload(name, B=3, T=1))
