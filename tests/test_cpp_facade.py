@@ -111,3 +111,13 @@ def test_knot_functions_main(tmp_path, pkg):
     eq = float(r.stdout.split("eval_eq_to / eval_f_to ")[1].split(",")[0])
     assert first < 1e-13 and second < 1e-6 and eq < 1e-13, r.stdout   # second order: forward differences of Jacobians, eps = 2^-26
     assert "l 0.125, eq_dim(T-2) 1 eq_dim(0) 0" in r.stdout
+
+
+def test_reference_layout_kats_in_cpp(tmp_path, pkg):
+    """ddpb/layout.hpp (indexers, mat_seq_t, tensor_view_t under the reference's names) passes the known answers of the
+    reference's own unit tests, test/indexing.cpp and test/mat_seq.cpp.  Host code: runs without a GPU."""
+    exe = str(tmp_path / "layout_kats")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-I", os.path.join(PKG, "include"), os.path.join(ROOT, "tests", "cpp", "layout_kats.cpp"),
+                           "-L", PKG, "-lddpb", f"-Wl,-rpath,{PKG}", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "0 failures" in r.stdout, r.stdout
