@@ -121,3 +121,54 @@ def test_reference_layout_kats_in_cpp(tmp_path, pkg):
                            "-L", PKG, "-lddpb", f"-Wl,-rpath,{PKG}", "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "0 failures" in r.stdout, r.stdout
+
+
+def _build_pinocchio_ddp(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_urdf import UR5
+    exe = str(tmp_path / "pinocchio_ddp")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-I", os.path.join(PKG, "include"), os.path.join(ROOT, "tests", "cpp", "pinocchio_ddp.cpp"),
+                           "-L", PKG, "-lddpb", f"-Wl,-rpath,{PKG}", "-o", exe])
+    path = tmp_path / "ur5_like.urdf"
+    path.write_text(UR5)
+    return exe, str(path)
+
+
+def test_reference_style_arm_mains_compile(tmp_path, pkg):
+    import torch
+    exe, urdf = _build_pinocchio_ddp(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, urdf, "config", "3"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["config", "spatial"])
+def test_reference_style_arm_mains(tmp_path, pkg, kind):
+    """test/pinocchio_ddp.cpp and test/pinocchio_spatial_eq_ddp.cpp through the facade (UR5-style arm from URDF, horizon 10):
+    the final configuration against the oracle's solve of the same scenario."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from test_urdf import UR5
+    from ddp_pinocchio_b200 import capi, synthetic as S
+    exe, urdf = _build_pinocchio_ddp(tmp_path)
+    iters = 4
+    r = subprocess.run([exe, urdf, kind, str(iters)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    qT = np.array([float(v) for v in r.stdout.split("q_T")[1].split()])
+    m = capi.model_from_urdf(UR5)
+    T = 10
+    ne = np.full(T, 6, dtype=np.int32) if kind == "config" else np.array([0] * 8 + [3, 0], dtype=np.int32)
+    o = ol.Oracle(m, T, dt=0.01, c=1.0, hess_mode=0, eq_kind=S.EQ_CONFIG if kind == "config" else S.EQ_SPATIAL, frame=m.n_frames - 1,
+                  jac_mode=0, ne_per_knot=ne, targets=np.zeros(int(ne.sum())))
+    us = np.zeros((T, 6))
+    xs = o.rollout(np.zeros(12), us)
+    seed = np.array([0.01 * (((i * 37) % 19) - 9.0) for i in range(int(ne.sum()) * 12)])
+    ref = o.solve(xs, us, seed, iters, 1e4)
+    assert f"ne {int(ne.sum())} iterations {iters}" in r.stdout
+    # (4 iterations of forward-difference Hessians: the emulator is at 6e-12 (config) and 1e-8 (spatial) from the oracle here)
+    assert np.abs(qT - ref["xs"][T, :6]).max() < 1e-6, (qT, ref["xs"][T, :6])
