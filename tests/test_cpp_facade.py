@@ -172,3 +172,14 @@ def test_reference_style_arm_mains(tmp_path, pkg, kind):
     assert f"ne {int(ne.sum())} iterations {iters}" in r.stdout
     # (4 iterations of forward-difference Hessians: the emulator is at 6e-12 (config) and 1e-8 (spatial) from the oracle here)
     assert np.abs(qT - ref["xs"][T, :6]).max() < 1e-6, (qT, ref["xs"][T, :6])
+
+
+def test_reference_liegroup_tests_in_cpp(tmp_path, pkg):
+    """ddpb/liegroup.hpp (free-flyer / spherical / planar configuration spaces under the Model concept's names) passes the
+    reference's test/pinocchio.cpp -- integrate / difference round trips and the d_difference_dq_finish identity on
+    all_joints_test_model() -- and central-difference checks of its four Jacobians.  Host code: runs without a GPU."""
+    exe = str(tmp_path / "liegroup_kats")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-I", os.path.join(PKG, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "liegroup_kats.cpp"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "0 failures" in r.stdout, r.stdout[-2000:]
