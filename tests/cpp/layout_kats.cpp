@@ -15,34 +15,29 @@ static int failures = 0;
 
 int main() {
   using namespace ddpb;
-  {  // regular indexer
-    auto idx = indexing::mat_regular_indexer(3, 12, 3, 4);
-    CHECK(idx.index_begin() == 3);
-    CHECK(idx.index_end() == 12);
+  {  // regular indexer over [3, 12) of 3 x 4 matrices: iterator algebra and what a dereferenced iterator reports
+    const auto idx = indexing::mat_regular_indexer(3, 12, 3, 4);
+    CHECK(idx.index_begin() == 3 && idx.index_end() == 12 && idx.required_memory() == 9 * 12);
     auto it = begin(idx);
-    ++it; --it; it++; it--;
-    it += 4; it -= 2;
-    auto r = *it;
-    auto it1 = it++;
-    auto it2 = it--;
-    auto it3 = ++it;
-    auto it4 = --it;
-    CHECK(it1 == it);
-    CHECK(it2 == (it + 1));
-    CHECK(it3 == (it + 1));
-    CHECK(it4 == it);
-    CHECK(it == it);
-    CHECK(it != (it + 1));
-    CHECK((it + 1) > it);
-    CHECK((it - 1) < it);
-    CHECK((it + 1) >= it);
-    CHECK((it - 1) <= it);
-    CHECK(it >= it);
-    CHECK(it <= it);
-    CHECK(r.current_index() == 5);
-    CHECK(r.rows() == 3);
-    CHECK(r.cols() == 4);
-    CHECK(r.memory_offset() == 2 * 12);
+    ++it; --it; it++; it--;              // back at the first knot
+    CHECK((*it).current_index() == 3 && (*it).memory_offset() == 0);
+    it += 4; it -= 2;                    // third knot
+    const auto here = *it;
+    CHECK(here.current_index() == 5 && here.rows() == 3 && here.cols() == 4 && here.memory_offset() == 2 * 12);
+    // post-increment / post-decrement return the old position, the prefix forms the new one
+    const auto before_inc = it++;
+    CHECK(before_inc == it - 1);
+    const auto before_dec = it--;
+    CHECK(before_dec == it + 1);
+    CHECK(++it == before_dec);
+    CHECK(--it == before_inc);
+    // ordering
+    const auto next = it + 1, prev = it - 1;
+    CHECK(it == it && it != next && next > it && prev < it && next >= it && prev <= it && it >= it && it <= it);
+    // walking the whole range visits every knot once and ends at end()
+    index_t count = 0;
+    for (auto w = begin(idx); w != end(idx); ++w) ++count;
+    CHECK(count == 9);
   }
   {  // composed indexers
     auto idx = indexing::vec_regular_indexer(0, 12, 3);
