@@ -35,6 +35,26 @@ def test_aba_satisfies_inverse_dynamics(mk):
 
 
 @pytest.mark.parametrize("mk", MODELS, ids=MODEL_IDS)
+def test_forward_dynamics_is_affine_in_the_torque(mk):
+    """aba(q, v, tau + d) = aba(q, v, tau) + M^-1(q) d: the identity behind the torque-affine evaluation points of the
+    value-based linearization (csrc/linearize.cuh), at the reference's step eps = 2^-13 and at a large step, in __float128
+    (identity to rounding) and in double (the two sides differ by a few ulp of the acceleration: the noise a second ABA
+    run carries into the stencil anyway)."""
+    m = mk(); n = m.nq
+    o = ol.Oracle(m, 4)
+    rng = np.random.RandomState(7)
+    for step in (2.0 ** -13, 3.0):
+        q, v, tau = rng.uniform(-2, 2, n), rng.uniform(-1, 1, n), rng.uniform(-5, 5, n)
+        d = np.zeros(n); d[rng.randint(n)] = step
+        if n > 1:
+            d[rng.randint(n)] += step
+        for prec, tol in ((1, 1e-15), (0, 1e-12)):
+            minv = np.asarray(o.d_aba(q, v, tau, prec=prec)[2]).reshape(n, n)
+            a0, a1 = o.aba(q, v, tau, prec=prec), o.aba(q, v, tau + d, prec=prec)
+            assert np.abs(a1 - (a0 + minv @ d)).max() <= tol * max(1.0, np.abs(a1).max()), (step, prec)
+
+
+@pytest.mark.parametrize("mk", MODELS, ids=MODEL_IDS)
 def test_aba_derivatives_vs_quad_central_differences(mk):
     m = mk(); n = m.nq
     o = ol.Oracle(m, 4)
