@@ -1,5 +1,5 @@
 // liegroup.hpp -- configuration-space operations of the Model concept for joints whose configuration is NOT a vector
-// space: free-flyer SE(3), spherical SO(3), planar SE(2) (and the vector-space joints for completeness).
+// space: free-flyer SE(3), spherical SO(3), planar SE(2), unbounded revolute SO(2) (and the vector-space joints for completeness).
 //
 // The reference forwards these to Pinocchio (/root/reference/include/ddp/pinocchio_model.ipp:199-321:
 //   neutral -> pinocchio::neutral, integrate -> pinocchio::integrate, d_integrate_dq / dv -> dIntegrate(ARG0 / ARG1),
@@ -144,8 +144,9 @@ inline mat6 Ad_inv(const mat3& R, const double* t) {
 }
 
 // ---- joints -------------------------------------------------------------------------------------------
-enum class joint_kind { revolute, prismatic, spherical, planar, free_flyer };
-inline int nq_of(joint_kind k) { return k == joint_kind::free_flyer ? 7 : (k == joint_kind::spherical || k == joint_kind::planar ? 4 : 1); }
+// revolute_unbounded: what Pinocchio's URDF parser makes of a `continuous` joint -- q = (cos, sin), one tangent coordinate
+enum class joint_kind { revolute, prismatic, revolute_unbounded, spherical, planar, free_flyer };
+inline int nq_of(joint_kind k) { return k == joint_kind::free_flyer ? 7 : (k == joint_kind::spherical || k == joint_kind::planar ? 4 : (k == joint_kind::revolute_unbounded ? 2 : 1)); }
 inline int nv_of(joint_kind k) { return k == joint_kind::free_flyer ? 6 : (k == joint_kind::spherical || k == joint_kind::planar ? 3 : 1); }
 
 inline void neutral(joint_kind k, double* q) {
@@ -153,11 +154,17 @@ inline void neutral(joint_kind k, double* q) {
   if (k == joint_kind::free_flyer) q[6] = 1.0;
   if (k == joint_kind::spherical) q[3] = 1.0;
   if (k == joint_kind::planar) q[2] = 1.0;
+  if (k == joint_kind::revolute_unbounded) q[0] = 1.0;
 }
 inline void integrate(joint_kind k, const double* q, const double* v, double* out) {
   switch (k) {
     case joint_kind::revolute:
     case joint_kind::prismatic: out[0] = q[0] + v[0]; return;
+    case joint_kind::revolute_unbounded: {
+      const double cw = std::cos(v[0]), sw = std::sin(v[0]), c = q[0] * cw - q[1] * sw, s = q[1] * cw + q[0] * sw, n = std::sqrt(c * c + s * s);
+      out[0] = c / n; out[1] = s / n;
+      return;
+    }
     case joint_kind::spherical: {
       double e[4];
       quat_exp(v, e);
@@ -192,6 +199,7 @@ inline void difference(joint_kind k, const double* q0, const double* q1, double*
   switch (k) {
     case joint_kind::revolute:
     case joint_kind::prismatic: out[0] = q1[0] - q0[0]; return;
+    case joint_kind::revolute_unbounded: out[0] = std::atan2(q0[0] * q1[1] - q0[1] * q1[0], q0[0] * q1[0] + q0[1] * q1[1]); return;
     case joint_kind::spherical: {
       const double c[4] = {-q0[0], -q0[1], -q0[2], q0[3]};
       double r[4];
@@ -233,7 +241,7 @@ enum class jac_kind { integrate_dq, integrate_dv, difference_dq_start, differenc
 //   d (q1 (-) q0) / dq1 = Jr^-1(q1 (-) q0) ,  d (q1 (-) q0) / dq0 = -Jl^-1(q1 (-) q0)
 inline void jacobian(joint_kind k, jac_kind what, const double* a, const double* b, double* out) {
   const int nv = nv_of(k);
-  if (k == joint_kind::revolute || k == joint_kind::prismatic) { out[0] = what == jac_kind::difference_dq_start ? -1.0 : 1.0; return; }
+  if (nv == 1) { out[0] = what == jac_kind::difference_dq_start ? -1.0 : 1.0; return; }  // commutative groups
   double v[6], xi[6], mxi[6];
   if (what == jac_kind::integrate_dq || what == jac_kind::integrate_dv) for (int i = 0; i < nv; ++i) v[i] = b[i];
   else difference(k, a, b, v);
@@ -285,6 +293,7 @@ class config_space_t {
       switch (k) {
         case joint_kind::revolute:
         case joint_kind::prismatic: q[0] = 2 * r[0] - 1; break;
+        case joint_kind::revolute_unbounded: { const double th = 6.283185307179586 * r[0]; q[0] = std::cos(th); q[1] = std::sin(th); break; }
         case joint_kind::spherical: rot(r, q); break;
         case joint_kind::free_flyer: for (int i = 0; i < 3; ++i) q[i] = 2 * r[i] - 1; rot(r + 3, q + 3); break;
         case joint_kind::planar: { const double th = 6.283185307179586 * r[2]; q[0] = 2 * r[0] - 1; q[1] = 2 * r[1] - 1; q[2] = std::cos(th); q[3] = std::sin(th); break; }

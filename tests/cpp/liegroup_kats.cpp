@@ -119,11 +119,20 @@ int main() {
     CHECK(maxdiff(v, std::vector<double>(nv, 0.0)) == 0.0);
   }
   // Jacobians per joint kind and for the composite model; small tangents exercise the series branches
-  for (joint_kind k : {joint_kind::revolute, joint_kind::prismatic, joint_kind::spherical, joint_kind::planar, joint_kind::free_flyer}) {
+  for (joint_kind k : {joint_kind::revolute, joint_kind::prismatic, joint_kind::revolute_unbounded, joint_kind::spherical, joint_kind::planar, joint_kind::free_flyer}) {
     config_space_t one({k});
     for (int rep = 0; rep < 5; ++rep) { check_jacobians(one, 1.0, 2e-8); check_jacobians(one, 1e-4, 2e-8); check_jacobians(one, 1e-9, 2e-8); }
   }
   for (int rep = 0; rep < 5; ++rep) check_jacobians(model, 0.7, 2e-8);
+  {  // a chain as Pinocchio's URDF parser builds it when a joint is `continuous`: round trip through the (cos, sin) parametrisation
+    config_space_t arm({joint_kind::revolute, joint_kind::revolute_unbounded, joint_kind::prismatic});
+    CHECK(arm.configuration_dim() == 4 && arm.tangent_dim() == 3);
+    std::vector<double> q0 = random_q(arm), q1(4), v = {0.3, 2.5, -0.7}, d(3);
+    arm.integrate(q1.data(), q0.data(), v.data());
+    arm.difference(d.data(), q0.data(), q1.data());
+    CHECK(maxdiff(v, d) < 1e-14);
+    CHECK(std::fabs(q1[1] * q1[1] + q1[2] * q1[2] - 1.0) < 1e-15);
+  }
   std::printf("%d failures\n", failures);
   return failures != 0;
 }
